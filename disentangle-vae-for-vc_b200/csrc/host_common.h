@@ -1,0 +1,44 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, dtype tags, TMA map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+namespace dvae {
+
+enum DType : int { kBF16 = 0, kTF32 = 1 };  // activation storage: bf16 (kind::f16 MMA) or fp32 (kind::tf32 MMA)
+
+void set_last_error(const std::string& msg);
+
+#define DVAE_CHECK_CUDA(expr)                                                                         \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      ::dvae::set_last_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +     \
+                             __FILE__ + ":" + std::to_string(__LINE__));                              \
+      return 2;                                                                                       \
+    }                                                                                                 \
+  } while (0)
+
+#define DVAE_REQUIRE(cond, msg)                                                                       \
+  do {                                                                                                \
+    if (!(cond)) {                                                                                    \
+      ::dvae::set_last_error(std::string("invalid argument: ") + (msg) + " [" #cond "] at " +         \
+                             __FILE__ + ":" + std::to_string(__LINE__));                              \
+      return 1;                                                                                       \
+    }                                                                                                 \
+  } while (0)
+
+// rank-3 tiled tensor map, 128-byte swizzle, zero fill out of bounds.  dims/box are in elements
+// (innermost first); strides in bytes for dims 1 and 2.
+int encode_map3(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
+
+inline int ceil_div(long a, long b) { return static_cast<int>((a + b - 1) / b); }
+
+int num_sms();
+
+}  // namespace dvae

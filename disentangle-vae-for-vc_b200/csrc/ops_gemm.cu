@@ -1,0 +1,408 @@
+// C-ABI launchers for every dense contraction on the Disentangled-VAE hot path.  All of them drive the
+// single tcgen05 kernel in tc_gemm.cuh; what changes is the tensor-map geometry, the operand majors and
+// the epilogue:
+//
+//   Linear   fwd : out[M,N]  = x[M,K] . w[N,K]^T  (+bias, relu)          A K-major , B K-major
+//   Linear   dgrad: dx[M,K]  = dy[M,N] . w[N,K]                           A K-major , B MN-major
+//   Linear   wgrad: dw[N,K] += dy[M,N]^T . x[M,K]                         A MN-major, B MN-major, split-K
+//   Conv1d-5 fwd / dgrad / wgrad on channels-last [R,T,C] (implicit GEMM, taps = shifted TMA boxes)
+//   LSTM     fwd step  : gates = xproj_t + h_{t-1} . W_hh^T  -> fused cell epilogue
+//   LSTM     bwd step  : dh_rec = da_{t+1} . W_hh             -> fused cell-backward epilogue
+//
+// Reference call sites (model/disentangled_vae.py): Conv1d :154-160,:178-189,:54-78; LSTM :163,:172,:193;
+// Linear :165-171,:194.
+#include <cuda_bf16.h>
+
+#include "host_common.h"
+#include "tc_gemm.cuh"
+
+namespace dvae {
+
+template <int BN>
+struct Stages {
+  static constexpr int value = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+};
+
+template <int BN, bool A_MN, bool B_MN, int EB, class Epi>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const OperandWalk& wa, const OperandWalk& wb,
+                       const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream) {
+  constexpr int ST = Stages<BN>::value;
+  auto kern = tc_gemm_kernel<BN, ST, A_MN, B_MN, EB, Epi>;
+  constexpr int smem = gemm_smem_bytes<BN, ST>();
+  static bool configured = false;  // one flag per template instantiation
+  if (!configured) {
+    DVAE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
+  kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, wa, wb, shp, ep);
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static OperandWalk zero_walk() {
+  OperandWalk w;
+  for (int d = 0; d < 3; ++d) w.base[d] = w.per_j[d] = w.per_tap[d] = w.per_box[d] = w.per_tile[d] = w.per_z[d] = 0;
+  return w;
+}
+
+static int pick_bn(int N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }
+
+// ------------------------------------------------------------------------------------ Linear
+template <typename AT>
+static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, AT* out, float* out_f32, long ldo, int M,
+                        int N, int K, int relu, int bn_override, cudaStream_t st) {
+  constexpr int EB = sizeof(AT);
+  constexpr int BK = 128 / EB;
+  CUtensorMap ta, tb;
+  const int BN = bn_override ? bn_override : pick_bn(N);
+  if (int e = encode_map3(&ta, x, EB, K, M, 1, ldx * EB, (uint64_t)M * ldx * EB, BK, 128, 1)) return e;
+  if (int e = encode_map3(&tb, w, EB, K, N, 1, (uint64_t)K * EB, (uint64_t)N * K * EB, BK, BN, 1)) return e;
+  OperandWalk wa = zero_walk(), wb = zero_walk();
+  wa.per_j[0] = BK; wa.per_tile[1] = 128;
+  wb.per_j[0] = BK; wb.per_tile[1] = BN;
+  GemmShape shp{M, N, ceil_div(K, BK), ceil_div(K, BK), 1};
+  typename EpiStore<AT>::Params ep{out, out_f32, bias, nullptr, ldo, 0, relu};
+  dim3 grid(ceil_div(M, 128), ceil_div(N, BN), 1);
+  switch (BN) {
+    case 64: return launch_gemm<64, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    case 128: return launch_gemm<128, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    default: return launch_gemm<256, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+  }
+}
+
+template <typename AT>
+static int linear_dgrad_t(const AT* dy, long lddy, const AT* w, AT* dx, float* dx_f32, const AT* relu_mask, long ldx,
+                          int M, int N, int K, int bn_override, cudaStream_t st) {
+  // dx[M,K] = dy[M,N] . w[N,K]   (GEMM output dim = K, reduction = N)
+  constexpr int EB = sizeof(AT);
+  constexpr int BK = 128 / EB;
+  CUtensorMap ta, tb;
+  const int BN = bn_override ? bn_override : pick_bn(K);
+  if (int e = encode_map3(&ta, dy, EB, N, M, 1, lddy * EB, (uint64_t)M * lddy * EB, BK, 128, 1)) return e;
+  if (int e = encode_map3(&tb, w, EB, K, N, 1, (uint64_t)K * EB, (uint64_t)N * K * EB, BK, BK, 1)) return e;
+  OperandWalk wa = zero_walk(), wb = zero_walk();
+  wa.per_j[0] = BK; wa.per_tile[1] = 128;
+  wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN;
+  GemmShape shp{M, K, ceil_div(N, BK), ceil_div(N, BK), 1};
+  typename EpiStore<AT>::Params ep{dx, dx_f32, nullptr, relu_mask, ldx, 0, 0};
+  dim3 grid(ceil_div(M, 128), ceil_div(K, BN), 1);
+  switch (BN) {
+    case 64: return launch_gemm<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    case 128: return launch_gemm<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    default: return launch_gemm<256, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+  }
+}
+
+static int pick_splits(int tiles, int num_kb) {
+  // fill ~2 CTAs per SM, never fewer than 4 k-blocks per split
+  int want = ceil_div(2 * num_sms(), tiles > 0 ? tiles : 1);
+  int cap = num_kb / 4 > 0 ? num_kb / 4 : 1;
+  int s = want < cap ? want : cap;
+  return s < 1 ? 1 : s;
+}
+
+template <typename AT>
+static int linear_wgrad_t(const AT* dy, long lddy, const AT* x, long ldx, float* dw, long lddw, int M, int N, int K,
+                          cudaStream_t st) {
+  // dw[N,K] += dy[M,N]^T . x[M,K]   (reduction over the M rows; both operands MN-major)
+  constexpr int EB = sizeof(AT);
+  constexpr int BK = 128 / EB;
+  CUtensorMap ta, tb;
+  const int BN = K <= 64 ? 64 : 128;
+  if (int e = encode_map3(&ta, dy, EB, N, M, 1, lddy * EB, (uint64_t)M * lddy * EB, BK, BK, 1)) return e;
+  if (int e = encode_map3(&tb, x, EB, K, M, 1, ldx * EB, (uint64_t)M * ldx * EB, BK, BK, 1)) return e;
+  OperandWalk wa = zero_walk(), wb = zero_walk();
+  wa.per_j[1] = BK; wa.per_box[0] = BK; wa.per_tile[0] = 128;
+  wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN;
+  const int num_kb = ceil_div(M, BK);
+  const int tiles = ceil_div(N, 128) * ceil_div(K, BN);
+  GemmShape shp{N, K, num_kb, num_kb, pick_splits(tiles, num_kb)};
+  EpiAtomic::Params ep{dw, lddw, 0};
+  dim3 grid(ceil_div(N, 128), ceil_div(K, BN), shp.splits);
+  if (BN == 64) return launch_gemm<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
+  return launch_gemm<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
+}
+
+// ------------------------------------------------------------------------------------ Conv1d k=5 pad=2
+// activations channels-last [R, T, C]; weights re-laid as w_k[Cout][5][Cin] (prep_conv_weight).
+static bool conv_tile_geometry(int T, int* box_t, int* box_r, int* tiles_per_seq) {
+  if (T <= 128) {
+    if (128 % T) return false;
+    *box_t = T; *box_r = 128 / T; *tiles_per_seq = 0;  // 0: several sequences per tile
+  } else {
+    if (T % 128) return false;
+    *box_t = 128; *box_r = 1; *tiles_per_seq = T / 128;
+  }
+  return true;
+}
+
+template <typename AT>
+static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, float* y_f32, int R, int T, int Cin, int Cout,
+                       bool dgrad, cudaStream_t st) {
+  // fwd :  y[r,t,co]  = sum_{k,ci} x[r,t+k-2,ci] wk[co][k][ci]                     (B K-major)
+  // dgrad: dx[r,t,ci] = sum_{k',co} dy[r,t+k'-2,co] wk[co][4-k'][ci]               (B MN-major)
+  // In dgrad mode the caller passes x:=dy, y:=dx, and (Cin, Cout) are still the forward layer's.
+  constexpr int EB = sizeof(AT);
+  constexpr int BK = 128 / EB;
+  int box_t, box_r, tps;
+  DVAE_REQUIRE(conv_tile_geometry(T, &box_t, &box_r, &tps), "T must divide 128 or be a multiple of 128");
+  DVAE_REQUIRE(tps == 0, "T > 128 not wired for the conv path (model is locked to T = 64)");
+  const int Ca = dgrad ? Cout : Cin;  // channels of the A operand (reduction)
+  const int Cn = dgrad ? Cin : Cout;  // output channels of this GEMM
+  CUtensorMap ta, tb;
+  if (int e = encode_map3(&ta, x, EB, Ca, T, R, (uint64_t)Ca * EB, (uint64_t)T * Ca * EB, BK, box_t, box_r)) return e;
+  OperandWalk wa = zero_walk(), wb = zero_walk();
+  wa.base[1] = -2; wa.per_j[0] = BK; wa.per_tap[1] = 1; wa.per_tile[2] = box_r;
+  const int BN = pick_bn(Cn);
+  if (!dgrad) {
+    if (int e = encode_map3(&tb, wk, EB, Cin, 5, Cout, (uint64_t)Cin * EB, (uint64_t)5 * Cin * EB, BK, 1, BN)) return e;
+    wb.per_j[0] = BK; wb.per_tap[1] = 1; wb.per_tile[2] = BN;
+  } else {
+    if (int e = encode_map3(&tb, wk, EB, Cin, 5, Cout, (uint64_t)Cin * EB, (uint64_t)5 * Cin * EB, BK, 1, BK)) return e;
+    wb.base[1] = 4; wb.per_tap[1] = -1; wb.per_j[2] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN;
+  }
+  const int kpt = ceil_div(Ca, BK);
+  GemmShape shp{R * T, Cn, 5 * kpt, kpt, 1};
+  typename EpiStore<AT>::Params ep{y, y_f32, bias, nullptr, (long)Cn, 0, 0};
+  dim3 grid(ceil_div((long)R * T, 128), ceil_div(Cn, BN), 1);
+  if (!dgrad) {
+    switch (BN) {
+      case 64: return launch_gemm<64, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 128: return launch_gemm<128, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      default: return launch_gemm<256, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    }
+  }
+  switch (BN) {
+    case 64: return launch_gemm<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    case 128: return launch_gemm<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    default: return launch_gemm<256, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+  }
+}
+
+template <typename AT>
+static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, int Cin, int Cout, cudaStream_t st) {
+  // dwk[co][k][ci] += sum_{r,t} dy[r,t,co] x[r,t+k-2,ci];  one GEMM batch (blockIdx.z) per tap, split-K over sequences
+  constexpr int EB = sizeof(AT);
+  constexpr int BK = 128 / EB;
+  DVAE_REQUIRE(T % BK == 0, "T must be a multiple of the k-block");
+  CUtensorMap ta, tb;
+  if (int e = encode_map3(&ta, dy, EB, Cout, T, R, (uint64_t)Cout * EB, (uint64_t)T * Cout * EB, BK, BK, 1)) return e;
+  if (int e = encode_map3(&tb, x, EB, Cin, T, R, (uint64_t)Cin * EB, (uint64_t)T * Cin * EB, BK, BK, 1)) return e;
+  const int BN = Cin <= 64 ? 64 : 128;
+  OperandWalk wa = zero_walk(), wb = zero_walk();
+  // k-block kb -> (sequence r = kb / (T/BK)  [the "tap" slot of the walk], time block j = kb % (T/BK))
+  wa.per_j[1] = BK; wa.per_tap[2] = 1; wa.per_box[0] = BK; wa.per_tile[0] = 128;
+  wb.base[1] = -2; wb.per_z[1] = 1; wb.per_j[1] = BK; wb.per_tap[2] = 1; wb.per_box[0] = BK; wb.per_tile[0] = BN;
+  const int kpt = T / BK;
+  const int num_kb = R * kpt;
+  const int tiles = ceil_div(Cout, 128) * ceil_div(Cin, BN) * 5;
+  GemmShape shp{Cout, Cin, num_kb, kpt, pick_splits(tiles, num_kb)};
+  EpiAtomic::Params ep{dwk, (long)5 * Cin, (long)Cin};
+  dim3 grid(ceil_div(Cout, 128), ceil_div(Cin, BN), 5 * shp.splits);
+  if (BN == 64) return launch_gemm<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
+  return launch_gemm<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
+}
+
+// ------------------------------------------------------------------------------------ LSTM
+// Layouts (rows = sequences, D = directions):
+//   xg    [rows, T, D*4H]  in: x-projection + biases, gate-interleaved per direction (tile of FWD_BN columns =
+//                          [i|f|g|o] x FWD_BN/4 units); out: activated gates (same layout, overwritten in place)
+//   h_all [rows, T, D*H]   layer output, also the A operand of the next step (3-D TMA over {D*H, T, rows})
+//   c_all [rows, T, D*H]   fp32 cell state
+//   whh_p [D][4H][H]       recurrent weights, rows gate-interleaved like xg columns
+template <int H>
+struct LstmFwdBN {
+  static constexpr int value = (4 * H >= 512) ? 128 : 256;  // H=64 -> one 256-wide tile holds all 4 gates of 64 units
+};
+static int lstm_fwd_bn(int H) { return H == 64 ? 256 : 128; }
+
+template <typename AT>
+static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows, int T, int H, int D, cudaStream_t st) {
+  constexpr int EB = sizeof(AT);
+  constexpr int BK = 128 / EB;
+  DVAE_REQUIRE(H % BK == 0 && (D == 1 || D == 2), "H must be a multiple of the k-block; D in {1,2}");
+  const int BN = lstm_fwd_bn(H);
+  DVAE_REQUIRE((4 * H) % BN == 0, "4H must be a multiple of the gate tile");
+  CUtensorMap ta, tb;
+  if (int e = encode_map3(&ta, h_all, EB, (uint64_t)D * H, T, rows, (uint64_t)D * H * EB, (uint64_t)T * D * H * EB, BK, 1, 128))
+    return e;
+  if (int e = encode_map3(&tb, whh_p, EB, H, 4 * H, D, (uint64_t)H * EB, (uint64_t)4 * H * H * EB, BK, BN, 1)) return e;
+  const long ldx = (long)T * D * 4 * H, ldc = (long)T * D * H;
+  for (int s = 0; s < T; ++s) {
+    const int tf = s, tr = T - 1 - s;
+    OperandWalk wa = zero_walk(), wb = zero_walk();
+    wa.base[1] = tf - 1; wa.per_j[0] = BK; wa.per_tile[2] = 128; wa.per_z[0] = H; wa.per_z[1] = (tr + 1) - (tf - 1);
+    wb.per_j[0] = BK; wb.per_tile[1] = BN; wb.per_z[2] = 1;
+    GemmShape shp{rows, 4 * H, s == 0 ? 0 : H / BK, H / BK, 1};
+    typename EpiLstmFwd<AT>::Params ep;
+    ep.xproj = xg + (long)tf * D * 4 * H;
+    ep.gates = xg + (long)tf * D * 4 * H;
+    ep.c_prev = s == 0 ? nullptr : c_all + (long)(tf - 1) * D * H;
+    ep.c_out = c_all + (long)tf * D * H;
+    ep.h_out = h_all + (long)tf * D * H;
+    ep.ldx = ldx; ep.ldc = ldc; ep.ldh = ldc;
+    ep.z_x = 4 * H + (long)(tr - tf) * D * 4 * H;
+    ep.z_c_prev = H + (long)((tr + 1) - (tf - 1)) * D * H;
+    ep.z_c_out = H + (long)(tr - tf) * D * H;
+    ep.z_h = H + (long)(tr - tf) * D * H;
+    dim3 grid(ceil_div(rows, 128), 4 * H / BN, D);
+    int e = (BN == 256) ? launch_gemm<256, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                        : launch_gemm<128, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    if (e) return e;
+  }
+  return 0;
+}
+
+// Backward through time.  dh_all [rows,T,D*H] is the gradient wrt the layer output; produces da_all
+// [rows,T,D*4H] (pre-activation gate gradients, natural torch order i,f,g,o per direction).  whh_n is the
+// natural-order copy [D][4H][H].  dc_ws: fp32 [D, rows, H] scratch.
+template <typename AT>
+static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, const AT* whh_n, AT* da_all, float* dc_ws,
+                      int rows, int T, int H, int D, cudaStream_t st) {
+  constexpr int EB = sizeof(AT);
+  constexpr int BK = 128 / EB;
+  constexpr int BN = 64;
+  DVAE_REQUIRE(H % 64 == 0 && (D == 1 || D == 2), "H must be a multiple of 64; D in {1,2}");
+  CUtensorMap ta, tb;
+  if (int e = encode_map3(&ta, da_all, EB, (uint64_t)D * 4 * H, T, rows, (uint64_t)D * 4 * H * EB,
+                          (uint64_t)T * D * 4 * H * EB, BK, 1, 128))
+    return e;
+  if (int e = encode_map3(&tb, whh_n, EB, H, 4 * H, D, (uint64_t)H * EB, (uint64_t)4 * H * H * EB, BK, BK, 1)) return e;
+  const long ldh = (long)T * D * H, ldx = (long)T * D * 4 * H;
+  for (int s = 0; s < T; ++s) {
+    const int tf = T - 1 - s, tr = s;  // forward direction walks time backwards, reverse direction forwards
+    OperandWalk wa = zero_walk(), wb = zero_walk();
+    wa.base[1] = tf + 1; wa.per_j[0] = BK; wa.per_tile[2] = 128; wa.per_z[0] = 4 * H; wa.per_z[1] = (tr - 1) - (tf + 1);
+    wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN; wb.per_z[2] = 1;
+    GemmShape shp{rows, H, s == 0 ? 0 : 4 * H / BK, 4 * H / BK, 1};
+    typename EpiLstmBwd<AT>::Params ep;
+    ep.dh_out = dh_all + (long)tf * D * H;
+    ep.gates = gates + (long)tf * D * 4 * H;
+    ep.c_t = c_all + (long)tf * D * H;
+    ep.c_prev = (s == T - 1) ? nullptr : c_all + (long)(tf - 1) * D * H;
+    ep.dc = dc_ws;
+    ep.da = da_all + (long)tf * D * 4 * H;
+    ep.ldh = ldh; ep.ldx = ldx; ep.ldc = ldh; ep.lda = ldx;
+    ep.z_h = H + (long)(tr - tf) * D * H;
+    ep.z_x = 4 * H + (long)(tr - tf) * D * 4 * H;
+    ep.z_c = H + (long)(tr - tf) * D * H;
+    ep.z_c_prev = H + (long)((tr + 1) - (tf - 1)) * D * H;
+    ep.z_dc = (long)rows * H;
+    ep.z_a = 4 * H + (long)(tr - tf) * D * 4 * H;
+    ep.H = H; ep.fwd_units = lstm_fwd_bn(H) / 4; ep.dc_zero = (s == 0);
+    dim3 grid(ceil_div(rows, 128), H / BN, D);
+    if (int e = launch_gemm<BN, false, true, EB, EpiLstmBwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)) return e;
+  }
+  return 0;
+}
+
+// dW_hh[d][4H][H] += sum_{r,t} da[r,t,d,:]^T h_prev[r,t,d,:]  with h_prev = h[t-1] (forward dir) / h[t+1] (reverse)
+template <typename AT>
+static int lstm_wgrad_hh_t(const AT* da_all, const AT* h_all, float* dwhh, int rows, int T, int H, int D, cudaStream_t st) {
+  constexpr int EB = sizeof(AT);
+  constexpr int BK = 128 / EB;
+  DVAE_REQUIRE(T % BK == 0, "T must be a multiple of the k-block");
+  CUtensorMap ta, tb;
+  if (int e = encode_map3(&ta, da_all, EB, (uint64_t)D * 4 * H, T, rows, (uint64_t)D * 4 * H * EB,
+                          (uint64_t)T * D * 4 * H * EB, BK, BK, 1))
+    return e;
+  if (int e = encode_map3(&tb, h_all, EB, (uint64_t)D * H, T, rows, (uint64_t)D * H * EB, (uint64_t)T * D * H * EB, BK, BK, 1))
+    return e;
+  const int BN = H <= 64 ? 64 : 128;
+  OperandWalk wa = zero_walk(), wb = zero_walk();
+  wa.per_j[1] = BK; wa.per_tap[2] = 1; wa.per_box[0] = BK; wa.per_tile[0] = 128; wa.per_z[0] = 4 * H;
+  wb.base[1] = -1; wb.per_z[1] = 2; wb.per_z[0] = H; wb.per_j[1] = BK; wb.per_tap[2] = 1; wb.per_box[0] = BK;
+  wb.per_tile[0] = BN;
+  const int kpt = T / BK, num_kb = rows * kpt;
+  const int tiles = ceil_div(4 * H, 128) * ceil_div(H, BN) * D;
+  GemmShape shp{4 * H, H, num_kb, kpt, pick_splits(tiles, num_kb)};
+  EpiAtomic::Params ep{dwhh, (long)H, (long)4 * H * H};
+  dim3 grid(ceil_div(4 * H, 128), ceil_div(H, BN), D * shp.splits);
+  if (BN == 64) return launch_gemm<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
+  return launch_gemm<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
+}
+
+}  // namespace dvae
+
+using namespace dvae;
+using bf16 = __nv_bfloat16;
+
+#define DISPATCH_DTYPE(dtype, CALL_BF16, CALL_F32)                      \
+  do {                                                                  \
+    if ((dtype) == kBF16) return CALL_BF16;                             \
+    if ((dtype) == kTF32) return CALL_F32;                              \
+    set_last_error("unknown dtype tag");                                \
+    return 1;                                                           \
+  } while (0)
+
+extern "C" {
+
+int dvae_linear_fwd(int dtype, const void* x, long ldx, const void* w, const float* bias, void* out, float* out_f32,
+                    long ldo, int M, int N, int K, int relu, int block_n, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype,
+                 linear_fwd_t<bf16>((const bf16*)x, ldx, (const bf16*)w, bias, (bf16*)out, out_f32, ldo, M, N, K, relu, block_n, st),
+                 linear_fwd_t<float>((const float*)x, ldx, (const float*)w, bias, (float*)out, out_f32, ldo, M, N, K, relu, block_n, st));
+}
+
+int dvae_linear_dgrad(int dtype, const void* dy, long lddy, const void* w, void* dx, float* dx_f32, const void* relu_mask,
+                      long ldx, int M, int N, int K, int block_n, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype,
+                 linear_dgrad_t<bf16>((const bf16*)dy, lddy, (const bf16*)w, (bf16*)dx, dx_f32, (const bf16*)relu_mask, ldx, M, N, K, block_n, st),
+                 linear_dgrad_t<float>((const float*)dy, lddy, (const float*)w, (float*)dx, dx_f32, (const float*)relu_mask, ldx, M, N, K, block_n, st));
+}
+
+int dvae_linear_wgrad(int dtype, const void* dy, long lddy, const void* x, long ldx, float* dw, long lddw, int M, int N,
+                      int K, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype, linear_wgrad_t<bf16>((const bf16*)dy, lddy, (const bf16*)x, ldx, dw, lddw, M, N, K, st),
+                 linear_wgrad_t<float>((const float*)dy, lddy, (const float*)x, ldx, dw, lddw, M, N, K, st));
+}
+
+int dvae_conv5_fwd(int dtype, const void* x, const void* wk, const float* bias, void* y, float* y_f32, int R, int T, int Cin,
+                   int Cout, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype, conv5_fwd_t<bf16>((const bf16*)x, (const bf16*)wk, bias, (bf16*)y, y_f32, R, T, Cin, Cout, false, st),
+                 conv5_fwd_t<float>((const float*)x, (const float*)wk, bias, (float*)y, y_f32, R, T, Cin, Cout, false, st));
+}
+
+int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,
+                     void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype, conv5_fwd_t<bf16>((const bf16*)dy, (const bf16*)wk, nullptr, (bf16*)dx, dx_f32, R, T, Cin, Cout, true, st),
+                 conv5_fwd_t<float>((const float*)dy, (const float*)wk, nullptr, (float*)dx, dx_f32, R, T, Cin, Cout, true, st));
+}
+
+int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R, int T, int Cin, int Cout, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype, conv5_wgrad_t<bf16>((const bf16*)dy, (const bf16*)x, dwk, R, T, Cin, Cout, st),
+                 conv5_wgrad_t<float>((const float*)dy, (const float*)x, dwk, R, T, Cin, Cout, st));
+}
+
+int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_all, int rows, int T, int H, int D,
+                  void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype, lstm_fwd_t<bf16>((bf16*)xg, (const bf16*)whh_p, (bf16*)h_all, c_all, rows, T, H, D, st),
+                 lstm_fwd_t<float>((float*)xg, (const float*)whh_p, (float*)h_all, c_all, rows, T, H, D, st));
+}
+
+int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all,
+                  float* dc_ws, int rows, int T, int H, int D, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype,
+                 lstm_bwd_t<bf16>((const bf16*)dh_all, (const bf16*)gates, c_all, (const bf16*)whh_n, (bf16*)da_all, dc_ws, rows, T, H, D, st),
+                 lstm_bwd_t<float>((const float*)dh_all, (const float*)gates, c_all, (const float*)whh_n, (float*)da_all, dc_ws, rows, T, H, D, st));
+}
+
+int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* dwhh, int rows, int T, int H, int D,
+                       void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype, lstm_wgrad_hh_t<bf16>((const bf16*)da_all, (const bf16*)h_all, dwhh, rows, T, H, D, st),
+                 lstm_wgrad_hh_t<float>((const float*)da_all, (const float*)h_all, dwhh, rows, T, H, D, st));
+}
+
+int dvae_lstm_gate_tile(int H) { return lstm_fwd_bn(H); }
+
+}  // extern "C"

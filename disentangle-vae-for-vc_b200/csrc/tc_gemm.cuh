@@ -1,0 +1,510 @@
+// Warp-specialised tcgen05 GEMM core for sm_100a.
+//
+//   D[128 x BLOCK_N] (fp32, TMEM)  =  sum over k-blocks  A_tile * B_tile^T
+//
+// * operands are fetched by TMA (3-D tiled tensor maps, 128-byte swizzle) into a STAGES-deep shared
+//   memory ring; one elected thread of warp 0 produces, one elected thread of warp 1 issues
+//   tcgen05.mma (kind::f16 for bf16, kind::tf32 for fp32 storage), warps 2..5 drain the TMEM
+//   accumulator through an epilogue functor.
+// * every operand may be K-major (reduction dim contiguous) or MN-major (output dim contiguous);
+//   MN-major tiles arrive as several 64-element-wide boxes.  This is what lets forward, dgrad and
+//   wgrad of Linear / Conv1d(k=5) / LSTM all run on the same kernel without transposed copies.
+// * the TMA box coordinates of k-block `kb` are an affine function of (j, tap, box, tile, z) described
+//   by OperandWalk.  Conv1d is an implicit GEMM: the 5 taps are 5 shifted reads of the same
+//   channels-last [R, T, C] tensor; rows that fall outside a sequence are zero-filled by TMA.
+// * split-K: gridDim.z = batches * splits, epilogue accumulates with red.global.add.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace dvae {
+
+constexpr int kBlockM = 128;
+constexpr int kGemmThreads = 192;
+constexpr int kSwizzleRow = 128;  // bytes per swizzle-128B row == BLOCK_K * ELEM_BYTES
+
+struct OperandWalk {
+  int base[3];
+  int per_j[3];     // k-block index inside a tap
+  int per_tap[3];   // conv tap index
+  int per_box[3];   // MN-major operands: successive 128-byte-wide boxes
+  int per_tile[3];  // blockIdx.x for A, blockIdx.y for B
+  int per_z[3];     // batch index (blockIdx.z / splits)
+};
+
+struct GemmShape {
+  int M, N;        // logical output extent (epilogue masks against it)
+  int num_kb;      // k-blocks per output tile (before split-K)
+  int kb_per_tap;  // conv: k-blocks per tap; otherwise == num_kb
+  int splits;      // split-K factor
+};
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  // sm_100 shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+  // version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
+         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int ELEM_BYTES, int BLOCK_N, bool A_MN, bool B_MN>
+__host__ __device__ constexpr uint32_t instr_desc() {
+  // c_format F32 [4,6) | a_format [7,10) | b_format [10,13) | a_major 15 | b_major 16 | N>>3 [17,23) | M>>4 [24,29)
+  const uint32_t fmt = (ELEM_BYTES == 2) ? 1u : 2u;  // BF16 : TF32
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+         (static_cast<uint32_t>(BLOCK_N >> 3) << 17) | (static_cast<uint32_t>(kBlockM >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES>
+constexpr int gemm_smem_bytes() {
+  return STAGES * (kBlockM * kSwizzleRow + BLOCK_N * kSwizzleRow) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi>
+__global__ void __launch_bounds__(kGemmThreads)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const OperandWalk wa, const OperandWalk wb, const GemmShape shp, const typename Epi::Params ep) {
+  constexpr int BLOCK_K = kSwizzleRow / ELEM_BYTES;  // 64 bf16 / 32 tf32
+  constexpr int UMMA_K = 32 / ELEM_BYTES;            // 16 / 8
+  constexpr int STAGE_A = kBlockM * kSwizzleRow;
+  constexpr int STAGE_B = BLOCK_N * kSwizzleRow;
+  constexpr int A_BOXES = A_MN ? (kBlockM * ELEM_BYTES / kSwizzleRow) : 1;
+  constexpr int B_BOXES = B_MN ? (BLOCK_N * ELEM_BYTES / kSwizzleRow) : 1;
+  constexpr int MN_BOX_BYTES = BLOCK_K * kSwizzleRow;  // one MN-major box: BLOCK_K rows of 128 B
+  constexpr int A_BOX_BYTES = A_MN ? MN_BOX_BYTES : STAGE_A;
+  constexpr int B_BOX_BYTES = B_MN ? MN_BOX_BYTES : STAGE_B;
+  constexpr uint32_t ADV_A = (A_MN ? UMMA_K * kSwizzleRow : 32) >> 4;  // descriptor advance per MMA (16 B units)
+  constexpr uint32_t ADV_B = (B_MN ? UMMA_K * kSwizzleRow : 32) >> 4;
+  constexpr uint32_t IDESC = instr_desc<ELEM_BYTES, BLOCK_N, A_MN, B_MN>();
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "TMEM allocation must be a power of two");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t smem_base = raw_addr + pad;
+  const uint32_t bar_base = smem_base + STAGES * (STAGE_A + STAGE_B);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * (STAGE_A + STAGE_B) + 8 * (2 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const int zb = blockIdx.z / shp.splits;
+  const int split = blockIdx.z - zb * shp.splits;
+  // split-K range of this CTA
+  const int kb_chunk = (shp.num_kb + shp.splits - 1) / shp.splits;
+  const int kb_begin = split * kb_chunk;
+  const int kb_end = min(shp.num_kb, kb_begin + kb_chunk);
+  const int num_local = max(0, kb_end - kb_begin);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), BLOCK_N);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < num_local; ++it) {
+        const int kb = kb_begin + it;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+        ptx::mbar_expect_tx(full_bar(s), STAGE_A + STAGE_B);
+        const int tap = kb / shp.kb_per_tap;
+        const int j = kb - tap * shp.kb_per_tap;
+        const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
+        const uint32_t sb = sa + STAGE_A;
+#pragma unroll
+        for (int i = 0; i < A_BOXES; ++i) {
+          int c[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            c[d] = wa.base[d] + j * wa.per_j[d] + tap * wa.per_tap[d] + i * wa.per_box[d] + tile_m * wa.per_tile[d] +
+                   zb * wa.per_z[d];
+          ptx::tma_load_3d(sa + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
+        }
+#pragma unroll
+        for (int i = 0; i < B_BOXES; ++i) {
+          int c[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + i * wb.per_box[d] + tile_n * wb.per_tile[d] +
+                   zb * wb.per_z[d];
+          ptx::tma_load_3d(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    for (int it = 0; it < num_local; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      ptx::mbar_wait(full_bar(s), ph);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
+        const uint32_t sb = sa + STAGE_A;
+        const uint64_t adesc = A_MN ? smem_desc(sa, MN_BOX_BYTES, 1024) : smem_desc(sa, 16, 1024);
+        const uint64_t bdesc = B_MN ? smem_desc(sb, MN_BOX_BYTES, 1024) : smem_desc(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          ptx::umma<ELEM_BYTES>(tmem_base, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        ptx::umma_commit(empty_bar(s));  // frees the smem slot once these MMAs retire
+      }
+      __syncwarp();
+    }
+    if (num_local > 0 && lane == 0) ptx::umma_commit(tmem_full_bar);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int m = tile_m * kBlockM + q * 32 + lane;
+    if (num_local > 0) {
+      ptx::mbar_wait(tmem_full_bar, 0);
+      ptx::tc_fence_after();
+    }
+    Epi::template run<BLOCK_N>(ep, tmem_base + (static_cast<uint32_t>(q * 32) << 16), num_local > 0, m,
+                               tile_n * BLOCK_N, zb, shp);
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, BLOCK_N);
+  }
+}
+
+// =====================================================================================
+// Epilogues.  Each receives the TMEM address of its warp's 32-lane slice; thread `lane` owns
+// output row m and reads BLOCK_N fp32 columns in chunks.
+// =====================================================================================
+template <typename T>
+struct Act8;  // pack / unpack 8 consecutive activations
+template <>
+struct Act8<float> {
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <>
+struct Act8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+
+// ---- out = act(acc + bias) -> activation dtype, optionally mirrored in fp32; optional relu-mask multiply
+template <typename OutT>
+struct EpiStore {
+  struct Params {
+    OutT* out;            // may be null
+    float* out_f32;       // may be null
+    const float* bias;    // [N] or null
+    const OutT* mask;     // dgrad of a ReLU layer: zero the result where mask <= 0 (same layout as out); or null
+    long ldo;             // row stride (elements) of out / out_f32 / mask
+    long z_stride;        // batch stride (elements)
+    int relu;
+  };
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, bool has_acc, int m, int n0, int zb,
+                                             const GemmShape& shp) {
+    const bool row_ok = m < shp.M;
+    const long row_off = static_cast<long>(zb) * p.z_stride + static_cast<long>(m) * p.ldo;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      if (n0 + c >= shp.N) break;
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores below
+      float v[32];
+      if (has_acc) {
+        ptx::tmem_ld_x32(taddr + c, v);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+      const int nb = n0 + c;
+      const bool full = (nb + 32 <= shp.N);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (full || nb + i < shp.N) v[i] += __ldg(p.bias + nb + i);
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (row_ok) {
+      const bool vec = full && ((p.ldo & 7) == 0);
+      if (p.mask != nullptr) {
+        const OutT* mk = p.mask + row_off + nb;
+        if (vec) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float mv[8];
+            Act8<OutT>::load(mk + 8 * g, mv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[8 * g + i] = mv[i] > 0.f ? v[8 * g + i] : 0.f;
+          }
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (nb + i < shp.N) v[i] = to_f32(mk[i]) > 0.f ? v[i] : 0.f;
+        }
+      }
+      if (p.out != nullptr) {
+        OutT* o = p.out + row_off + nb;
+        if (vec) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) Act8<OutT>::store(o + 8 * g, v + 8 * g);
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (nb + i < shp.N) o[i] = from_f32<OutT>(v[i]);
+        }
+      }
+      if (p.out_f32 != nullptr) {
+        float* o = p.out_f32 + row_off + nb;
+        if (vec) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) Act8<float>::store(o + 8 * g, v + 8 * g);
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (nb + i < shp.N) o[i] = v[i];
+        }
+      }
+      }  // row_ok
+    }
+  }
+};
+
+// ---- out_f32 += acc  (split-K weight gradients)
+struct EpiAtomic {
+  struct Params {
+    float* out;
+    long ldo;
+    long z_stride;
+  };
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, bool has_acc, int m, int n0, int zb,
+                                             const GemmShape& shp) {
+    if (!has_acc) return;
+    const bool row_ok = m < shp.M;
+    float* row = p.out + static_cast<long>(zb) * p.z_stride + static_cast<long>(m) * p.ldo;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      if (n0 + c >= shp.N) break;
+      __syncwarp();
+      float v[32];
+      ptx::tmem_ld_x32(taddr + c, v);
+      ptx::tmem_ld_wait();
+      const int nb = n0 + c;
+      if (row_ok) {
+        if (nb + 32 <= shp.N && (p.ldo & 3) == 0) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            ptx::red_add_v4(row + nb + 4 * g, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        } else {
+          for (int i = 0; i < 32; ++i)
+            if (nb + i < shp.N) atomicAdd(row + nb + i, v[i]);
+        }
+      }
+    }
+  }
+};
+
+// ---- LSTM cell forward.  The N tile holds [i | f | g | o] pre-activations of BLOCK_N/4 hidden units
+// (gate-interleaved weight rows, see prep_lstm_weights).  a = acc + xproj;  c = s(f) c_prev + s(i) tanh(g);
+// h = s(o) tanh(c).  Saves the activated gates and c for the backward pass.
+template <typename ActT>
+struct EpiLstmFwd {
+  struct Params {
+    const ActT* xproj;   // [rows, ldx] at time t (permuted gate layout), + zb * z_x
+    const float* c_prev; // [rows, ldc] at the previous time step (null on the first step)
+    float* c_out;        // [rows, ldc] at time t
+    ActT* h_out;         // [rows, ldh] at time t (+ zb * z_h: direction offset in the concat output)
+    ActT* gates;         // [rows, ldx] at time t, activated gates (same permuted layout), + zb * z_x
+    long ldx, ldc, ldh;
+    // element offsets applied when zb == 1 (reverse direction of a bidirectional layer: other weights,
+    // other half of the concat output, and a different time index)
+    long z_x, z_c_prev, z_c_out, z_h;
+  };
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, bool has_acc, int m, int n0, int zb,
+                                             const GemmShape& shp) {
+    constexpr int UNITS = BLOCK_N / 4;
+    const bool row_ok = m < shp.M;
+    const int unit0 = n0 / 4;
+    const ActT* xp = p.xproj + zb * p.z_x + static_cast<long>(m) * p.ldx + n0;
+    ActT* gs = p.gates + zb * p.z_x + static_cast<long>(m) * p.ldx + n0;
+    const float* cp = p.c_prev ? p.c_prev + zb * p.z_c_prev + static_cast<long>(m) * p.ldc + unit0 : nullptr;
+    float* co = p.c_out + zb * p.z_c_out + static_cast<long>(m) * p.ldc + unit0;
+    ActT* ho = p.h_out + zb * p.z_h + static_cast<long>(m) * p.ldh + unit0;
+#pragma unroll 1
+    for (int u = 0; u < UNITS; u += 8) {
+      __syncwarp();
+      float a[4][8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (has_acc) ptx::tmem_ld_x8(taddr + g * UNITS + u, a[g]);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[g][i] = 0.f;
+        }
+      }
+      if (has_acc) ptx::tmem_ld_wait();
+      if (row_ok) {
+      float cprev[8];
+      if (cp) Act8<float>::load(cp + u, cprev);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cprev[i] = 0.f;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float x[8];
+        Act8<ActT>::load(xp + g * UNITS + u, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[g][i] += x[i];
+      }
+      float cn[8], hn[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float ig = sigmoid_f(a[0][i]), fg = sigmoid_f(a[1][i]), gg = tanh_f(a[2][i]), og = sigmoid_f(a[3][i]);
+        a[0][i] = ig; a[1][i] = fg; a[2][i] = gg; a[3][i] = og;
+        cn[i] = fg * cprev[i] + ig * gg;
+        hn[i] = og * tanh_f(cn[i]);
+      }
+      Act8<float>::store(co + u, cn);
+      Act8<ActT>::store(ho + u, hn);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) Act8<ActT>::store(gs + g * UNITS + u, a[g]);
+      }  // row_ok
+    }
+  }
+};
+
+// ---- LSTM cell backward for one time step.  acc = dh_rec[m, unit] = da_{t+1} . W_hh (absent on the last
+// step).  dh = dh_out + acc; emits da_t (natural torch gate order i,f,g,o: column g*H + unit) and the new
+// dc carry.
+template <typename ActT>
+struct EpiLstmBwd {
+  struct Params {
+    const ActT* dh_out;  // [rows, ldh] grad wrt this layer's output at time t (+ zb * z_h)
+    const ActT* gates;   // activated gates at time t, forward's permuted layout with FWD_UNITS per tile
+    const float* c_t;    // [rows, ldc] at time t
+    const float* c_prev; // at the previous time step or null
+    float* dc;           // [rows, H] carry, in/out (+ zb * z_dc)
+    ActT* da;            // [rows, lda] at time t, natural gate order (+ zb * z_a)
+    long ldh, ldx, ldc, lda;
+    long z_h, z_x, z_c, z_c_prev, z_dc, z_a;  // element offsets applied when zb == 1 (reverse direction)
+    int H, fwd_units, dc_zero;                // dc_zero: treat incoming carry as zero (first processed step)
+  };
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, bool has_acc, int m, int n0, int zb,
+                                             const GemmShape& shp) {
+    const bool row_ok = m < shp.M;
+    const long r = m;
+    const ActT* dho = p.dh_out + zb * p.z_h + r * p.ldh;
+    const ActT* gs = p.gates + zb * p.z_x + r * p.ldx;
+    const float* ct = p.c_t + zb * p.z_c + r * p.ldc;
+    const float* cp = p.c_prev ? p.c_prev + zb * p.z_c_prev + r * p.ldc : nullptr;
+    float* dcp = p.dc + zb * p.z_dc + r * p.H;
+    ActT* da = p.da + zb * p.z_a + r * p.lda;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 8) {
+      const int u = n0 + c;
+      if (u >= shp.N) break;
+      __syncwarp();
+      float acc[8];
+      if (has_acc) {
+        ptx::tmem_ld_x8(taddr + c, acc);
+        ptx::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      }
+      if (row_ok) {
+      float dh[8], g4[4][8], cc[8], cpv[8], dc[8];
+      Act8<ActT>::load(dho + u, dh);
+      const long gbase = static_cast<long>(u / p.fwd_units) * 4 * p.fwd_units + (u % p.fwd_units);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) Act8<ActT>::load(gs + gbase + g * p.fwd_units, g4[g]);
+      Act8<float>::load(ct + u, cc);
+      if (cp) Act8<float>::load(cp + u, cpv);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cpv[i] = 0.f;
+      }
+      if (p.dc_zero) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dc[i] = 0.f;
+      } else {
+        Act8<float>::load(dcp + u, dc);
+      }
+      float dai[8], daf[8], dag[8], dao[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float ig = g4[0][i], fg = g4[1][i], gg = g4[2][i], og = g4[3][i];
+        const float tc = tanh_f(cc[i]);
+        const float dht = dh[i] + acc[i];
+        const float dct = dc[i] + dht * og * (1.f - tc * tc);
+        dao[i] = dht * tc * og * (1.f - og);
+        dai[i] = dct * gg * ig * (1.f - ig);
+        dag[i] = dct * ig * (1.f - gg * gg);
+        daf[i] = dct * cpv[i] * fg * (1.f - fg);
+        dc[i] = dct * fg;
+      }
+      Act8<float>::store(dcp + u, dc);
+      Act8<ActT>::store(da + 0 * p.H + u, dai);
+      Act8<ActT>::store(da + 1 * p.H + u, daf);
+      Act8<ActT>::store(da + 2 * p.H + u, dag);
+      Act8<ActT>::store(da + 3 * p.H + u, dao);
+      }  // row_ok
+    }
+  }
+};
+
+}  // namespace dvae

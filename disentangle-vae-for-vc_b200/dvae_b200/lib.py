@@ -1,0 +1,88 @@
+"""ctypes binding of libdvae_b200.so (the C-ABI declared in include/dvae_b200.h).
+
+Every entry point takes raw device pointers, sizes and a cudaStream_t and returns an int status
+(0 = ok).  `call()` raises RuntimeError with `dvae_last_error()` on a non-zero status.  The library
+must exist: there is deliberately no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdvae_b200.so")
+
+BF16, TF32 = 0, 1
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+        "(dvae_b200 has no CPU / PyTorch fallback)")
+
+_lib = C.CDLL(LIB_PATH)
+_lib.dvae_last_error.restype = C.c_char_p
+
+_p, _i, _l, _f = C.c_void_p, C.c_int, C.c_long, C.c_float
+
+# name -> argtypes (all return int)
+_SIGNATURES = {
+    "dvae_linear_fwd": [_i, _p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
+    "dvae_linear_dgrad": [_i, _p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _p],
+    "dvae_linear_wgrad": [_i, _p, _l, _p, _l, _p, _l, _i, _i, _i, _p],
+    "dvae_conv5_fwd": [_i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dvae_conv5_dgrad": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dvae_conv5_wgrad": [_i, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dvae_lstm_fwd": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dvae_lstm_bwd": [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dvae_lstm_wgrad_hh": [_i, _p, _p, _p, _i, _i, _i, _i, _p],
+}
+_OPTIONAL = {}
+
+
+def _bind(name, argtypes):
+    fn = getattr(_lib, name)
+    fn.argtypes = argtypes
+    fn.restype = C.c_int
+    return fn
+
+
+def register(name, argtypes):
+    _SIGNATURES[name] = argtypes
+    _FUNCS[name] = _bind(name, argtypes)
+
+
+_FUNCS = {n: _bind(n, a) for n, a in _SIGNATURES.items()}
+for _n in ("dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile"):
+    getattr(_lib, _n).restype = C.c_int
+
+
+def ptr(t):
+    """Device pointer of a tensor (or None)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    rc = _FUNCS[name](*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (status {rc}): {_lib.dvae_last_error().decode()}")
+
+
+def version() -> int:
+    return _lib.dvae_version()
+
+
+def lstm_gate_tile(hidden: int) -> int:
+    return _lib.dvae_lstm_gate_tile(hidden)
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES.keys()) + ["dvae_last_error", "dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile"]
