@@ -25,7 +25,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int encode_map3(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
-                uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+                uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool mn_major) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -40,8 +40,9 @@ int encode_map3(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0,
   cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  CUresult r = fn(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw =
+      (mn_major && elem_bytes == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
     snprintf(buf, sizeof(buf),

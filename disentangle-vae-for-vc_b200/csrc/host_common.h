@@ -34,8 +34,11 @@ void set_last_error(const std::string& msg);
 
 // rank-3 tiled tensor map, 128-byte swizzle, zero fill out of bounds.  dims/box are in elements
 // (innermost first); strides in bytes for dims 1 and 2.
+// mn_major: the operand is consumed MN-major by tcgen05.mma; 32-bit MN-major operands need the 32-byte-atom
+// flavour of the 128-byte swizzle.
 int encode_map3(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
-                uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
+                uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
+                bool mn_major = false);
 
 inline int ceil_div(long a, long b) { return static_cast<int>((a + b - 1) / b); }
 

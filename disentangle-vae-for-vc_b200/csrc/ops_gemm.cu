@@ -80,7 +80,7 @@ static int linear_dgrad_t(const AT* dy, long lddy, const AT* w, AT* dx, float* d
   CUtensorMap ta, tb;
   const int BN = bn_override ? bn_override : pick_bn(K);
   if (int e = encode_map3(&ta, dy, EB, N, M, 1, lddy * EB, (uint64_t)M * lddy * EB, BK, 128, 1)) return e;
-  if (int e = encode_map3(&tb, w, EB, K, N, 1, (uint64_t)K * EB, (uint64_t)N * K * EB, BK, BK, 1)) return e;
+  if (int e = encode_map3(&tb, w, EB, K, N, 1, (uint64_t)K * EB, (uint64_t)N * K * EB, BK, BK, 1, true)) return e;
   OperandWalk wa = zero_walk(), wb = zero_walk();
   wa.per_j[0] = BK; wa.per_tile[1] = 128;
   wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN;
@@ -110,8 +110,8 @@ static int linear_wgrad_t(const AT* dy, long lddy, const AT* x, long ldx, float*
   constexpr int BK = 128 / EB;
   CUtensorMap ta, tb;
   const int BN = K <= 64 ? 64 : 128;
-  if (int e = encode_map3(&ta, dy, EB, N, M, 1, lddy * EB, (uint64_t)M * lddy * EB, BK, BK, 1)) return e;
-  if (int e = encode_map3(&tb, x, EB, K, M, 1, ldx * EB, (uint64_t)M * ldx * EB, BK, BK, 1)) return e;
+  if (int e = encode_map3(&ta, dy, EB, N, M, 1, lddy * EB, (uint64_t)M * lddy * EB, BK, BK, 1, true)) return e;
+  if (int e = encode_map3(&tb, x, EB, K, M, 1, ldx * EB, (uint64_t)M * ldx * EB, BK, BK, 1, true)) return e;
   OperandWalk wa = zero_walk(), wb = zero_walk();
   wa.per_j[1] = BK; wa.per_box[0] = BK; wa.per_tile[0] = 128;
   wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN;
@@ -159,7 +159,7 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
     if (int e = encode_map3(&tb, wk, EB, Cin, 5, Cout, (uint64_t)Cin * EB, (uint64_t)5 * Cin * EB, BK, 1, BN)) return e;
     wb.per_j[0] = BK; wb.per_tap[1] = 1; wb.per_tile[2] = BN;
   } else {
-    if (int e = encode_map3(&tb, wk, EB, Cin, 5, Cout, (uint64_t)Cin * EB, (uint64_t)5 * Cin * EB, BK, 1, BK)) return e;
+    if (int e = encode_map3(&tb, wk, EB, Cin, 5, Cout, (uint64_t)Cin * EB, (uint64_t)5 * Cin * EB, BK, 1, BK, true)) return e;
     wb.base[1] = 4; wb.per_tap[1] = -1; wb.per_j[2] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN;
   }
   const int kpt = ceil_div(Ca, BK);
@@ -187,8 +187,8 @@ static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, in
   constexpr int BK = 128 / EB;
   DVAE_REQUIRE(T % BK == 0, "T must be a multiple of the k-block");
   CUtensorMap ta, tb;
-  if (int e = encode_map3(&ta, dy, EB, Cout, T, R, (uint64_t)Cout * EB, (uint64_t)T * Cout * EB, BK, BK, 1)) return e;
-  if (int e = encode_map3(&tb, x, EB, Cin, T, R, (uint64_t)Cin * EB, (uint64_t)T * Cin * EB, BK, BK, 1)) return e;
+  if (int e = encode_map3(&ta, dy, EB, Cout, T, R, (uint64_t)Cout * EB, (uint64_t)T * Cout * EB, BK, BK, 1, true)) return e;
+  if (int e = encode_map3(&tb, x, EB, Cin, T, R, (uint64_t)Cin * EB, (uint64_t)T * Cin * EB, BK, BK, 1, true)) return e;
   const int BN = Cin <= 64 ? 64 : 128;
   OperandWalk wa = zero_walk(), wb = zero_walk();
   // k-block kb -> (sequence r = kb / (T/BK)  [the "tap" slot of the walk], time block j = kb % (T/BK))
@@ -268,7 +268,7 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
   if (int e = encode_map3(&ta, da_all, EB, (uint64_t)D * 4 * H, T, rows, (uint64_t)D * 4 * H * EB,
                           (uint64_t)T * D * 4 * H * EB, BK, 1, 128))
     return e;
-  if (int e = encode_map3(&tb, whh_n, EB, H, 4 * H, D, (uint64_t)H * EB, (uint64_t)4 * H * H * EB, BK, BK, 1)) return e;
+  if (int e = encode_map3(&tb, whh_n, EB, H, 4 * H, D, (uint64_t)H * EB, (uint64_t)4 * H * H * EB, BK, BK, 1, true)) return e;
   const long ldh = (long)T * D * H, ldx = (long)T * D * 4 * H;
   for (int s = 0; s < T; ++s) {
     const int tf = T - 1 - s, tr = s;  // forward direction walks time backwards, reverse direction forwards
@@ -305,9 +305,9 @@ static int lstm_wgrad_hh_t(const AT* da_all, const AT* h_all, float* dwhh, int r
   DVAE_REQUIRE(T % BK == 0, "T must be a multiple of the k-block");
   CUtensorMap ta, tb;
   if (int e = encode_map3(&ta, da_all, EB, (uint64_t)D * 4 * H, T, rows, (uint64_t)D * 4 * H * EB,
-                          (uint64_t)T * D * 4 * H * EB, BK, BK, 1))
+                          (uint64_t)T * D * 4 * H * EB, BK, BK, 1, true))
     return e;
-  if (int e = encode_map3(&tb, h_all, EB, (uint64_t)D * H, T, rows, (uint64_t)D * H * EB, (uint64_t)T * D * H * EB, BK, BK, 1))
+  if (int e = encode_map3(&tb, h_all, EB, (uint64_t)D * H, T, rows, (uint64_t)D * H * EB, (uint64_t)T * D * H * EB, BK, BK, 1, true))
     return e;
   const int BN = H <= 64 ? 64 : 128;
   OperandWalk wa = zero_walk(), wb = zero_walk();

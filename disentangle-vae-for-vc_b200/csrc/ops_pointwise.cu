@@ -1,0 +1,549 @@
+// Memory-bound kernels of the Disentangled-VAE hot path (everything that is not a tensor-core contraction):
+// weight re-layouts, NCL <-> channels-last packing, train/eval BatchNorm1d (stats, apply+activation, backward),
+// column sums (bias gradients).  All are coalesced, 16/32-byte vectorised, fp32 (or fp64) accumulating.
+//
+// Reference semantics: torch.nn.BatchNorm1d in train mode (model/disentangled_vae.py:159,:182,:58) = biased batch
+// variance for normalisation, unbiased for running_var, momentum 0.1, eps 1e-5; statistics are kept PER CALL
+// (x1-call, x2-call = "halves") although both halves live in one tensor here.
+#include <cuda_bf16.h>
+
+#include "act_types.cuh"
+#include "host_common.h"
+
+namespace dvae {
+
+using bf16 = __nv_bfloat16;
+constexpr int kAct_None = 0, kAct_Relu = 1, kAct_Tanh = 2;
+
+static inline int grid_for(long n, int block, int max_blocks = 148 * 16) {
+  long g = (n + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  return g < 1 ? 1 : static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------------------------ weight preparation
+template <typename AT>
+__global__ void cast_kernel(const float* __restrict__ src, AT* __restrict__ dst, long n) {
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x * 8;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  for (long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (aligned && i + 8 <= n) {
+      float v[8];
+      Act8<float>::load(src + i, v);
+      Act8<AT>::store(dst + i, v);
+    } else {
+      for (long j = i; j < n && j < i + 8; ++j) dst[j] = from_f32<AT>(src[j]);
+    }
+  }
+}
+
+// w[Co][Ci][5] (torch Conv1d) -> wk[Co][5][Ci]: the reduction dim (ci) becomes contiguous per tap
+template <typename AT>
+__global__ void conv_weight_kernel(const float* __restrict__ w, AT* __restrict__ wk, int Co, int Ci) {
+  const long n = static_cast<long>(Co) * 5 * Ci;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ci = i % Ci;
+    const int k = (i / Ci) % 5;
+    const int co = i / (5L * Ci);
+    wk[i] = from_f32<AT>(w[(static_cast<long>(co) * Ci + ci) * 5 + k]);
+  }
+}
+// dwk[Co][5][Ci] fp32 -> dw[Co][Ci][5] fp32 (gradient back in the parameter's layout)
+__global__ void conv_wgrad_unpack_kernel(const float* __restrict__ dwk, float* __restrict__ dw, int Co, int Ci) {
+  const long n = static_cast<long>(Co) * 5 * Ci;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int k = i % 5;
+    const int ci = (i / 5) % Ci;
+    const int co = i / (5L * Ci);
+    dw[i] = dwk[(static_cast<long>(co) * 5 + k) * Ci + ci];
+  }
+}
+
+__device__ __forceinline__ int gate_perm_src(int n, int H, int tile) {
+  // destination row n of the gate-interleaved layout <- source row of the torch [i;f;g;o] layout
+  const int units = tile >> 2;
+  const int jn = n / tile, within = n - jn * tile;
+  const int g = within / units, u = jn * units + (within - g * units);
+  return g * H + u;
+}
+template <typename AT>
+__global__ void lstm_weight_kernel(const float* __restrict__ w, AT* __restrict__ dst, int H, int In, int tile) {
+  const long n = 4L * H * In;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int col = i % In;
+    const int row = i / In;
+    dst[i] = from_f32<AT>(w[static_cast<long>(gate_perm_src(row, H, tile)) * In + col]);
+  }
+}
+__global__ void lstm_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, float* __restrict__ dst,
+                                 int H, int tile) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < 4 * H) {
+    const int s = gate_perm_src(n, H, tile);
+    dst[n] = b_ih[s] + b_hh[s];
+  }
+}
+
+// a += b (both activation dtype); joins the two gradient branches that meet at the decoder output
+template <typename AT>
+__global__ void add_inplace_kernel(AT* __restrict__ a, const AT* __restrict__ b, long n) {
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x * 8;
+  for (long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float u[8], v[8];
+      Act8<AT>::load(a + i, u);
+      Act8<AT>::load(b + i, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] += v[k];
+      Act8<AT>::store(a + i, u);
+    } else {
+      for (long j = i; j < n; ++j) a[j] = from_f32<AT>(to_f32(a[j]) + to_f32(b[j]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ layout packing
+// x fp32 [R][C][T] (reference NCL) -> y act [R][T][C] (channels-last, the GEMM A-operand layout)
+template <typename AT>
+__global__ void ncl_to_cl_kernel(const float* __restrict__ x, AT* __restrict__ y, int C, int T) {
+  extern __shared__ float tile[];  // [C][T+1]
+  const long r = blockIdx.x;
+  const float* xr = x + r * C * T;
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int c = i / T, t = i - c * T;
+    tile[c * (T + 1) + t] = xr[i];
+  }
+  __syncthreads();
+  AT* yr = y + r * C * T;
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    yr[i] = from_f32<AT>(tile[c * (T + 1) + t]);
+  }
+}
+// channels-last -> NCL fp32 with optional residual:  out[r][c][t] = a[r][t][c] (+ b[r][t][c]);  a is fp32 or act
+template <typename TA, typename TB>
+__global__ void cl_to_ncl_kernel(const TA* __restrict__ a, const TB* __restrict__ b, float* __restrict__ out_a,
+                                 float* __restrict__ out_sum, int C, int T) {
+  extern __shared__ float tile[];  // two [T][C+1] planes
+  float* ta = tile;
+  float* tb = tile + T * (C + 1);
+  const long r = blockIdx.x;
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    const float va = to_f32(a[r * C * T + i]);
+    ta[t * (C + 1) + c] = va;
+    if (b != nullptr) tb[t * (C + 1) + c] = va + to_f32(b[r * C * T + i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int c = i / T, t = i - c * T;
+    if (out_a != nullptr) out_a[r * C * T + i] = ta[t * (C + 1) + c];
+    if (out_sum != nullptr) out_sum[r * C * T + i] = tb[t * (C + 1) + c];
+  }
+}
+// backward of the residual output: d_rec[r][t][c] = g_rec[r][c][t] + g_hat[r][c][t];  d_post = g_hat  (either may be null)
+template <typename AT>
+__global__ void recon_out_bwd_kernel(const float* __restrict__ g_rec, const float* __restrict__ g_hat, AT* __restrict__ d_rec,
+                                     AT* __restrict__ d_post, int C, int T) {
+  extern __shared__ float tile[];
+  float* ta = tile;
+  float* tb = tile + C * (T + 1);
+  const long r = blockIdx.x;
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int c = i / T, t = i - c * T;
+    const float gh = g_hat ? g_hat[r * C * T + i] : 0.f;
+    const float gr = g_rec ? g_rec[r * C * T + i] : 0.f;
+    ta[c * (T + 1) + t] = gr + gh;
+    tb[c * (T + 1) + t] = gh;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    d_rec[r * C * T + i] = from_f32<AT>(ta[c * (T + 1) + t]);
+    d_post[r * C * T + i] = from_f32<AT>(tb[c * (T + 1) + t]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ BatchNorm1d
+// stats buffer (double) [halves][2][C]: sum, sum of squares.  Block = 64 rows x C channels.
+constexpr int kBnRowsPerBlock = 64;
+template <typename AT>
+__global__ void bn_stats_kernel(const AT* __restrict__ y, double* __restrict__ sums, int rows_half, int C) {
+  extern __shared__ float red[];  // [lanes][2][C]
+  const int tpr = C >> 3;                     // threads per row (8 channels each)
+  const int lanes = blockDim.x / tpr;         // row lanes
+  const int rl = threadIdx.x / tpr, cg = threadIdx.x - rl * tpr;
+  const long row0 = static_cast<long>(blockIdx.x) * kBnRowsPerBlock;
+  const int half = static_cast<int>(row0 / rows_half);
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (rl < lanes) {
+    for (int r = rl; r < kBnRowsPerBlock; r += lanes) {
+      float v[8];
+      Act8<AT>::load(y + (row0 + r) * C + cg * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[(rl * 2 + 0) * C + cg * 8 + i] = s[i];
+      red[(rl * 2 + 1) * C + cg * 8 + i] = q[i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * 2 * C + i];
+    atomicAdd(sums + static_cast<long>(half) * 2 * C + i, static_cast<double>(acc));
+  }
+}
+// stat (fp32) [halves][4][C]: mean, rstd, scale = rstd*gamma, shift = beta - mean*scale.  Running statistics are
+// updated half by half, in call order (x1 then x2), exactly like two consecutive nn.BatchNorm1d calls.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ stat, float* __restrict__ run_mean,
+                                   float* __restrict__ run_var, long long* __restrict__ num_batches, int halves, int C,
+                                   double n, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float rm = run_mean ? run_mean[c] : 0.f, rv = run_var ? run_var[c] : 1.f;
+    for (int h = 0; h < halves; ++h) {
+      const double mean = sums[(h * 2 + 0) * C + c] / n;
+      double var = sums[(h * 2 + 1) * C + c] / n - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      const float rstd = rsqrtf(static_cast<float>(var) + eps);
+      const float scale = rstd * gamma[c];
+      stat[(h * 4 + 0) * C + c] = static_cast<float>(mean);
+      stat[(h * 4 + 1) * C + c] = rstd;
+      stat[(h * 4 + 2) * C + c] = scale;
+      stat[(h * 4 + 3) * C + c] = beta[c] - static_cast<float>(mean) * scale;
+      rm = (1.f - momentum) * rm + momentum * static_cast<float>(mean);
+      rv = (1.f - momentum) * rv + momentum * static_cast<float>(var * (n / (n - 1.0)));
+    }
+    if (run_mean) run_mean[c] = rm;
+    if (run_var) run_var[c] = rv;
+  }
+  if (c == 0 && num_batches) *num_batches += halves;
+}
+// eval mode: stat from the running statistics
+__global__ void bn_eval_stat_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ run_mean, const float* __restrict__ run_var,
+                                    float* __restrict__ stat, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float rstd = rsqrtf(run_var[c] + eps);
+    const float scale = rstd * gamma[c];
+    stat[0 * C + c] = run_mean[c];
+    stat[1 * C + c] = rstd;
+    stat[2 * C + c] = scale;
+    stat[3 * C + c] = beta[c] - run_mean[c] * scale;
+  }
+}
+
+__device__ __forceinline__ float apply_act(float z, int act) {
+  if (act == kAct_Relu) return fmaxf(z, 0.f);
+  if (act == kAct_Tanh) return tanhf(z);
+  return z;
+}
+__device__ __forceinline__ float act_grad_from_z(float z, int act) {
+  if (act == kAct_Relu) return z > 0.f ? 1.f : 0.f;
+  if (act == kAct_Tanh) { const float t = tanhf(z); return 1.f - t * t; }
+  return 1.f;
+}
+
+// out = act(y * scale[h] + shift[h])
+template <typename AT>
+__global__ void bn_apply_kernel(const AT* __restrict__ y, AT* __restrict__ out, const float* __restrict__ stat, long rows,
+                                int rows_half, int C, int act) {
+  const int tpr = C >> 3;
+  const long total = rows * tpr;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long row = i / tpr;
+    const int cg = static_cast<int>(i - row * tpr);
+    const int h = static_cast<int>(row / rows_half);
+    const float* sc = stat + (h * 4 + 2) * C + cg * 8;
+    const float* sh = stat + (h * 4 + 3) * C + cg * 8;
+    float v[8];
+    Act8<AT>::load(y + row * C + cg * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = apply_act(fmaf(v[k], __ldg(sc + k), __ldg(sh + k)), act);
+    Act8<AT>::store(out + row * C + cg * 8, v);
+  }
+}
+
+// backward pass 1: per (half, channel) sums of dz and dz*xhat, dz = dout * act'(z)
+template <typename AT>
+__global__ void bn_bwd_reduce_kernel(const AT* __restrict__ dout, const AT* __restrict__ y, const float* __restrict__ stat,
+                                     double* __restrict__ sums, int rows_half, int C, int act) {
+  extern __shared__ float red[];
+  const int tpr = C >> 3;
+  const int lanes = blockDim.x / tpr;
+  const int rl = threadIdx.x / tpr, cg = threadIdx.x - rl * tpr;
+  const long row0 = static_cast<long>(blockIdx.x) * kBnRowsPerBlock;
+  const int h = static_cast<int>(row0 / rows_half);
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (rl < lanes) {
+    float mean[8], rstd[8], sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mean[i] = stat[(h * 4 + 0) * C + cg * 8 + i];
+      rstd[i] = stat[(h * 4 + 1) * C + cg * 8 + i];
+      sc[i] = stat[(h * 4 + 2) * C + cg * 8 + i];
+      sh[i] = stat[(h * 4 + 3) * C + cg * 8 + i];
+    }
+    for (int r = rl; r < kBnRowsPerBlock; r += lanes) {
+      float v[8], d[8];
+      Act8<AT>::load(y + (row0 + r) * C + cg * 8, v);
+      Act8<AT>::load(dout + (row0 + r) * C + cg * 8, d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dz = d[i] * act_grad_from_z(fmaf(v[i], sc[i], sh[i]), act);
+        s[i] += dz;
+        q[i] += dz * (v[i] - mean[i]) * rstd[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      red[(rl * 2 + 0) * C + cg * 8 + i] = s[i];
+      red[(rl * 2 + 1) * C + cg * 8 + i] = q[i];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * 2 * C + i];
+    atomicAdd(sums + static_cast<long>(h) * 2 * C + i, static_cast<double>(acc));
+  }
+}
+// dgamma = sum_h sum dz*xhat, dbeta = sum_h sum dz; coef [halves][2][C] = (sum dz)/n, (sum dz*xhat)/n
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, float* __restrict__ coef, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, int halves, int C, double n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double dg = 0.0, db = 0.0;
+  for (int h = 0; h < halves; ++h) {
+    const double s = sums[(h * 2 + 0) * C + c], q = sums[(h * 2 + 1) * C + c];
+    db += s; dg += q;
+    coef[(h * 2 + 0) * C + c] = static_cast<float>(s / n);
+    coef[(h * 2 + 1) * C + c] = static_cast<float>(q / n);
+  }
+  dgamma[c] = static_cast<float>(dg);
+  dbeta[c] = static_cast<float>(db);
+}
+// backward pass 2: dy = scale * (dz - mean(dz) - xhat * mean(dz*xhat))
+template <typename AT>
+__global__ void bn_bwd_apply_kernel(const AT* __restrict__ dout, const AT* __restrict__ y, const float* __restrict__ stat,
+                                    const float* __restrict__ coef, AT* __restrict__ dy, long rows, int rows_half, int C,
+                                    int act) {
+  const int tpr = C >> 3;
+  const long total = rows * tpr;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long row = i / tpr;
+    const int cg = static_cast<int>(i - row * tpr);
+    const int h = static_cast<int>(row / rows_half);
+    const int c0 = cg * 8;
+    float v[8], d[8];
+    Act8<AT>::load(y + row * C + c0, v);
+    Act8<AT>::load(dout + row * C + c0, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float mean = __ldg(stat + (h * 4 + 0) * C + c0 + k), rstd = __ldg(stat + (h * 4 + 1) * C + c0 + k);
+      const float sc = __ldg(stat + (h * 4 + 2) * C + c0 + k), sh = __ldg(stat + (h * 4 + 3) * C + c0 + k);
+      const float dz = d[k] * act_grad_from_z(fmaf(v[k], sc, sh), act);
+      const float xh = (v[k] - mean) * rstd;
+      d[k] = sc * (dz - __ldg(coef + (h * 2 + 0) * C + c0 + k) - xh * __ldg(coef + (h * 2 + 1) * C + c0 + k));
+    }
+    Act8<AT>::store(dy + row * C + c0, d);
+  }
+}
+
+// ------------------------------------------------------------------------------------ column sums (bias gradients)
+template <typename AT>
+__global__ void colsum_kernel(const AT* __restrict__ x, float* __restrict__ out, long rows, int C, long ldx) {
+  // block = 256 threads; thread owns 8 channels of one row lane; grid.x over row chunks, grid.y over channel chunks of 2048
+  const int c0 = blockIdx.y * 2048;
+  const int cw = min(2048, C - c0);
+  const int tpr = cw >> 3;
+  const int lanes = blockDim.x / tpr;
+  const int rl = threadIdx.x / tpr, cg = threadIdx.x - rl * tpr;
+  extern __shared__ float red[];  // [lanes][cw]
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  const long rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const long r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  if (rl < lanes) {
+    for (long r = r0 + rl; r < r1; r += lanes) {
+      float v[8];
+      Act8<AT>::load(x + r * ldx + c0 + cg * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[rl * cw + cg * 8 + i] = s[i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cw; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * cw + i];
+    atomicAdd(out + c0 + i, acc);
+  }
+}
+
+}  // namespace dvae
+
+using namespace dvae;
+
+#define DISPATCH_AT(dtype, ...)                              \
+  do {                                                       \
+    if ((dtype) == kBF16) { using AT = bf16; __VA_ARGS__; }  \
+    else if ((dtype) == kTF32) { using AT = float; __VA_ARGS__; } \
+    else { set_last_error("unknown dtype tag"); return 1; }  \
+  } while (0)
+
+extern "C" {
+
+int dvae_prep_cast(int dtype, const float* src, void* dst, long n, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_AT(dtype, cast_kernel<AT><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>(src, (AT*)dst, n));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dvae_add_inplace(int dtype, void* a, const void* b, long n, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_AT(dtype, add_inplace_kernel<AT><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>((AT*)a, (const AT*)b, n));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dvae_prep_conv_weight(int dtype, const float* w, void* wk, int Co, int Ci, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_AT(dtype, conv_weight_kernel<AT><<<grid_for(5L * Co * Ci, 256), 256, 0, st>>>(w, (AT*)wk, Co, Ci));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dvae_conv_wgrad_unpack(const float* dwk, float* dw, int Co, int Ci, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  conv_wgrad_unpack_kernel<<<grid_for(5L * Co * Ci, 256), 256, 0, st>>>(dwk, dw, Co, Ci);
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dvae_prep_lstm_weight(int dtype, const float* w, void* dst, int H, int In, int tile, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DVAE_REQUIRE(tile % 4 == 0 && (4 * H) % tile == 0, "gate tile must divide 4H");
+  DISPATCH_AT(dtype, lstm_weight_kernel<AT><<<grid_for(4L * H * In, 256), 256, 0, st>>>(w, (AT*)dst, H, In, tile));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dvae_prep_lstm_bias(const float* b_ih, const float* b_hh, float* dst, int H, int tile, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  lstm_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, st>>>(b_ih, b_hh, dst, H, tile);
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int dvae_pack_ncl_to_cl(int dtype, const float* x, void* y, int R, int C, int T, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (R == 0) return 0;
+  const int smem = C * (T + 1) * 4;
+  DVAE_REQUIRE(smem <= 48 * 1024, "C*(T+1) tile must fit 48 KB of shared memory");
+  DISPATCH_AT(dtype, ncl_to_cl_kernel<AT><<<R, 256, smem, st>>>(x, (AT*)y, C, T));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// out_a[r][c][t] = a[r][t][c] ; out_sum = a + b.  a_is_f32: a is fp32 (else act dtype); b is act dtype (may be null).
+int dvae_unpack_cl_to_ncl(int dtype, const void* a, int a_is_f32, const void* b, float* out_a, float* out_sum, int R, int C,
+                          int T, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (R == 0) return 0;
+  const int smem = 2 * T * (C + 1) * 4;
+  DVAE_REQUIRE(smem <= 48 * 1024, "2*T*(C+1) tile must fit 48 KB of shared memory");
+  if (a_is_f32) {
+    DISPATCH_AT(dtype, cl_to_ncl_kernel<float, AT><<<R, 256, smem, st>>>((const float*)a, (const AT*)b, out_a, out_sum, C, T));
+  } else {
+    DISPATCH_AT(dtype, cl_to_ncl_kernel<AT, AT><<<R, 256, smem, st>>>((const AT*)a, (const AT*)b, out_a, out_sum, C, T));
+  }
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dvae_recon_out_bwd(int dtype, const float* g_rec, const float* g_hat, void* d_rec, void* d_post, int R, int C, int T,
+                       void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (R == 0) return 0;
+  const int smem = 2 * C * (T + 1) * 4;
+  DVAE_REQUIRE(smem <= 48 * 1024, "tile must fit 48 KB of shared memory");
+  DISPATCH_AT(dtype, recon_out_bwd_kernel<AT><<<R, 256, smem, st>>>(g_rec, g_hat, (AT*)d_rec, (AT*)d_post, C, T));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Train-mode BatchNorm forward over y [halves*rows_half, C]: statistics per half, then act(y*scale+shift).
+// ws: double [halves*2*C] scratch; stat: fp32 [halves*4*C] (kept for backward).
+int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
+                      float* run_var, long long* num_batches, double* ws, float* stat, int rows_half, int halves, int C,
+                      int act, float eps, float momentum, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DVAE_REQUIRE(C % 8 == 0 && C <= 2048, "C must be a multiple of 8 (<= 2048)");
+  DVAE_REQUIRE(rows_half % kBnRowsPerBlock == 0, "rows per half must be a multiple of 64");
+  const long rows = static_cast<long>(rows_half) * halves;
+  DVAE_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * halves * 2 * C, st));
+  const int tpr = C / 8;
+  const int threads = 256;
+  const int lanes = threads / tpr;
+  DVAE_REQUIRE(lanes >= 1, "C too large for one block");
+  const int smem = lanes * 2 * C * 4;
+  DISPATCH_AT(dtype, bn_stats_kernel<AT><<<rows / kBnRowsPerBlock, threads, smem, st>>>((const AT*)y, ws, rows_half, C));
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, gamma, beta, stat, run_mean, run_var, num_batches, halves, C,
+                                                        static_cast<double>(rows_half), eps, momentum);
+  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<grid_for(rows * tpr, 256), 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half, C, act));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dvae_bn_eval_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, const float* run_mean,
+                     const float* run_var, float* stat, long rows, int C, int act, float eps, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DVAE_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  bn_eval_stat_kernel<<<ceil_div(C, 128), 128, 0, st>>>(gamma, beta, run_mean, run_var, stat, C, eps);
+  const int tpr = C / 8;
+  const int rows_half = rows > 0x7fffffffL ? 0x7fffffff : static_cast<int>(rows);
+  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<grid_for(rows * tpr, 256), 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half > 0 ? rows_half : 1, C, act));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// Train-mode BatchNorm backward (through the activation): dout -> dy, dgamma, dbeta.  coef: fp32 [halves*2*C] scratch.
+int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* stat, double* ws, float* coef, void* dy,
+                      float* dgamma, float* dbeta, int rows_half, int halves, int C, int act, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DVAE_REQUIRE(C % 8 == 0 && C <= 2048, "C must be a multiple of 8 (<= 2048)");
+  DVAE_REQUIRE(rows_half % kBnRowsPerBlock == 0, "rows per half must be a multiple of 64");
+  const long rows = static_cast<long>(rows_half) * halves;
+  DVAE_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * halves * 2 * C, st));
+  const int tpr = C / 8, threads = 256, lanes = threads / tpr;
+  const int smem = lanes * 2 * C * 4;
+  DISPATCH_AT(dtype, bn_bwd_reduce_kernel<AT><<<rows / kBnRowsPerBlock, threads, smem, st>>>((const AT*)dout, (const AT*)y, stat, ws, rows_half, C, act));
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, coef, dgamma, dbeta, halves, C, static_cast<double>(rows_half));
+  DISPATCH_AT(dtype, bn_bwd_apply_kernel<AT><<<grid_for(rows * tpr, 256), 256, 0, st>>>((const AT*)dout, (const AT*)y, stat, coef, (AT*)dy, rows, rows_half, C, act));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// out[C] (fp32) += column sums of x [rows, C] (row stride ldx)
+int dvae_colsum(int dtype, const void* x, float* out, long rows, int C, long ldx, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DVAE_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
+  if (rows == 0) return 0;
+  const int ychunks = ceil_div(C, 2048);
+  DVAE_REQUIRE(C <= 2048 || C % 2048 == 0, "C above 2048 must be a multiple of 2048");
+  const int cw = C < 2048 ? C : 2048;
+  const int tpr = cw / 8, lanes = 256 / tpr;
+  long gx = (rows + 255) / 256;
+  if (gx > 148 * 4) gx = 148 * 4;
+  dim3 grid(static_cast<unsigned>(gx), ychunks);
+  const int smem = lanes * cw * 4;
+  DISPATCH_AT(dtype, colsum_kernel<AT><<<grid, 256, smem, st>>>((const AT*)x, out, rows, C, ldx));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include "act_types.cuh"
 #include "ptx.cuh"
 
 namespace dvae {
@@ -40,11 +41,12 @@ struct GemmShape {
   int splits;      // split-K factor
 };
 
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   // sm_100 shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-  // version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+  // version=1 [46,48) | layout [61,64): SWIZZLE_128B = 2, SWIZZLE_128B_BASE32B = 1
   return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
-         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (static_cast<uint64_t>(layout_type) << 61);
 }
 
 template <int ELEM_BYTES, int BLOCK_N, bool A_MN, bool B_MN>
@@ -162,8 +164,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) {
         const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
         const uint32_t sb = sa + STAGE_A;
-        const uint64_t adesc = A_MN ? smem_desc(sa, MN_BOX_BYTES, 1024) : smem_desc(sa, 16, 1024);
-        const uint64_t bdesc = B_MN ? smem_desc(sb, MN_BOX_BYTES, 1024) : smem_desc(sb, 16, 1024);
+        // K-major: 8-row x 128 B swizzle atoms, 1024 B apart.  MN-major: atoms of (128 B along MN) x (8 k-rows),
+        // next atom along MN one TMA box further (LBO), next k-group SBO further.  32-bit MN-major operands
+        // only exist in the 32-byte-atom swizzle (4 k-rows per atom): layout type 1, SBO 512.
+        constexpr uint32_t MN_LAYOUT = (ELEM_BYTES == 4) ? 1u : 2u;
+        constexpr uint32_t MN_SBO = (ELEM_BYTES == 4) ? 512u : 1024u;
+        const uint64_t adesc = A_MN ? smem_desc(sa, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sa, 16, 1024, 2);
+        const uint64_t bdesc = B_MN ? smem_desc(sb, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sb, 16, 1024, 2);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
           ptx::umma<ELEM_BYTES>(tmem_base, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC, (it > 0 || k > 0) ? 1u : 0u);
@@ -196,48 +203,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Epilogues.  Each receives the TMEM address of its warp's 32-lane slice; thread `lane` owns
 // output row m and reads BLOCK_N fp32 columns in chunks.
 // =====================================================================================
-template <typename T>
-struct Act8;  // pack / unpack 8 consecutive activations
-template <>
-struct Act8<float> {
-  static __device__ __forceinline__ void load(const float* p, float* v) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  }
-  static __device__ __forceinline__ void store(float* p, const float* v) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  }
-};
-template <>
-struct Act8<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h[i]);
-      v[2 * i] = f.x; v[2 * i + 1] = f.y;
-    }
-  }
-  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
-    uint4 u;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    *reinterpret_cast<uint4*>(p) = u;
-  }
-};
-template <typename T> __device__ __forceinline__ float to_f32(T v);
-template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
-template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-template <typename T> __device__ __forceinline__ T from_f32(float v);
-template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
-template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
-
-__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_f(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
-
 // ---- out = act(acc + bias) -> activation dtype, optionally mirrored in fp32; optional relu-mask multiply
 template <typename OutT>
 struct EpiStore {

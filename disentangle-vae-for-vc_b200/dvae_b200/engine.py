@@ -1,0 +1,304 @@
+"""Hand-scheduled forward / backward of the Disentangled-VAE network on the dvae_b200 kernels.
+
+The engine owns no parameters: it reads the fp32 master parameters of the drop-in nn.Module, re-lays them for the
+tensor cores (bf16 or tf32 storage, conv taps / LSTM gate interleave), runs both pair members (x1-call and x2-call
+of model/disentangled_vae.py:250-279) as ONE batch of 2R rows -- BatchNorm statistics stay per call ("halves",
+SURVEY F5) -- and keeps exactly the intermediates the backward schedule needs.
+
+Data layout in HBM (R2 = rows in flight, T = 64 frames):
+  activations  channels-last [R2, T, C] in the storage dtype (bf16 | fp32-as-tf32): the K-major A operand of every
+               forward GEMM and, read MN-major, the operand of every weight-gradient GEMM (no transposes anywhere)
+  conv weights [Cout, 5, Cin]; linear weights [N, K]; LSTM weights twice: gate-interleaved (forward) + natural (backward)
+  LSTM state   h [R2, T, D*H] storage dtype, c [R2, T, D*H] fp32, activated gates [R2, T, D*4H] storage dtype
+  gradients    fp32, accumulated with split-K reductions, returned in the parameters' own layouts
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import lib, ops
+
+Tensor = torch.Tensor
+T_FRAMES = 64
+N_MELS = 80
+
+ENC_CONVS = [("enc_modules.%d.0.conv" % i, "enc_modules.%d.1" % i, lib.ACT_RELU) for i in range(3)]
+DEC_CONVS = [("dec_modules.%d.0" % i, "dec_modules.%d.1" % i, lib.ACT_RELU) for i in range(3)]
+POST_CONVS = [("postnet.convolutions.%d.0.conv" % i, "postnet.convolutions.%d.1" % i,
+               lib.ACT_TANH if i < 4 else lib.ACT_NONE) for i in range(5)]
+# (prefix, layers, directions, hidden)
+LSTMS = {"enc_lstm": (2, 2, 64), "dec_lstm1": (1, 1, 512), "dec_lstm2": (2, 1, 1024)}
+LINEARS = ["enc_linear.linear_layer", "dec_pre_linear1", "dec_pre_linear2", "dec_linear2.linear_layer"]
+
+
+class PreparedWeights:
+    """Tensor-core copies of the fp32 parameters (rebuilt whenever the parameters change)."""
+
+    def __init__(self, dt: int, P: Dict[str, Tensor]):
+        ad = ops.act_dtype(dt)
+        self.dt = dt
+        self.conv: Dict[str, Tensor] = {}
+        self.lin: Dict[str, Tensor] = {}
+        self.lstm: Dict[str, dict] = {}
+        for conv, _, _ in ENC_CONVS + DEC_CONVS + POST_CONVS:
+            self.conv[conv] = ops.prep_conv_weight(dt, P[conv + ".weight"])
+        for name in LINEARS:
+            w = P[name + ".weight"]
+            if dt == lib.TF32:
+                self.lin[name] = w  # fp32 storage is already the tf32 operand
+            else:
+                c = torch.empty_like(w, dtype=ad)
+                ops.prep_cast(dt, w, c)
+                self.lin[name] = c
+        # style + content heads fused into one [2L, 2048] GEMM (rows: style_mu, style_logvar, content_mu, content_logvar)
+        ws, wc = P["style.linear_layer.weight"], P["content.linear_layer.weight"]
+        n_s, n_c = ws.shape[0], wc.shape[0]
+        heads_w = torch.empty((n_s + n_c, ws.shape[1]), device=ws.device, dtype=ad)
+        ops.prep_cast(dt, ws, heads_w[:n_s])
+        ops.prep_cast(dt, wc, heads_w[n_s:])
+        heads_b = torch.empty((n_s + n_c,), device=ws.device, dtype=torch.float32)
+        ops.prep_cast(lib.TF32, P["style.linear_layer.bias"], heads_b[:n_s])
+        ops.prep_cast(lib.TF32, P["content.linear_layer.bias"], heads_b[n_s:])
+        self.heads_w, self.heads_b, self.n_style = heads_w, heads_b, n_s
+        for prefix, (layers, D, H) in LSTMS.items():
+            tile = lib.lstm_gate_tile(H)
+            per_layer = []
+            for l in range(layers):
+                In = P[f"{prefix}.weight_ih_l{l}"].shape[1]
+                dev = ws.device
+                wih_p = torch.empty((D * 4 * H, In), device=dev, dtype=ad)
+                wih_n = torch.empty((D * 4 * H, In), device=dev, dtype=ad)
+                whh_p = torch.empty((D, 4 * H, H), device=dev, dtype=ad)
+                whh_n = torch.empty((D, 4 * H, H), device=dev, dtype=ad)
+                bias_p = torch.empty((D * 4 * H,), device=dev, dtype=torch.float32)
+                for d in range(D):
+                    suf = "_reverse" if d == 1 else ""
+                    w_ih, w_hh = P[f"{prefix}.weight_ih_l{l}{suf}"], P[f"{prefix}.weight_hh_l{l}{suf}"]
+                    ops.prep_lstm_weight(dt, w_ih, wih_p[d * 4 * H:(d + 1) * 4 * H], H, tile)
+                    ops.prep_lstm_weight(dt, w_hh, whh_p[d], H, tile)
+                    ops.prep_cast(dt, w_ih, wih_n[d * 4 * H:(d + 1) * 4 * H])
+                    ops.prep_cast(dt, w_hh, whh_n[d])
+                    ops.prep_lstm_bias(P[f"{prefix}.bias_ih_l{l}{suf}"], P[f"{prefix}.bias_hh_l{l}{suf}"],
+                                       bias_p[d * 4 * H:(d + 1) * 4 * H], H, tile)
+                per_layer.append(dict(wih_p=wih_p, wih_n=wih_n, whh_p=whh_p, whh_n=whh_n, bias_p=bias_p, In=In))
+            self.lstm[prefix] = dict(layers=per_layer, D=D, H=H)
+
+
+class Engine:
+    def __init__(self, dt: int, latent_dim: int, speaker_size: int, bn_eps: float = 1e-5, bn_momentum: float = 0.1):
+        self.dt = dt
+        self.L = latent_dim
+        self.S = speaker_size
+        self.eps = bn_eps
+        self.momentum = bn_momentum
+
+    # ------------------------------------------------------------------ building blocks (forward)
+    def _conv_stack(self, W: PreparedWeights, P, B, h: Tensor, convs, halves: int, training: bool, saved: Optional[list]):
+        dt = self.dt
+        for conv, bn, act in convs:
+            x_in = h
+            y = ops.conv5_fwd(dt, x_in, W.conv[conv], P[conv + ".bias"])
+            C = y.shape[-1]
+            if training:
+                h, stat = ops.bn_train_fwd(dt, y.view(-1, C), P[bn + ".weight"], P[bn + ".bias"], B[bn + ".running_mean"],
+                                           B[bn + ".running_var"], B[bn + ".num_batches_tracked"], halves, act, self.eps,
+                                           self.momentum)
+                h = h.view_as(y)
+                if saved is not None:
+                    saved.append(dict(conv=conv, bn=bn, act=act, x_in=x_in, y=y, stat=stat))
+            else:
+                h = ops.bn_eval_fwd(dt, y.view(-1, C), P[bn + ".weight"], P[bn + ".bias"], B[bn + ".running_mean"],
+                                    B[bn + ".running_var"], act, self.eps).view_as(y)
+        return h
+
+    def _lstm(self, W: PreparedWeights, prefix: str, x: Tensor, saved: Optional[list]) -> Tensor:
+        dt = self.dt
+        info = W.lstm[prefix]
+        D, H = info["D"], info["H"]
+        rows, T, _ = x.shape
+        for lw in info["layers"]:
+            In = lw["In"]
+            xg, _ = ops.linear_fwd(dt, x.reshape(rows * T, In), lw["wih_p"], lw["bias_p"])
+            xg = xg.view(rows, T, D * 4 * H)
+            h_all, c_all = ops.lstm_fwd(dt, xg, lw["whh_p"], H, D)
+            if saved is not None:
+                saved.append(dict(prefix=prefix, x_in=x, gates=xg, h_all=h_all, c_all=c_all, lw=lw, D=D, H=H))
+            x = h_all
+        return x
+
+    def encode_rows(self, W, P, B, x_cl: Tensor, halves: int, training: bool, saved: Optional[dict]):
+        """x_cl [R2, T, 80] act -> (heads fp32 [R2, 2L], e act [R2, 2048])."""
+        dt = self.dt
+        R2 = x_cl.shape[0]
+        sv_conv = [] if saved is not None else None
+        sv_lstm = [] if saved is not None else None
+        h = self._conv_stack(W, P, B, x_cl, ENC_CONVS, halves, training, sv_conv)
+        h = self._lstm(W, "enc_lstm", h, sv_lstm)                      # [R2, T, 128]
+        flat = h.view(R2, T_FRAMES * 128)
+        e, _ = ops.linear_fwd(dt, flat, W.lin["enc_linear.linear_layer"], P["enc_linear.linear_layer.bias"], relu=True)
+        _, heads = ops.linear_fwd(dt, e, W.heads_w, W.heads_b, want_f32=True, want_act=False)
+        if saved is not None:
+            saved.update(enc_convs=sv_conv, enc_lstm=sv_lstm, flat=flat, e=e, heads=heads)
+        return heads, e
+
+    def decode_rows(self, W, P, B, z: Tensor, halves: int, training: bool, saved: Optional[dict]):
+        """z act [R2, L] -> (rec act [R2, T, 80], rec32 fp32 [R2, T, 80])."""
+        dt = self.dt
+        R2 = z.shape[0]
+        d1, _ = ops.linear_fwd(dt, z, W.lin["dec_pre_linear1"], P["dec_pre_linear1.bias"])
+        d2, _ = ops.linear_fwd(dt, d1, W.lin["dec_pre_linear2"], P["dec_pre_linear2.bias"])
+        sv_l1 = [] if saved is not None else None
+        sv_conv = [] if saved is not None else None
+        sv_l2 = [] if saved is not None else None
+        h = self._lstm(W, "dec_lstm1", d2.view(R2, T_FRAMES, 128), sv_l1)      # [R2, T, 512]
+        h = self._conv_stack(W, P, B, h, DEC_CONVS, halves, training, sv_conv)
+        h = self._lstm(W, "dec_lstm2", h, sv_l2)                               # [R2, T, 1024]
+        rec, rec32 = ops.linear_fwd(dt, h.view(R2 * T_FRAMES, 1024), W.lin["dec_linear2.linear_layer"],
+                                    P["dec_linear2.linear_layer.bias"], want_f32=True)
+        rec = rec.view(R2, T_FRAMES, N_MELS)
+        rec32 = rec32.view(R2, T_FRAMES, N_MELS)
+        if saved is not None:
+            saved.update(z=z, d1=d1, d2=d2, dec_lstm1=sv_l1, dec_convs=sv_conv, dec_lstm2=sv_l2, h_top=h, rec=rec)
+        return rec, rec32
+
+    def postnet_rows(self, W, P, B, rec: Tensor, halves: int, training: bool, saved: Optional[dict]) -> Tensor:
+        sv = [] if saved is not None else None
+        out = self._conv_stack(W, P, B, rec, POST_CONVS, halves, training, sv)
+        if saved is not None:
+            saved["post_convs"] = sv
+        return out
+
+    # ------------------------------------------------------------------ full training-step forward
+    def forward(self, W: PreparedWeights, P, B, x1: Tensor, x2: Tensor, eps: Sequence[Optional[Tensor]], training: bool,
+                sample_content: bool, keep: bool):
+        """Returns (outputs10, saved).  x1, x2 fp32 [R, 80, 64]."""
+        dt = self.dt
+        R = x1.shape[0]
+        assert x1.shape == x2.shape and tuple(x1.shape[1:]) == (N_MELS, T_FRAMES), \
+            f"expected [R, 80, 64] mel chunks, got {tuple(x1.shape)} (the network is locked to 64 frames)"
+        saved: Optional[dict] = {} if keep else None
+        x_cl = torch.empty((2 * R, T_FRAMES, N_MELS), device=x1.device, dtype=ops.act_dtype(dt))
+        ops.pack_ncl_to_cl(dt, x1, x_cl[:R])
+        ops.pack_ncl_to_cl(dt, x2, x_cl[R:])
+        heads, _ = self.encode_rows(W, P, B, x_cl, 2, training, saved)
+        z, q, zs = ops.latent_tail_fwd(dt, heads, eps[0], eps[1], eps[2], R, self.L, self.S, sample_content)
+        rec, rec32 = self.decode_rows(W, P, B, z, 2, training, saved)
+        post = self.postnet_rows(W, P, B, rec, 2, training, saved)
+        recon, hat = ops.unpack_cl_to_ncl(dt, rec32, post)
+        if saved is not None:
+            saved.update(R=R, eps=list(eps), sample_content=sample_content)
+        outs = (recon[:R], recon[R:], hat[:R], hat[R:], q[0], q[1], q[2], q[3], zs[0], zs[1])
+        return outs, saved
+
+    # ------------------------------------------------------------------ building blocks (backward)
+    def _conv_stack_bwd(self, W, dout: Tensor, saved_layers: list, grads: Dict[str, Tensor], halves: int, need_dx: bool):
+        dt = self.dt
+        for i in range(len(saved_layers) - 1, -1, -1):
+            s = saved_layers[i]
+            y = s["y"]
+            C = y.shape[-1]
+            dy, dgamma, dbeta = ops.bn_train_bwd(dt, dout.reshape(-1, C), y.view(-1, C), s["stat"], halves, s["act"])
+            dy = dy.view_as(y)
+            grads[s["bn"] + ".weight"] = dgamma
+            grads[s["bn"] + ".bias"] = dbeta
+            wk = W.conv[s["conv"]]
+            dwk = torch.zeros(wk.shape, device=wk.device, dtype=torch.float32)
+            ops.conv5_wgrad(dt, dy, s["x_in"], dwk)
+            grads[s["conv"] + ".weight"] = ops.conv_wgrad_unpack(dwk)
+            # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero (BN removes the mean)
+            grads[s["conv"] + ".bias"] = torch.zeros((C,), device=wk.device, dtype=torch.float32)
+            if i > 0 or need_dx:
+                dout = ops.conv5_dgrad(dt, dy, wk)
+            else:
+                dout = None
+        return dout
+
+    def _lstm_bwd(self, W, prefix: str, dh: Tensor, saved_layers: list, grads: Dict[str, Tensor], need_dx: bool):
+        dt = self.dt
+        for l in range(len(saved_layers) - 1, -1, -1):
+            s = saved_layers[l]
+            D, H, lw = s["D"], s["H"], s["lw"]
+            rows, T, _ = s["h_all"].shape
+            In = lw["In"]
+            da = ops.lstm_bwd(dt, dh.reshape(rows, T, D * H), s["gates"], s["c_all"], lw["whh_n"], H, D)
+            da2 = da.view(rows * T, D * 4 * H)
+            dwih = torch.zeros((D * 4 * H, In), device=da.device, dtype=torch.float32)
+            ops.linear_wgrad(dt, da2, s["x_in"].reshape(rows * T, In), dwih)
+            dwhh = torch.zeros((D, 4 * H, H), device=da.device, dtype=torch.float32)
+            ops.lstm_wgrad_hh(dt, da, s["h_all"], dwhh, H, D)
+            db = torch.zeros((D * 4 * H,), device=da.device, dtype=torch.float32)
+            ops.colsum(dt, da2, db)
+            for d in range(D):
+                suf = "_reverse" if d == 1 else ""
+                grads[f"{prefix}.weight_ih_l{l}{suf}"] = dwih[d * 4 * H:(d + 1) * 4 * H]
+                grads[f"{prefix}.weight_hh_l{l}{suf}"] = dwhh[d]
+                grads[f"{prefix}.bias_ih_l{l}{suf}"] = db[d * 4 * H:(d + 1) * 4 * H]
+                grads[f"{prefix}.bias_hh_l{l}{suf}"] = db[d * 4 * H:(d + 1) * 4 * H].clone()  # b_ih and b_hh: equal grads
+            if l > 0 or need_dx:
+                dh, _ = ops.linear_dgrad(dt, da2, lw["wih_n"])
+                dh = dh.view(rows, T, In)
+            else:
+                dh = None
+        return dh
+
+    def _linear_bwd(self, name: str, W_act: Tensor, dy: Tensor, x: Tensor, grads, relu_mask=None, want_f32=False,
+                    need_dx: bool = True):
+        dt = self.dt
+        N, K = W_act.shape
+        dw = torch.zeros((N, K), device=dy.device, dtype=torch.float32)
+        ops.linear_wgrad(dt, dy, x, dw)
+        db = torch.zeros((N,), device=dy.device, dtype=torch.float32)
+        ops.colsum(dt, dy, db)
+        grads[name + ".weight"] = dw
+        grads[name + ".bias"] = db
+        if not need_dx:
+            return None
+        dx, dx32 = ops.linear_dgrad(dt, dy, W_act, relu_mask=relu_mask, want_f32=want_f32, want_act=not want_f32)
+        return dx32 if want_f32 else dx
+
+    # ------------------------------------------------------------------ full backward
+    def backward(self, W: PreparedWeights, saved: dict, gouts: Sequence[Optional[Tensor]]) -> Dict[str, Tensor]:
+        """gouts: gradients of the 10 forward outputs (None = zero).  Returns {param name: fp32 gradient}."""
+        dt = self.dt
+        ad = ops.act_dtype(dt)
+        R = saved["R"]
+        R2 = 2 * R
+        dev = saved["heads"].device
+        grads: Dict[str, Tensor] = {}
+        g = [t.contiguous() if t is not None else None for t in gouts]
+        # ---- residual output: recon_hat = recon + postnet(recon)  (:277-278)
+        d_rec = torch.empty((R2, T_FRAMES, N_MELS), device=dev, dtype=ad)
+        d_post = torch.empty((R2, T_FRAMES, N_MELS), device=dev, dtype=ad)
+        ops.recon_out_bwd(dt, g[0], g[2], d_rec[:R], d_post[:R])
+        ops.recon_out_bwd(dt, g[1], g[3], d_rec[R:], d_post[R:])
+        d_in = self._conv_stack_bwd(W, d_post, saved["post_convs"], grads, 2, need_dx=True)
+        ops.add_inplace(dt, d_rec, d_in)
+        # ---- decoder
+        d_rec2 = d_rec.view(R2 * T_FRAMES, N_MELS)
+        dh = self._linear_bwd("dec_linear2.linear_layer", W.lin["dec_linear2.linear_layer"], d_rec2,
+                              saved["h_top"].view(R2 * T_FRAMES, 1024), grads)
+        dh = self._lstm_bwd(W, "dec_lstm2", dh, saved["dec_lstm2"], grads, need_dx=True)
+        dh = self._conv_stack_bwd(W, dh, saved["dec_convs"], grads, 2, need_dx=True)
+        dh = self._lstm_bwd(W, "dec_lstm1", dh, saved["dec_lstm1"], grads, need_dx=True)     # [R2, T, 128]
+        d_d2 = dh.reshape(R2, T_FRAMES * 128)
+        d_d1 = self._linear_bwd("dec_pre_linear2", W.lin["dec_pre_linear2"], d_d2, saved["d1"], grads)
+        dz = self._linear_bwd("dec_pre_linear1", W.lin["dec_pre_linear1"], d_d1, saved["z"], grads, want_f32=True)
+        # ---- latent tail (:252-272)
+        eps = saved["eps"]
+        dheads = ops.latent_tail_bwd(dt, saved["heads"], eps[0], eps[1], eps[2], dz, g[4:8], g[8:10], R, self.L, self.S,
+                                     saved["sample_content"])
+        # ---- encoder heads + linear
+        n_s = W.n_style
+        dw = torch.zeros(W.heads_w.shape, device=dev, dtype=torch.float32)
+        ops.linear_wgrad(dt, dheads, saved["e"], dw)
+        db = torch.zeros((W.heads_w.shape[0],), device=dev, dtype=torch.float32)
+        ops.colsum(dt, dheads, db)
+        grads["style.linear_layer.weight"], grads["content.linear_layer.weight"] = dw[:n_s], dw[n_s:]
+        grads["style.linear_layer.bias"], grads["content.linear_layer.bias"] = db[:n_s], db[n_s:]
+        d_e, _ = ops.linear_dgrad(dt, dheads, W.heads_w, relu_mask=saved["e"])
+        d_flat = self._linear_bwd("enc_linear.linear_layer", W.lin["enc_linear.linear_layer"], d_e, saved["flat"], grads)
+        dh = self._lstm_bwd(W, "enc_lstm", d_flat.view(R2, T_FRAMES, 128), saved["enc_lstm"], grads, need_dx=True)
+        self._conv_stack_bwd(W, dh, saved["enc_convs"], grads, 2, need_dx=False)
+        return grads

@@ -38,6 +38,31 @@ _SIGNATURES = {
     "dvae_lstm_fwd": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_lstm_bwd": [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_lstm_wgrad_hh": [_i, _p, _p, _p, _i, _i, _i, _i, _p],
+    # weight preparation / layout
+    "dvae_prep_cast": [_i, _p, _p, _l, _p],
+    "dvae_add_inplace": [_i, _p, _p, _l, _p],
+    "dvae_prep_conv_weight": [_i, _p, _p, _i, _i, _p],
+    "dvae_conv_wgrad_unpack": [_p, _p, _i, _i, _p],
+    "dvae_prep_lstm_weight": [_i, _p, _p, _i, _i, _i, _p],
+    "dvae_prep_lstm_bias": [_p, _p, _p, _i, _i, _p],
+    "dvae_pack_ncl_to_cl": [_i, _p, _p, _i, _i, _i, _p],
+    "dvae_unpack_cl_to_ncl": [_i, _p, _i, _p, _p, _p, _i, _i, _i, _p],
+    "dvae_recon_out_bwd": [_i, _p, _p, _p, _p, _i, _i, _i, _p],
+    # batch norm / reductions
+    "dvae_bn_train_fwd": [_i] + [_p] * 9 + [_i, _i, _i, _i, _f, _f, _p],
+    "dvae_bn_eval_fwd": [_i] + [_p] * 7 + [_l, _i, _i, _f, _p],
+    "dvae_bn_train_bwd": [_i] + [_p] * 8 + [_i, _i, _i, _i, _p],
+    "dvae_colsum": [_i, _p, _p, _l, _i, _l, _p],
+    # latent tail / loss / speaker groups
+    "dvae_latent_tail_fwd": [_i] + [_p] * 11 + [_i, _i, _i, _i, _p],
+    "dvae_latent_tail_bwd": [_i] + [_p] * 12 + [_i, _i, _i, _i, _p],
+    "dvae_loss_fwd": [_p] * 6 + [_l] + [_p] * 4 + [_i, _i, _p, _p, _i, _f, _f, _f, _p, _p, _p],
+    "dvae_loss_bwd": [_p] * 6 + [_l] + [_p] * 4 + [_i, _i, _p, _p, _i, _f, _f, _f] + [_p] * 11 + [_p],
+    "dvae_segment_ids_sorted": [_p, _p, _p, _p, _l, _p],
+    "dvae_group_accumulate": [_i, _p, _p, _p, _p, _p, _l, _i, _p],
+    "dvae_group_finalize": [_i, _p, _p, _p, _p, _p, _l, _i, _p],
+    "dvae_group_pog_bwd": [_p] * 7 + [_l, _i, _p],
+    "dvae_group_reparam": [_p] * 5 + [_l, _i, _p],
 }
 _OPTIONAL = {}
 

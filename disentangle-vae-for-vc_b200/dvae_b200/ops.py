@@ -132,3 +132,224 @@ def lstm_wgrad_hh(dt: int, da_all: Tensor, h_all: Tensor, dwhh: Tensor, H: int, 
     rows, T, _ = da_all.shape
     assert tuple(dwhh.shape) == (D, 4 * H, H)
     call("dvae_lstm_wgrad_hh", dt, ptr(da_all), ptr(h_all), ptr(dwhh), rows, T, H, D, stream())
+
+
+# ------------------------------------------------------------------------------- weight preparation
+def prep_cast(dt: int, src: Tensor, dst: Tensor) -> None:
+    _chk(src, torch.float32), _chk(dst, act_dtype(dt))
+    assert src.numel() == dst.numel()
+    call("dvae_prep_cast", dt, ptr(src), ptr(dst), src.numel(), stream())
+
+
+def add_inplace(dt: int, a: Tensor, b: Tensor) -> None:
+    _chk(a, act_dtype(dt)), _chk(b, act_dtype(dt))
+    assert a.numel() == b.numel()
+    call("dvae_add_inplace", dt, ptr(a), ptr(b), a.numel(), stream())
+
+
+def prep_conv_weight(dt: int, w: Tensor) -> Tensor:
+    """torch Conv1d weight [Co,Ci,5] fp32 -> [Co,5,Ci] activation dtype."""
+    _chk(w, torch.float32)
+    Co, Ci, k = w.shape
+    assert k == 5
+    wk = torch.empty((Co, 5, Ci), device=w.device, dtype=act_dtype(dt))
+    call("dvae_prep_conv_weight", dt, ptr(w), ptr(wk), Co, Ci, stream())
+    return wk
+
+
+def conv_wgrad_unpack(dwk: Tensor) -> Tensor:
+    _chk(dwk, torch.float32)
+    Co, k, Ci = dwk.shape
+    dw = torch.empty((Co, Ci, 5), device=dwk.device, dtype=torch.float32)
+    call("dvae_conv_wgrad_unpack", ptr(dwk), ptr(dw), Co, Ci, stream())
+    return dw
+
+
+def prep_lstm_weight(dt: int, w: Tensor, dst: Tensor, H: int, tile: int) -> None:
+    """w [4H, In] fp32 (torch gate order) -> dst [4H, In] activation dtype, rows gate-interleaved per `tile` columns."""
+    _chk(w, torch.float32), _chk(dst, act_dtype(dt))
+    In = w.shape[1]
+    assert tuple(w.shape) == (4 * H, In) and tuple(dst.shape) == (4 * H, In)
+    call("dvae_prep_lstm_weight", dt, ptr(w), ptr(dst), H, In, tile, stream())
+
+
+def prep_lstm_bias(b_ih: Tensor, b_hh: Tensor, dst: Tensor, H: int, tile: int) -> None:
+    _chk(b_ih, torch.float32), _chk(b_hh, torch.float32), _chk(dst, torch.float32)
+    call("dvae_prep_lstm_bias", ptr(b_ih), ptr(b_hh), ptr(dst), H, tile, stream())
+
+
+# ------------------------------------------------------------------------------- layout
+def pack_ncl_to_cl(dt: int, x: Tensor, out: Tensor) -> None:
+    """x fp32 [R,C,T] -> out act [R,T,C]."""
+    _chk(x, torch.float32), _chk(out, act_dtype(dt))
+    R, Cc, T = x.shape
+    assert tuple(out.shape) == (R, T, Cc)
+    call("dvae_pack_ncl_to_cl", dt, ptr(x), ptr(out), R, Cc, T, stream())
+
+
+def unpack_cl_to_ncl(dt: int, a: Tensor, b: Optional[Tensor], want_a: bool = True):
+    """a [R,T,C] (fp32 or act), b [R,T,C] act or None -> (a^T fp32 [R,C,T] or None, (a+b)^T fp32 or None)."""
+    assert a.is_cuda and a.is_contiguous()
+    R, T, Cc = a.shape
+    out_a = torch.empty((R, Cc, T), device=a.device, dtype=torch.float32) if want_a else None
+    out_s = torch.empty((R, Cc, T), device=a.device, dtype=torch.float32) if b is not None else None
+    call("dvae_unpack_cl_to_ncl", dt, ptr(a), int(a.dtype == torch.float32), ptr(b), ptr(out_a), ptr(out_s), R, Cc, T, stream())
+    return out_a, out_s
+
+
+def recon_out_bwd(dt: int, g_rec: Optional[Tensor], g_hat: Optional[Tensor], d_rec: Tensor, d_post: Tensor) -> None:
+    """g_* fp32 [R,C,T] (or None) -> d_rec = (g_rec + g_hat)^T, d_post = g_hat^T, both act [R,T,C]."""
+    R, T, Cc = d_rec.shape
+    for g in (g_rec, g_hat):
+        if g is not None:
+            _chk(g, torch.float32)
+            assert tuple(g.shape) == (R, Cc, T)
+    call("dvae_recon_out_bwd", dt, ptr(g_rec), ptr(g_hat), ptr(d_rec), ptr(d_post), R, Cc, T, stream())
+
+
+# ------------------------------------------------------------------------------- batch norm
+def bn_train_fwd(dt: int, y: Tensor, gamma: Tensor, beta: Tensor, run_mean: Optional[Tensor], run_var: Optional[Tensor],
+                 num_batches: Optional[Tensor], halves: int, act: int, eps: float, momentum: float):
+    """y [rows, C] (rows = halves * rows_half).  Returns (out act [rows,C], stat fp32 [halves,4,C])."""
+    ad = act_dtype(dt)
+    _chk(y, ad)
+    C = y.shape[-1]
+    rows = y.numel() // C
+    assert rows % halves == 0
+    out = torch.empty_like(y)
+    ws = torch.empty((halves * 2 * C,), device=y.device, dtype=torch.float64)
+    stat = torch.empty((halves, 4, C), device=y.device, dtype=torch.float32)
+    call("dvae_bn_train_fwd", dt, ptr(y), ptr(out), ptr(gamma), ptr(beta), ptr(run_mean), ptr(run_var), ptr(num_batches),
+         ptr(ws), ptr(stat), rows // halves, halves, C, act, eps, momentum, stream())
+    return out, stat
+
+
+def bn_eval_fwd(dt: int, y: Tensor, gamma: Tensor, beta: Tensor, run_mean: Tensor, run_var: Tensor, act: int, eps: float):
+    ad = act_dtype(dt)
+    _chk(y, ad)
+    C = y.shape[-1]
+    rows = y.numel() // C
+    out = torch.empty_like(y)
+    stat = torch.empty((1, 4, C), device=y.device, dtype=torch.float32)
+    call("dvae_bn_eval_fwd", dt, ptr(y), ptr(out), ptr(gamma), ptr(beta), ptr(run_mean), ptr(run_var), ptr(stat), rows, C, act,
+         eps, stream())
+    return out
+
+
+def bn_train_bwd(dt: int, dout: Tensor, y: Tensor, stat: Tensor, halves: int, act: int):
+    """Returns (dy act [rows,C], dgamma fp32 [C], dbeta fp32 [C])."""
+    ad = act_dtype(dt)
+    _chk(dout, ad), _chk(y, ad), _chk(stat, torch.float32)
+    C = y.shape[-1]
+    rows = y.numel() // C
+    dy = torch.empty_like(y)
+    ws = torch.empty((halves * 2 * C,), device=y.device, dtype=torch.float64)
+    coef = torch.empty((halves * 2 * C,), device=y.device, dtype=torch.float32)
+    dgamma = torch.empty((C,), device=y.device, dtype=torch.float32)
+    dbeta = torch.empty((C,), device=y.device, dtype=torch.float32)
+    call("dvae_bn_train_bwd", dt, ptr(dout), ptr(y), ptr(stat), ptr(ws), ptr(coef), ptr(dy), ptr(dgamma), ptr(dbeta),
+         rows // halves, halves, C, act, stream())
+    return dy, dgamma, dbeta
+
+
+def colsum(dt: int, x: Tensor, out: Tensor) -> None:
+    """out[C] (fp32, accumulating) += column sums of x viewed as [rows, C]."""
+    _chk(x, act_dtype(dt)), _chk(out, torch.float32)
+    C = out.numel()
+    rows = x.numel() // C
+    call("dvae_colsum", dt, ptr(x), ptr(out), rows, C, C, stream())
+
+
+# ------------------------------------------------------------------------------- latent tail / loss
+def latent_tail_fwd(dt: int, heads: Tensor, eps_c1, eps_c2, eps_s: Tensor, R: int, L: int, S: int, sample_content: bool):
+    _chk(heads, torch.float32)
+    assert tuple(heads.shape) == (2 * R, 2 * L)
+    dev = heads.device
+    z = torch.empty((2 * R, L), device=dev, dtype=act_dtype(dt))
+    q = [torch.empty((R, L), device=dev, dtype=torch.float32) for _ in range(4)]
+    zs = [torch.empty((R, S), device=dev, dtype=torch.float32) for _ in range(2)]
+    call("dvae_latent_tail_fwd", dt, ptr(heads), ptr(eps_c1), ptr(eps_c2), ptr(eps_s), ptr(z), ptr(q[0]), ptr(q[1]), ptr(q[2]),
+         ptr(q[3]), ptr(zs[0]), ptr(zs[1]), R, L, S, int(sample_content), stream())
+    return z, q, zs
+
+
+def latent_tail_bwd(dt: int, heads: Tensor, eps_c1, eps_c2, eps_s, dz: Tensor, dq, dzs, R: int, L: int, S: int,
+                    sample_content: bool) -> Tensor:
+    _chk(dz, torch.float32)
+    dheads = torch.empty((2 * R, 2 * L), device=heads.device, dtype=act_dtype(dt))
+    call("dvae_latent_tail_bwd", dt, ptr(heads), ptr(eps_c1), ptr(eps_c2), ptr(eps_s), ptr(dz), ptr(dq[0]), ptr(dq[1]), ptr(dq[2]),
+         ptr(dq[3]), ptr(dzs[0]), ptr(dzs[1]), ptr(dheads), R, L, S, int(sample_content), stream())
+    return dheads
+
+
+def loss_fwd(x1, x2, r1, r2, h1, h2, q1_mu, q1_lv, q2_mu, q2_lv, s_mu, s_lv, batch_size: float, mse_cof: float,
+             kl_cof: float) -> Tensor:
+    ts = [x1, x2, r1, r2, h1, h2, q1_mu, q1_lv, q2_mu, q2_lv, s_mu, s_lv]
+    for t in ts:
+        _chk(t, torch.float32)
+    n = x1.numel()
+    assert all(t.numel() == n for t in ts[:6])
+    rows, L = q1_mu.shape
+    S = s_mu.shape[1]
+    ws = torch.empty((9,), device=x1.device, dtype=torch.float64)
+    out = torch.empty((8,), device=x1.device, dtype=torch.float32)
+    call("dvae_loss_fwd", *[ptr(t) for t in ts[:6]], n, *[ptr(t) for t in ts[6:10]], rows, L, ptr(s_mu), ptr(s_lv), S,
+         float(batch_size), float(mse_cof), float(kl_cof), ptr(ws), ptr(out), stream())
+    return out
+
+
+def loss_bwd(x1, x2, r1, r2, h1, h2, q1_mu, q1_lv, q2_mu, q2_lv, s_mu, s_lv, batch_size, mse_cof, kl_cof, gout: Tensor):
+    ts = [x1, x2, r1, r2, h1, h2, q1_mu, q1_lv, q2_mu, q2_lv, s_mu, s_lv]
+    _chk(gout, torch.float32)
+    n = x1.numel()
+    rows, L = q1_mu.shape
+    S = s_mu.shape[1]
+    outs = [torch.empty_like(t) for t in ts[2:]]
+    call("dvae_loss_bwd", *[ptr(t) for t in ts[:6]], n, *[ptr(t) for t in ts[6:10]], rows, L, ptr(s_mu), ptr(s_lv), S,
+         float(batch_size), float(mse_cof), float(kl_cof), ptr(gout), *[ptr(t) for t in outs], stream())
+    return outs
+
+
+# ------------------------------------------------------------------------------- speaker groups
+MODE_POG, MODE_MEAN, MODE_RAW = 0, 1, 2
+
+
+def segment_ids_sorted(labels: Tensor):
+    """labels int64 [B] on device with equal ids adjacent -> (gid int32 [B], num_groups int32 [1] on device)."""
+    _chk(labels, torch.int64)
+    B = labels.numel()
+    gid = torch.empty((B,), device=labels.device, dtype=torch.int32)
+    scratch = torch.empty((max(1, (B + 1023) // 1024),), device=labels.device, dtype=torch.int32)
+    ng = torch.empty((1,), device=labels.device, dtype=torch.int32)
+    call("dvae_segment_ids_sorted", ptr(labels), ptr(gid), ptr(scratch), ptr(ng), B, stream())
+    return gid, ng
+
+
+def group_accumulate(mode: int, a: Tensor, b: Tensor, gid: Tensor, G: int):
+    _chk(a, torch.float32), _chk(b, torch.float32), _chk(gid, torch.int32)
+    B, D = a.shape
+    acc = torch.zeros((G, 2, D), device=a.device, dtype=torch.float32)
+    cnt = torch.zeros((G,), device=a.device, dtype=torch.float32)
+    call("dvae_group_accumulate", mode, ptr(a), ptr(b), ptr(gid), ptr(acc), ptr(cnt), B, D, stream())
+    return acc, cnt
+
+
+def group_finalize(mode: int, acc: Tensor, cnt: Tensor, gid: Tensor, B: int, D: int, want_b: bool = True):
+    out_a = torch.empty((B, D), device=acc.device, dtype=torch.float32)
+    out_b = torch.empty((B, D), device=acc.device, dtype=torch.float32) if want_b else None
+    call("dvae_group_finalize", mode, ptr(acc), ptr(cnt), ptr(gid), ptr(out_a), ptr(out_b), B, D, stream())
+    return out_a, out_b
+
+
+def group_pog_bwd(mu: Tensor, logvar: Tensor, gid: Tensor, acc_f: Tensor, acc_g: Tensor):
+    B, D = mu.shape
+    dmu, dlv = torch.empty_like(mu), torch.empty_like(mu)
+    call("dvae_group_pog_bwd", ptr(mu), ptr(logvar), ptr(gid), ptr(acc_f), ptr(acc_g), ptr(dmu), ptr(dlv), B, D, stream())
+    return dmu, dlv
+
+
+def group_reparam(mu: Tensor, logvar: Tensor, gid: Tensor, eps_group: Tensor) -> Tensor:
+    B, D = mu.shape
+    z = torch.empty_like(mu)
+    call("dvae_group_reparam", ptr(mu), ptr(logvar), ptr(gid), ptr(eps_group), ptr(z), B, D, stream())
+    return z

@@ -136,7 +136,7 @@ def _lstm_ref(xproj_nat, whh, D, H):
 
 
 @pytest.mark.parametrize("name", DTS)
-@pytest.mark.parametrize("rows,H,D,T", [(8, 64, 2, 64), (130, 64, 1, 64), (16, 512, 1, 64), (256, 1024, 1, 8)])
+@pytest.mark.parametrize("rows,H,D,T", [(8, 64, 2, 64), (130, 64, 1, 64), (16, 512, 1, 64), (256, 1024, 1, 64)])
 def test_lstm(name, rows, H, D, T):
     _setup()
     from dvae_b200 import lib, ops
