@@ -39,10 +39,35 @@ struct Act8<__nv_bfloat16> {
     *reinterpret_cast<uint4*>(p) = u;
   }
 };
+// fp32 storage whose values are kept on the tf32 grid (10 mantissa bits, round-to-nearest).  tcgen05 kind::tf32
+// TRUNCATES the low 13 bits of its fp32 operands; truncation is a biased error that compounds through un-normalised
+// layers, so every tensor that feeds a tf32 MMA is rounded once, when it is stored.
+struct tf32_t {
+  float x;
+};
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+template <>
+struct Act8<tf32_t> {
+  static __device__ __forceinline__ void load(const tf32_t* p, float* v) {
+    Act8<float>::load(reinterpret_cast<const float*>(p), v);
+  }
+  static __device__ __forceinline__ void store(tf32_t* p, const float* v) {
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = round_tf32(v[i]);
+    Act8<float>::store(reinterpret_cast<float*>(p), r);
+  }
+};
 template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<tf32_t>(tf32_t v) { return v.x; }
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ tf32_t from_f32<tf32_t>(float v) { tf32_t t; t.x = round_tf32(v); return t; }
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 

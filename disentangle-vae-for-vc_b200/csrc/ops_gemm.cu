@@ -343,7 +343,7 @@ int dvae_linear_fwd(int dtype, const void* x, long ldx, const void* w, const flo
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype,
                  linear_fwd_t<bf16>((const bf16*)x, ldx, (const bf16*)w, bias, (bf16*)out, out_f32, ldo, M, N, K, relu, block_n, st),
-                 linear_fwd_t<float>((const float*)x, ldx, (const float*)w, bias, (float*)out, out_f32, ldo, M, N, K, relu, block_n, st));
+                 linear_fwd_t<tf32_t>((const tf32_t*)x, ldx, (const tf32_t*)w, bias, (tf32_t*)out, out_f32, ldo, M, N, K, relu, block_n, st));
 }
 
 int dvae_linear_dgrad(int dtype, const void* dy, long lddy, const void* w, void* dx, float* dx_f32, const void* relu_mask,
@@ -351,41 +351,41 @@ int dvae_linear_dgrad(int dtype, const void* dy, long lddy, const void* w, void*
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype,
                  linear_dgrad_t<bf16>((const bf16*)dy, lddy, (const bf16*)w, (bf16*)dx, dx_f32, (const bf16*)relu_mask, ldx, M, N, K, block_n, st),
-                 linear_dgrad_t<float>((const float*)dy, lddy, (const float*)w, (float*)dx, dx_f32, (const float*)relu_mask, ldx, M, N, K, block_n, st));
+                 linear_dgrad_t<tf32_t>((const tf32_t*)dy, lddy, (const tf32_t*)w, (tf32_t*)dx, dx_f32, (const tf32_t*)relu_mask, ldx, M, N, K, block_n, st));
 }
 
 int dvae_linear_wgrad(int dtype, const void* dy, long lddy, const void* x, long ldx, float* dw, long lddw, int M, int N,
                       int K, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype, linear_wgrad_t<bf16>((const bf16*)dy, lddy, (const bf16*)x, ldx, dw, lddw, M, N, K, st),
-                 linear_wgrad_t<float>((const float*)dy, lddy, (const float*)x, ldx, dw, lddw, M, N, K, st));
+                 linear_wgrad_t<tf32_t>((const tf32_t*)dy, lddy, (const tf32_t*)x, ldx, dw, lddw, M, N, K, st));
 }
 
 int dvae_conv5_fwd(int dtype, const void* x, const void* wk, const float* bias, void* y, float* y_f32, int R, int T, int Cin,
                    int Cout, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype, conv5_fwd_t<bf16>((const bf16*)x, (const bf16*)wk, bias, (bf16*)y, y_f32, R, T, Cin, Cout, false, st),
-                 conv5_fwd_t<float>((const float*)x, (const float*)wk, bias, (float*)y, y_f32, R, T, Cin, Cout, false, st));
+                 conv5_fwd_t<tf32_t>((const tf32_t*)x, (const tf32_t*)wk, bias, (tf32_t*)y, y_f32, R, T, Cin, Cout, false, st));
 }
 
 int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,
                      void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype, conv5_fwd_t<bf16>((const bf16*)dy, (const bf16*)wk, nullptr, (bf16*)dx, dx_f32, R, T, Cin, Cout, true, st),
-                 conv5_fwd_t<float>((const float*)dy, (const float*)wk, nullptr, (float*)dx, dx_f32, R, T, Cin, Cout, true, st));
+                 conv5_fwd_t<tf32_t>((const tf32_t*)dy, (const tf32_t*)wk, nullptr, (tf32_t*)dx, dx_f32, R, T, Cin, Cout, true, st));
 }
 
 int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R, int T, int Cin, int Cout, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype, conv5_wgrad_t<bf16>((const bf16*)dy, (const bf16*)x, dwk, R, T, Cin, Cout, st),
-                 conv5_wgrad_t<float>((const float*)dy, (const float*)x, dwk, R, T, Cin, Cout, st));
+                 conv5_wgrad_t<tf32_t>((const tf32_t*)dy, (const tf32_t*)x, dwk, R, T, Cin, Cout, st));
 }
 
 int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_all, int rows, int T, int H, int D,
                   void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype, lstm_fwd_t<bf16>((bf16*)xg, (const bf16*)whh_p, (bf16*)h_all, c_all, rows, T, H, D, st),
-                 lstm_fwd_t<float>((float*)xg, (const float*)whh_p, (float*)h_all, c_all, rows, T, H, D, st));
+                 lstm_fwd_t<tf32_t>((tf32_t*)xg, (const tf32_t*)whh_p, (tf32_t*)h_all, c_all, rows, T, H, D, st));
 }
 
 int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all,
@@ -393,14 +393,14 @@ int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float*
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype,
                  lstm_bwd_t<bf16>((const bf16*)dh_all, (const bf16*)gates, c_all, (const bf16*)whh_n, (bf16*)da_all, dc_ws, rows, T, H, D, st),
-                 lstm_bwd_t<float>((const float*)dh_all, (const float*)gates, c_all, (const float*)whh_n, (float*)da_all, dc_ws, rows, T, H, D, st));
+                 lstm_bwd_t<tf32_t>((const tf32_t*)dh_all, (const tf32_t*)gates, c_all, (const tf32_t*)whh_n, (tf32_t*)da_all, dc_ws, rows, T, H, D, st));
 }
 
 int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* dwhh, int rows, int T, int H, int D,
                        void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype, lstm_wgrad_hh_t<bf16>((const bf16*)da_all, (const bf16*)h_all, dwhh, rows, T, H, D, st),
-                 lstm_wgrad_hh_t<float>((const float*)da_all, (const float*)h_all, dwhh, rows, T, H, D, st));
+                 lstm_wgrad_hh_t<tf32_t>((const tf32_t*)da_all, (const tf32_t*)h_all, dwhh, rows, T, H, D, st));
 }
 
 int dvae_lstm_gate_tile(int H) { return lstm_fwd_bn(H); }

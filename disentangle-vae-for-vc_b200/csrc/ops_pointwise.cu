@@ -399,7 +399,7 @@ using namespace dvae;
 #define DISPATCH_AT(dtype, ...)                              \
   do {                                                       \
     if ((dtype) == kBF16) { using AT = bf16; __VA_ARGS__; }  \
-    else if ((dtype) == kTF32) { using AT = float; __VA_ARGS__; } \
+    else if ((dtype) == kTF32) { using AT = tf32_t; __VA_ARGS__; } \
     else { set_last_error("unknown dtype tag"); return 1; }  \
   } while (0)
 
@@ -408,6 +408,12 @@ extern "C" {
 int dvae_prep_cast(int dtype, const float* src, void* dst, long n, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_AT(dtype, cast_kernel<AT><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>(src, (AT*)dst, n));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dvae_copy_f32(const float* src, float* dst, long n, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  cast_kernel<float><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>(src, dst, n);   // exact copy (no tf32 rounding)
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -46,12 +46,9 @@ class PreparedWeights:
             self.conv[conv] = ops.prep_conv_weight(dt, P[conv + ".weight"])
         for name in LINEARS:
             w = P[name + ".weight"]
-            if dt == lib.TF32:
-                self.lin[name] = w  # fp32 storage is already the tf32 operand
-            else:
-                c = torch.empty_like(w, dtype=ad)
-                ops.prep_cast(dt, w, c)
-                self.lin[name] = c
+            c = torch.empty_like(w, dtype=ad)   # bf16 copy, or fp32 rounded onto the tf32 grid
+            ops.prep_cast(dt, w, c)
+            self.lin[name] = c
         # style + content heads fused into one [2L, 2048] GEMM (rows: style_mu, style_logvar, content_mu, content_logvar)
         ws, wc = P["style.linear_layer.weight"], P["content.linear_layer.weight"]
         n_s, n_c = ws.shape[0], wc.shape[0]
@@ -59,8 +56,8 @@ class PreparedWeights:
         ops.prep_cast(dt, ws, heads_w[:n_s])
         ops.prep_cast(dt, wc, heads_w[n_s:])
         heads_b = torch.empty((n_s + n_c,), device=ws.device, dtype=torch.float32)
-        ops.prep_cast(lib.TF32, P["style.linear_layer.bias"], heads_b[:n_s])
-        ops.prep_cast(lib.TF32, P["content.linear_layer.bias"], heads_b[n_s:])
+        ops.copy_f32(P["style.linear_layer.bias"], heads_b[:n_s])
+        ops.copy_f32(P["content.linear_layer.bias"], heads_b[n_s:])
         self.heads_w, self.heads_b, self.n_style = heads_w, heads_b, n_s
         for prefix, (layers, D, H) in LSTMS.items():
             tile = lib.lstm_gate_tile(H)
@@ -86,8 +83,45 @@ class PreparedWeights:
             self.lstm[prefix] = dict(layers=per_layer, D=D, H=H)
 
 
+class GradSink:
+    """Where parameter gradients land: private fp32 tensors, or views into the flat all-reduce buckets of
+    dvae_b200.parallel.GradBuckets (then `done()` may trigger that bucket's overlapped all-reduce)."""
+
+    def __init__(self, device, buckets=None):
+        self.device = device
+        self.buckets = buckets
+        self.grads: Dict[str, Tensor] = {}
+        if buckets is not None:
+            buckets.begin()
+
+    def buf(self, name: str, shape) -> Tensor:
+        """Zero-initialised fp32 buffer for the gradient of `name`."""
+        t = self.buckets.view(name) if self.buckets is not None else torch.zeros(tuple(shape), device=self.device,
+                                                                               dtype=torch.float32)
+        self.grads[name] = t
+        return t
+
+    def done(self, name: str) -> None:
+        if self.buckets is not None:
+            self.buckets.ready(name)
+
+    def put(self, name: str, src: Tensor) -> None:
+        """Gradient computed elsewhere (a slice of a fused GEMM output): copy into place when bucketed."""
+        if self.buckets is None:
+            self.grads[name] = src
+        else:
+            ops.copy_f32(src.contiguous(), self.buf(name, src.shape))
+        self.done(name)
+
+    def finish(self) -> Dict[str, Tensor]:
+        if self.buckets is not None:
+            self.buckets.finish()
+        return self.grads
+
+
 class Engine:
     def __init__(self, dt: int, latent_dim: int, speaker_size: int, bn_eps: float = 1e-5, bn_momentum: float = 0.1):
+        self.buckets = None   # set to a parallel.GradBuckets for data-parallel training
         self.dt = dt
         self.L = latent_dim
         self.S = speaker_size
@@ -193,29 +227,33 @@ class Engine:
         return outs, saved
 
     # ------------------------------------------------------------------ building blocks (backward)
-    def _conv_stack_bwd(self, W, dout: Tensor, saved_layers: list, grads: Dict[str, Tensor], halves: int, need_dx: bool):
+    def _conv_stack_bwd(self, W, dout: Tensor, saved_layers: list, sink: GradSink, halves: int, need_dx: bool):
         dt = self.dt
         for i in range(len(saved_layers) - 1, -1, -1):
             s = saved_layers[i]
             y = s["y"]
             C = y.shape[-1]
-            dy, dgamma, dbeta = ops.bn_train_bwd(dt, dout.reshape(-1, C), y.view(-1, C), s["stat"], halves, s["act"])
+            gname, bname = s["bn"] + ".weight", s["bn"] + ".bias"
+            dy, _, _ = ops.bn_train_bwd(dt, dout.reshape(-1, C), y.view(-1, C), s["stat"], halves, s["act"],
+                                        dgamma=sink.buf(gname, (C,)), dbeta=sink.buf(bname, (C,)))
             dy = dy.view_as(y)
-            grads[s["bn"] + ".weight"] = dgamma
-            grads[s["bn"] + ".bias"] = dbeta
+            sink.done(gname), sink.done(bname)
             wk = W.conv[s["conv"]]
+            Co, _, Ci = wk.shape
             dwk = torch.zeros(wk.shape, device=wk.device, dtype=torch.float32)
             ops.conv5_wgrad(dt, dy, s["x_in"], dwk)
-            grads[s["conv"] + ".weight"] = ops.conv_wgrad_unpack(dwk)
+            ops.conv_wgrad_unpack(dwk, out=sink.buf(s["conv"] + ".weight", (Co, Ci, 5)))
+            sink.done(s["conv"] + ".weight")
             # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero (BN removes the mean)
-            grads[s["conv"] + ".bias"] = torch.zeros((C,), device=wk.device, dtype=torch.float32)
+            sink.buf(s["conv"] + ".bias", (C,))
+            sink.done(s["conv"] + ".bias")
             if i > 0 or need_dx:
                 dout = ops.conv5_dgrad(dt, dy, wk)
             else:
                 dout = None
         return dout
 
-    def _lstm_bwd(self, W, prefix: str, dh: Tensor, saved_layers: list, grads: Dict[str, Tensor], need_dx: bool):
+    def _lstm_bwd(self, W, prefix: str, dh: Tensor, saved_layers: list, sink: GradSink, need_dx: bool):
         dt = self.dt
         for l in range(len(saved_layers) - 1, -1, -1):
             s = saved_layers[l]
@@ -224,18 +262,32 @@ class Engine:
             In = lw["In"]
             da = ops.lstm_bwd(dt, dh.reshape(rows, T, D * H), s["gates"], s["c_all"], lw["whh_n"], H, D)
             da2 = da.view(rows * T, D * 4 * H)
-            dwih = torch.zeros((D * 4 * H, In), device=da.device, dtype=torch.float32)
-            ops.linear_wgrad(dt, da2, s["x_in"].reshape(rows * T, In), dwih)
-            dwhh = torch.zeros((D, 4 * H, H), device=da.device, dtype=torch.float32)
-            ops.lstm_wgrad_hh(dt, da, s["h_all"], dwhh, H, D)
-            db = torch.zeros((D * 4 * H,), device=da.device, dtype=torch.float32)
-            ops.colsum(dt, da2, db)
-            for d in range(D):
-                suf = "_reverse" if d == 1 else ""
-                grads[f"{prefix}.weight_ih_l{l}{suf}"] = dwih[d * 4 * H:(d + 1) * 4 * H]
-                grads[f"{prefix}.weight_hh_l{l}{suf}"] = dwhh[d]
-                grads[f"{prefix}.bias_ih_l{l}{suf}"] = db[d * 4 * H:(d + 1) * 4 * H]
-                grads[f"{prefix}.bias_hh_l{l}{suf}"] = db[d * 4 * H:(d + 1) * 4 * H].clone()  # b_ih and b_hh: equal grads
+            x2 = s["x_in"].reshape(rows * T, In)
+            if D == 1:   # gradients land directly in their final buffers
+                n_ih, n_hh = f"{prefix}.weight_ih_l{l}", f"{prefix}.weight_hh_l{l}"
+                ops.linear_wgrad(dt, da2, x2, sink.buf(n_ih, (4 * H, In)))
+                sink.done(n_ih)
+                ops.lstm_wgrad_hh(dt, da, s["h_all"], sink.buf(n_hh, (4 * H, H)).view(1, 4 * H, H), H, 1)
+                sink.done(n_hh)
+                db = sink.buf(f"{prefix}.bias_ih_l{l}", (4 * H,))
+                ops.colsum(dt, da2, db)
+                sink.done(f"{prefix}.bias_ih_l{l}")
+                ops.copy_f32(db, sink.buf(f"{prefix}.bias_hh_l{l}", (4 * H,)))   # b_ih and b_hh: equal gradients
+                sink.done(f"{prefix}.bias_hh_l{l}")
+            else:        # both directions come out of one GEMM; slice per direction
+                dwih = torch.zeros((D * 4 * H, In), device=da.device, dtype=torch.float32)
+                ops.linear_wgrad(dt, da2, x2, dwih)
+                dwhh = torch.zeros((D, 4 * H, H), device=da.device, dtype=torch.float32)
+                ops.lstm_wgrad_hh(dt, da, s["h_all"], dwhh, H, D)
+                db = torch.zeros((D * 4 * H,), device=da.device, dtype=torch.float32)
+                ops.colsum(dt, da2, db)
+                for d in range(D):
+                    suf = "_reverse" if d == 1 else ""
+                    sl = slice(d * 4 * H, (d + 1) * 4 * H)
+                    sink.put(f"{prefix}.weight_ih_l{l}{suf}", dwih[sl])
+                    sink.put(f"{prefix}.weight_hh_l{l}{suf}", dwhh[d])
+                    sink.put(f"{prefix}.bias_ih_l{l}{suf}", db[sl])
+                    sink.put(f"{prefix}.bias_hh_l{l}{suf}", db[sl].clone())
             if l > 0 or need_dx:
                 dh, _ = ops.linear_dgrad(dt, da2, lw["wih_n"])
                 dh = dh.view(rows, T, In)
@@ -243,16 +295,14 @@ class Engine:
                 dh = None
         return dh
 
-    def _linear_bwd(self, name: str, W_act: Tensor, dy: Tensor, x: Tensor, grads, relu_mask=None, want_f32=False,
-                    need_dx: bool = True):
+    def _linear_bwd(self, name: str, W_act: Tensor, dy: Tensor, x: Tensor, sink: GradSink, relu_mask=None,
+                    want_f32=False, need_dx: bool = True):
         dt = self.dt
         N, K = W_act.shape
-        dw = torch.zeros((N, K), device=dy.device, dtype=torch.float32)
-        ops.linear_wgrad(dt, dy, x, dw)
-        db = torch.zeros((N,), device=dy.device, dtype=torch.float32)
-        ops.colsum(dt, dy, db)
-        grads[name + ".weight"] = dw
-        grads[name + ".bias"] = db
+        ops.linear_wgrad(dt, dy, x, sink.buf(name + ".weight", (N, K)))
+        sink.done(name + ".weight")
+        ops.colsum(dt, dy, sink.buf(name + ".bias", (N,)))
+        sink.done(name + ".bias")
         if not need_dx:
             return None
         dx, dx32 = ops.linear_dgrad(dt, dy, W_act, relu_mask=relu_mask, want_f32=want_f32, want_act=not want_f32)
@@ -266,7 +316,8 @@ class Engine:
         R = saved["R"]
         R2 = 2 * R
         dev = saved["heads"].device
-        grads: Dict[str, Tensor] = {}
+        sink = GradSink(dev, self.buckets)
+        grads = sink   # the helpers below take the sink
         g = [t.contiguous() if t is not None else None for t in gouts]
         # ---- residual output: recon_hat = recon + postnet(recon)  (:277-278)
         d_rec = torch.empty((R2, T_FRAMES, N_MELS), device=dev, dtype=ad)
@@ -295,10 +346,10 @@ class Engine:
         ops.linear_wgrad(dt, dheads, saved["e"], dw)
         db = torch.zeros((W.heads_w.shape[0],), device=dev, dtype=torch.float32)
         ops.colsum(dt, dheads, db)
-        grads["style.linear_layer.weight"], grads["content.linear_layer.weight"] = dw[:n_s], dw[n_s:]
-        grads["style.linear_layer.bias"], grads["content.linear_layer.bias"] = db[:n_s], db[n_s:]
+        sink.put("style.linear_layer.weight", dw[:n_s]), sink.put("content.linear_layer.weight", dw[n_s:])
+        sink.put("style.linear_layer.bias", db[:n_s]), sink.put("content.linear_layer.bias", db[n_s:])
         d_e, _ = ops.linear_dgrad(dt, dheads, W.heads_w, relu_mask=saved["e"])
         d_flat = self._linear_bwd("enc_linear.linear_layer", W.lin["enc_linear.linear_layer"], d_e, saved["flat"], grads)
         dh = self._lstm_bwd(W, "enc_lstm", d_flat.view(R2, T_FRAMES, 128), saved["enc_lstm"], grads, need_dx=True)
         self._conv_stack_bwd(W, dh, saved["enc_convs"], grads, 2, need_dx=False)
-        return grads
+        return sink.finish()

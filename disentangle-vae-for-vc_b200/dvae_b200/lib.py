@@ -41,6 +41,7 @@ _SIGNATURES = {
     # weight preparation / layout
     "dvae_prep_cast": [_i, _p, _p, _l, _p],
     "dvae_add_inplace": [_i, _p, _p, _l, _p],
+    "dvae_copy_f32": [_p, _p, _l, _p],
     "dvae_prep_conv_weight": [_i, _p, _p, _i, _i, _p],
     "dvae_conv_wgrad_unpack": [_p, _p, _i, _i, _p],
     "dvae_prep_lstm_weight": [_i, _p, _p, _i, _i, _i, _p],
@@ -95,7 +96,15 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched per C-ABI call (bench.py reports the total as `gpu_launches`)
+LAUNCHES = 0
+_LAUNCHES_PER_CALL = {"dvae_bn_train_fwd": 3, "dvae_bn_train_bwd": 3, "dvae_bn_eval_fwd": 2, "dvae_segment_ids_sorted": 3}
+_TIME_STEP_ARG = {"dvae_lstm_fwd": 6, "dvae_lstm_bwd": 8}   # index of T: one GEMM launch per time step
+
+
 def call(name, *args):
+    global LAUNCHES
+    LAUNCHES += args[_TIME_STEP_ARG[name]] if name in _TIME_STEP_ARG else _LAUNCHES_PER_CALL.get(name, 1)
     rc = _FUNCS[name](*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (status {rc}): {_lib.dvae_last_error().decode()}")

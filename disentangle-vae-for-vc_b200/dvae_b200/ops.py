@@ -135,6 +135,13 @@ def lstm_wgrad_hh(dt: int, da_all: Tensor, h_all: Tensor, dwhh: Tensor, H: int, 
 
 
 # ------------------------------------------------------------------------------- weight preparation
+def copy_f32(src: Tensor, dst: Tensor) -> None:
+    """fp32 device copy through the library (used to scatter gradient slices into bucket views)."""
+    _chk(src, torch.float32), _chk(dst, torch.float32)
+    assert src.numel() == dst.numel()
+    call("dvae_copy_f32", ptr(src), ptr(dst), src.numel(), stream())
+
+
 def prep_cast(dt: int, src: Tensor, dst: Tensor) -> None:
     _chk(src, torch.float32), _chk(dst, act_dtype(dt))
     assert src.numel() == dst.numel()
@@ -157,10 +164,12 @@ def prep_conv_weight(dt: int, w: Tensor) -> Tensor:
     return wk
 
 
-def conv_wgrad_unpack(dwk: Tensor) -> Tensor:
+def conv_wgrad_unpack(dwk: Tensor, out: Optional[Tensor] = None) -> Tensor:
     _chk(dwk, torch.float32)
     Co, k, Ci = dwk.shape
-    dw = torch.empty((Co, Ci, 5), device=dwk.device, dtype=torch.float32)
+    dw = out if out is not None else torch.empty((Co, Ci, 5), device=dwk.device, dtype=torch.float32)
+    _chk(dw, torch.float32)
+    assert tuple(dw.shape) == (Co, Ci, 5)
     call("dvae_conv_wgrad_unpack", ptr(dwk), ptr(dw), Co, Ci, stream())
     return dw
 
@@ -236,7 +245,8 @@ def bn_eval_fwd(dt: int, y: Tensor, gamma: Tensor, beta: Tensor, run_mean: Tenso
     return out
 
 
-def bn_train_bwd(dt: int, dout: Tensor, y: Tensor, stat: Tensor, halves: int, act: int):
+def bn_train_bwd(dt: int, dout: Tensor, y: Tensor, stat: Tensor, halves: int, act: int,
+                 dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None):
     """Returns (dy act [rows,C], dgamma fp32 [C], dbeta fp32 [C])."""
     ad = act_dtype(dt)
     _chk(dout, ad), _chk(y, ad), _chk(stat, torch.float32)
@@ -245,8 +255,8 @@ def bn_train_bwd(dt: int, dout: Tensor, y: Tensor, stat: Tensor, halves: int, ac
     dy = torch.empty_like(y)
     ws = torch.empty((halves * 2 * C,), device=y.device, dtype=torch.float64)
     coef = torch.empty((halves * 2 * C,), device=y.device, dtype=torch.float32)
-    dgamma = torch.empty((C,), device=y.device, dtype=torch.float32)
-    dbeta = torch.empty((C,), device=y.device, dtype=torch.float32)
+    dgamma = dgamma if dgamma is not None else torch.empty((C,), device=y.device, dtype=torch.float32)
+    dbeta = dbeta if dbeta is not None else torch.empty((C,), device=y.device, dtype=torch.float32)
     call("dvae_bn_train_bwd", dt, ptr(dout), ptr(y), ptr(stat), ptr(ws), ptr(coef), ptr(dy), ptr(dgamma), ptr(dbeta),
          rows // halves, halves, C, act, stream())
     return dy, dgamma, dbeta

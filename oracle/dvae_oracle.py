@@ -210,7 +210,8 @@ def lstm(sd: SD, x: Tensor, prefix: str, num_layers: int, bidirectional: bool) -
             for nm in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
                 flat.append(sd[f"{prefix}.{nm}_l{layer}{suf}"])
     h0 = x.new_zeros(num_layers * dirs, R, hid)
-    out, _, _ = torch.lstm(x, (h0, h0.clone()), flat, True, num_layers, 0.0, False, bidirectional, True)
+    # `train` only matters to cuDNN (its backward refuses inference-mode graphs); dropout is 0 either way
+    out, _, _ = torch.lstm(x, (h0, h0.clone()), flat, True, num_layers, 0.0, torch.is_grad_enabled(), bidirectional, True)
     return out
 
 
