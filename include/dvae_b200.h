@@ -1,0 +1,113 @@
+/* dvae_b200 -- C-ABI of the B200 (sm_100a) Disentangled-VAE hot path.
+ *
+ * The reference (v-manhlt3/Disentangle-VAE-for-VC) has no FFI layer: its boundary is the Python class API of
+ * model/disentangled_vae.py and model/variational_base_vae.py, which reaches the GPU through torch.nn (cuDNN/cuBLAS).
+ * This header is what replaces those library calls.  Each entry point names the reference call site(s) it stands in
+ * for (paths relative to the reference root).  The Python host side (disentangle-vae-for-vc_b200/dvae_b200/lib.py)
+ * binds exactly these symbols with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions: plain pointers + sizes, no allocation inside, no implicit synchronisation, everything is enqueued on
+ * `stream` (a cudaStream_t passed as void*).  Return 0 = ok, 1 = invalid argument, 2 = CUDA error; the message is in
+ * dvae_last_error() (thread local).  `dtype` tags the activation storage: 0 = bf16 (tcgen05 kind::f16),
+ * 1 = fp32 kept on the tf32 grid (tcgen05 kind::tf32).  "act" below means that storage type.  Activations are
+ * channels-last [rows, T, C]; T = 64 (model/disentangled_vae.py:165,235).
+ */
+#ifndef DVAE_B200_H
+#define DVAE_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* dvae_last_error(void);
+int dvae_version(void);
+int dvae_sm_arch(void);              /* 100: built for sm_100a only */
+int dvae_lstm_gate_tile(int H);      /* gate-interleave tile (columns) used by the LSTM forward for hidden size H */
+
+/* ---- nn.Linear (model/disentangled_vae.py:98-100 LinearNorm.forward; :165-171, :194, :211-213, :232-233, :247) */
+int dvae_linear_fwd(int dtype, const void* x, long ldx, const void* w, const float* bias, void* out, float* out_f32,
+                    long ldo, int M, int N, int K, int relu, int block_n, void* stream);
+int dvae_linear_dgrad(int dtype, const void* dy, long lddy, const void* w, void* dx, float* dx_f32, const void* relu_mask,
+                      long ldx, int M, int N, int K, int block_n, void* stream);
+int dvae_linear_wgrad(int dtype, const void* dy, long lddy, const void* x, long ldx, float* dw, long lddw, int M, int N,
+                      int K, void* stream);
+
+/* ---- nn.Conv1d k=5 pad=2 (ConvNorm.forward :119-121; enc :154-160/:201-202, dec :178-189/:242-243, postnet :54-78/:81-87)
+ *      x [R,T,Cin] act, wk [Cout,5,Cin] act (dvae_prep_conv_weight), y [R,T,Cout] */
+int dvae_conv5_fwd(int dtype, const void* x, const void* wk, const float* bias, void* y, float* y_f32, int R, int T, int Cin,
+                   int Cout, void* stream);
+int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,
+                     void* stream);
+int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R, int T, int Cin, int Cout, void* stream);
+
+/* ---- nn.LSTM recurrence (:163/:208 enc_lstm, :172/:238 dec_lstm1, :193/:246 dec_lstm2); the input projection is a
+ *      dvae_linear_fwd with gate-interleaved weights.  xg [rows,T,D*4H] in: projection, out: activated gates */
+int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_all, int rows, int T, int H, int D,
+                  void* stream);
+int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all,
+                  float* dc_ws, int rows, int T, int H, int D, void* stream);
+int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* dwhh, int rows, int T, int H, int D,
+                       void* stream);
+
+/* ---- parameter re-layout (replaces cuDNN's internal filter transforms / flatten_parameters :206) */
+int dvae_prep_cast(int dtype, const float* src, void* dst, long n, void* stream);
+int dvae_copy_f32(const float* src, float* dst, long n, void* stream);
+int dvae_add_inplace(int dtype, void* a, const void* b, long n, void* stream);
+int dvae_prep_conv_weight(int dtype, const float* w, void* wk, int Co, int Ci, void* stream);
+int dvae_conv_wgrad_unpack(const float* dwk, float* dw, int Co, int Ci, void* stream);
+int dvae_prep_lstm_weight(int dtype, const float* w, void* dst, int H, int In, int tile, void* stream);
+int dvae_prep_lstm_bias(const float* b_ih, const float* b_hh, float* dst, int H, int tile, void* stream);
+
+/* ---- layout: NCL fp32 <-> channels-last act (the transposes at :204, :240, :244, :248), residual output :277-278 */
+int dvae_pack_ncl_to_cl(int dtype, const float* x, void* y, int R, int C, int T, void* stream);
+int dvae_unpack_cl_to_ncl(int dtype, const void* a, int a_is_f32, const void* b, float* out_a, float* out_sum, int R, int C,
+                          int T, void* stream);
+int dvae_recon_out_bwd(int dtype, const float* g_rec, const float* g_hat, void* d_rec, void* d_post, int R, int C, int T,
+                       void* stream);
+
+/* ---- nn.BatchNorm1d + activation (:159 / :182,:189 / :58,:69,:78 with F.relu :202,:243 and torch.tanh :83) */
+int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
+                      float* run_var, long long* num_batches, double* ws, float* stat, int rows_half, int halves, int C,
+                      int act, float eps, float momentum, void* stream);
+int dvae_bn_eval_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, const float* run_mean,
+                     const float* run_var, float* stat, long rows, int C, int act, float eps, void* stream);
+int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* stat, double* ws, float* coef, void* dy,
+                      float* dgamma, float* dbeta, int rows_half, int halves, int C, int act, void* stream);
+int dvae_colsum(int dtype, const void* x, float* out, long rows, int C, long ldx, void* stream);
+
+/* ---- latent tail: _reparameterize :222-228, pair-mean style posterior with detach :257-261, concatenations :263-272 */
+int dvae_latent_tail_fwd(int dtype, const float* heads, const float* eps_c1, const float* eps_c2, const float* eps_s,
+                         void* z, float* q1_mu, float* q1_lv, float* q2_mu, float* q2_lv, float* zs_mu, float* zs_lv, int R,
+                         int L, int S, int sample_content, void* stream);
+int dvae_latent_tail_bwd(int dtype, const float* heads, const float* eps_c1, const float* eps_c2, const float* eps_s,
+                         const float* dz, const float* dq1_mu, const float* dq1_lv, const float* dq2_mu, const float* dq2_lv,
+                         const float* dzs_mu, const float* dzs_lv, void* dheads, int R, int L, int S, int sample_content,
+                         void* stream);
+
+/* ---- ConvolutionalMulVAE.loss_functionGVAE2 :310-327 (4 x L1-sum/batch_size, 2 x KL, style KL, total) */
+int dvae_loss_fwd(const float* x1, const float* x2, const float* r1, const float* r2, const float* h1, const float* h2, long n,
+                  const float* q1_mu, const float* q1_lv, const float* q2_mu, const float* q2_lv, int q_rows, int L,
+                  const float* s_mu, const float* s_lv, int S, float batch_size, float mse_cof, float kl_cof, void* ws,
+                  float* out, void* stream);
+int dvae_loss_bwd(const float* x1, const float* x2, const float* r1, const float* r2, const float* h1, const float* h2, long n,
+                  const float* q1_mu, const float* q1_lv, const float* q2_mu, const float* q2_lv, int q_rows, int L,
+                  const float* s_mu, const float* s_lv, int S, float batch_size, float mse_cof, float kl_cof,
+                  const float* gout, float* dr1, float* dr2, float* dh1, float* dh2, float* dq1_mu, float* dq1_lv,
+                  float* dq2_mu, float* dq2_lv, float* ds_mu, float* ds_lv, void* stream);
+
+/* ---- speaker-group ops keyed by a group id per row: model/utils.py:13-75 accumulate_group_evidence (mode 0),
+ *      model/variational_base_vae.py:281-282 chunk mean (mode 1), raw segmented sums (mode 2),
+ *      model/utils.py:95-116 group_wise_reparameterize */
+int dvae_segment_ids_sorted(const long long* labels, int* gid, int* scratch, int* num_groups, long B, void* stream);
+int dvae_group_accumulate(int mode, const float* a, const float* b, const int* gid, float* acc, float* cnt, long B, int D,
+                          void* stream);
+int dvae_group_finalize(int mode, const float* acc, const float* cnt, const int* gid, float* out_a, float* out_b, long B,
+                        int D, void* stream);
+int dvae_group_pog_bwd(const float* mu, const float* logvar, const int* gid, const float* acc_f, const float* acc_g,
+                       float* dmu, float* dlv, long B, int D, void* stream);
+int dvae_group_reparam(const float* mu, const float* logvar, const int* gid, const float* eps_group, float* z, long B, int D,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVAE_B200_H */

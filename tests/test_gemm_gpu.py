@@ -32,7 +32,8 @@ def _rand(shape, name, scale=1.0, seed=0):
 
 def _tol(name, ref):
     # result rounding to the storage dtype + fp32 summation-order noise
-    return (2.0 ** -8 if name == "bf16" else 1e-5) * ref.abs().max().item() + 1e-6
+    # (bf16: 8 mantissa bits; tf32 storage is rounded onto the 10-bit tf32 grid when stored)
+    return (2.0 ** -8 if name == "bf16" else 2.0 ** -11) * ref.abs().max().item() + 1e-6
 
 
 @pytest.mark.parametrize("name", DTS)

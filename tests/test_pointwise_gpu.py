@@ -15,7 +15,11 @@ def _dt(name):
 
 
 def _act(t, name):
-    return t.to(torch.bfloat16) if name == "bf16" else t.float()
+    """Value as stored by the library: bf16 (RNE) or fp32 rounded to the tf32 grid (cvt.rna: 10 mantissa bits)."""
+    if name == "bf16":
+        return t.to(torch.bfloat16)
+    bits = t.float().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
 @pytest.mark.parametrize("name", DTS)
@@ -60,7 +64,7 @@ def test_batchnorm_train(name, C, act):
     for h in range(halves):   # two consecutive BatchNorm calls (x1 then x2): per-call statistics
         refs.append(fn(F.batch_norm(yr[h * R * T:(h + 1) * R * T], rm_r, rv_r, gr, br, True, 0.1, 1e-5)))
     ref = torch.cat(refs)
-    tol = 2.0 ** -7 if name == "bf16" else 2e-5
+    tol = 2.0 ** -7 if name == "bf16" else 2.0 ** -10
     assert (out.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
     assert torch.allclose(rm, rm_r, atol=1e-5) and torch.allclose(rv, rv_r, atol=1e-5, rtol=1e-5)
     assert int(nbt.item()) == halves
@@ -68,7 +72,7 @@ def test_batchnorm_train(name, C, act):
     ref.backward(dout.float())
     dy, dgamma, dbeta = ops.bn_train_bwd(dt, dout, y, stat, halves, act)
     rel = lambda a, b: (a.float() - b).norm().item() / (b.norm().item() + 1e-12)
-    assert rel(dy, yr.grad) <= (1e-2 if name == "bf16" else 1e-4)
+    assert rel(dy, yr.grad) <= (1e-2 if name == "bf16" else 1e-3)
     assert rel(dgamma, gr.grad) <= 1e-4 and rel(dbeta, br.grad) <= 1e-4
 
 
@@ -82,7 +86,7 @@ def test_batchnorm_eval_and_colsum(name):
     rm, rv = torch.randn(C, device="cuda") * 0.1, torch.rand(C, device="cuda") + 0.5
     out = ops.bn_eval_fwd(dt, y, gamma, beta, rm, rv, 2, 1e-5)
     ref = torch.tanh(F.batch_norm(y.float(), rm, rv, gamma, beta, False, 0.1, 1e-5))
-    assert (out.float() - ref).abs().max().item() <= (2.0 ** -7 if name == "bf16" else 2e-5)
+    assert (out.float() - ref).abs().max().item() <= (2.0 ** -7 if name == "bf16" else 2.0 ** -10)
     for Cc in (80, 512, 4096):
         x = _act(torch.randn(1000, Cc, device="cuda"), name)
         acc = torch.ones(Cc, device="cuda")
@@ -109,7 +113,7 @@ def test_latent_tail(name, sample):
     zst = e3 * torch.exp(0.5 * zlv) + zmu
     z_ref = torch.cat([torch.cat([zst, zc1], -1), torch.cat([zst, zc2], -1)], 0)
     q_ref = [torch.cat([zmu, cmu1], -1), torch.cat([zlv, clv1], -1), torch.cat([zmu, cmu2], -1), torch.cat([zlv, clv2], -1)]
-    assert (z.float() - z_ref).abs().max().item() <= (2.0 ** -7 * 4 if name == "bf16" else 1e-5)
+    assert (z.float() - z_ref).abs().max().item() <= (2.0 ** -7 * 4 if name == "bf16" else 2.0 ** -10 * 4)
     for a, b in zip(q + zs, q_ref + [zmu, zlv]):
         assert torch.allclose(a, b, atol=1e-6)
     dz = torch.randn(2 * R, L, device="cuda")
@@ -118,7 +122,7 @@ def test_latent_tail(name, sample):
     loss = (z_ref * dz).sum() + sum((a * b).sum() for a, b in zip(q_ref + [zmu, zlv], dq + dzs))
     loss.backward()
     dheads = ops.latent_tail_bwd(dt, heads, e1, e2, e3, dz, dq, dzs, R, L, S, sample)
-    assert (dheads.float() - hr.grad).abs().max().item() <= (2.0 ** -7 * hr.grad.abs().max().item() if name == "bf16" else 1e-5)
+    assert (dheads.float() - hr.grad).abs().max().item() <= (2.0 ** -7 if name == "bf16" else 2.0 ** -10) * hr.grad.abs().max().item()
     assert dheads[R:, :2 * S].abs().max().item() == 0.0     # member 2's style is detached (model/disentangled_vae.py:257)
 
 
