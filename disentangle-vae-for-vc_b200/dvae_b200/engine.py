@@ -226,6 +226,25 @@ class Engine:
         outs = (recon[:R], recon[R:], hat[:R], hat[R:], q[0], q[1], q[2], q[3], zs[0], zs[1])
         return outs, saved
 
+    @staticmethod
+    def discrete_decisions(saved: dict, outs, x1: Tensor, x2: Tensor) -> dict:
+        """The branch decisions this forward took at the network's kinks: ReLU masks (reference layout [R, C, T] per
+        call) and the signs of the L1 loss.  Parity tests hand them to the checker so that gradient comparisons are
+        made at matched decisions (plain tensor bookkeeping, not part of the compute path)."""
+        R = saved["R"]
+        d = {}
+        for group, key in (("enc_convs", "enc_modules"), ("dec_convs", "dec_modules")):
+            for i, s in enumerate(saved[group]):
+                y, st = s["y"].float(), s["stat"]
+                for call in range(2):
+                    z = y[call * R:(call + 1) * R] * st[call, 2] + st[call, 3]
+                    d[f"{key}.{i}:{call}"] = (z > 0).transpose(1, 2)
+        e = saved["e"].float()
+        d["enc_linear:0"], d["enc_linear:1"] = e[:R] > 0, e[R:] > 0
+        d["l1_signs"] = [torch.sign(outs[0] - x1), torch.sign(outs[1] - x2), torch.sign(outs[2] - x1),
+                         torch.sign(outs[3] - x2)]
+        return d
+
     # ------------------------------------------------------------------ building blocks (backward)
     def _conv_stack_bwd(self, W, dout: Tensor, saved_layers: list, sink: GradSink, halves: int, need_dx: bool):
         dt = self.dt

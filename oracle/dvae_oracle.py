@@ -194,6 +194,18 @@ def conv_bn(sd: SD, x: Tensor, conv_prefix: str, bn_prefix: str, training: bool)
                         training, BN_MOMENTUM, BN_EPS)
 
 
+def relu_at(x: Tensor, decisions: Optional[dict], key: str) -> Tensor:
+    """F.relu, or -- in matched-decision mode -- multiplication by a supplied 0/1 mask.
+
+    ReLU (and the L1 loss) are kinks: two forwards that differ by rounding take different branches on a small fraction
+    of elements, and the gradients then differ by O(sqrt(fraction)) no matter how good the arithmetic is.  Gradient
+    parity tests therefore evaluate the oracle AT THE CANDIDATE'S discrete decisions (`decisions[key]`), which makes
+    the oracle's backward a smooth function of the forward values."""
+    if decisions is None or key not in decisions:
+        return F.relu(x)
+    return x * decisions[key].to(x.dtype)
+
+
 def lstm(sd: SD, x: Tensor, prefix: str, num_layers: int, bidirectional: bool) -> Tensor:
     """batch_first LSTM with zero initial state (torch gate order i,f,g,o; two bias vectors).
 
@@ -248,22 +260,24 @@ def linear(sd: SD, x: Tensor, prefix: str) -> Tensor:
 # --------------------------------------------------------------------------------------
 # Network pieces (model/disentangled_vae.py)
 # --------------------------------------------------------------------------------------
-def encode(sd: SD, x: Tensor, training: bool, speaker_size: int = 4, latent_dim: int = 32):
+def encode(sd: SD, x: Tensor, training: bool, speaker_size: int = 4, latent_dim: int = 32,
+           decisions: Optional[dict] = None, call: int = 0):
     """DisentangledVAE.encode, model/disentangled_vae.py:198-220."""
     R = x.shape[0]
     for i in range(3):
-        x = F.relu(conv_bn(sd, x, f"enc_modules.{i}.0.conv", f"enc_modules.{i}.1", training))
+        x = relu_at(conv_bn(sd, x, f"enc_modules.{i}.0.conv", f"enc_modules.{i}.1", training), decisions,
+                    f"enc_modules.{i}:{call}")
     x = x.transpose(1, 2)                                     # :204  [R,64,512]
     out = lstm(sd, x, "enc_lstm", 2, True)                    # :208  [R,64,128]
     out = out.reshape(R, -1)                                  # :209  time-major flatten
-    out = F.relu(linear(sd, out, "enc_linear.linear_layer"))  # :211
+    out = relu_at(linear(sd, out, "enc_linear.linear_layer"), decisions, f"enc_linear:{call}")  # :211
     style = linear(sd, out, "style.linear_layer")             # :212
     content = linear(sd, out, "content.linear_layer")         # :213
     S, L = speaker_size, latent_dim
     return style[:, :S], style[:, S:], content[:, :L - S], content[:, L - S:]
 
 
-def decode(sd: SD, z: Tensor, training: bool) -> Tensor:
+def decode(sd: SD, z: Tensor, training: bool, decisions: Optional[dict] = None, call: int = 0) -> Tensor:
     """DisentangledVAE.decode, model/disentangled_vae.py:230-248."""
     R = z.shape[0]
     out = linear(sd, z, "dec_pre_linear1")
@@ -272,7 +286,8 @@ def decode(sd: SD, z: Tensor, training: bool) -> Tensor:
     out = lstm(sd, out, "dec_lstm1", 1, False)                # :238 [R,64,512]
     out = out.transpose(-1, -2)
     for i in range(3):
-        out = F.relu(conv_bn(sd, out, f"dec_modules.{i}.0", f"dec_modules.{i}.1", training))
+        out = relu_at(conv_bn(sd, out, f"dec_modules.{i}.0", f"dec_modules.{i}.1", training), decisions,
+                      f"dec_modules.{i}:{call}")
     out = out.transpose(-1, -2)
     out = lstm(sd, out, "dec_lstm2", 2, False)                # :246 [R,64,1024]
     out = linear(sd, out, "dec_linear2.linear_layer")         # :247 [R,64,80]
@@ -297,7 +312,7 @@ def reparameterize(mu: Tensor, logvar: Tensor, eps: Optional[Tensor]) -> Tensor:
 
 
 def forward(sd: SD, x1: Tensor, x2: Tensor, eps: Sequence[Tensor], training: bool = True,
-            sample_content: bool = True, speaker_size: int = 4, latent_dim: int = 32):
+            sample_content: bool = True, speaker_size: int = 4, latent_dim: int = 32, decisions: Optional[dict] = None):
     """DisentangledVAE.forward, model/disentangled_vae.py:250-279 -> the 10-tuple.
 
     `eps` = [eps_content1, eps_content2, eps_style] in the reference's draw order.
@@ -305,9 +320,9 @@ def forward(sd: SD, x1: Tensor, x2: Tensor, eps: Sequence[Tensor], training: boo
     forward (content noise on/off).  The style noise is always applied (:261).
     Mutates the BN buffers in `sd` exactly like the reference (x1 call first, then x2: F5).
     """
-    s_mu1, s_lv1, c_mu1, c_lv1 = encode(sd, x1, training, speaker_size, latent_dim)
+    s_mu1, s_lv1, c_mu1, c_lv1 = encode(sd, x1, training, speaker_size, latent_dim, decisions, 0)
     z_c1 = reparameterize(c_mu1, c_lv1, eps[0] if sample_content else None)
-    s_mu2, s_lv2, c_mu2, c_lv2 = encode(sd, x2, training, speaker_size, latent_dim)
+    s_mu2, s_lv2, c_mu2, c_lv2 = encode(sd, x2, training, speaker_size, latent_dim, decisions, 1)
     z_c2 = reparameterize(c_mu2, c_lv2, eps[1] if sample_content else None)
     s_mu2 = s_mu2.detach()                                    # :257
     s_lv2 = s_lv2.detach()                                    # :258
@@ -320,21 +335,25 @@ def forward(sd: SD, x1: Tensor, x2: Tensor, eps: Sequence[Tensor], training: boo
     q1_lv = torch.cat((z_s_lv, c_lv1), dim=-1)
     q2_mu = torch.cat((z_s_mu, c_mu2), dim=-1)
     q2_lv = torch.cat((z_s_lv, c_lv2), dim=-1)
-    r1 = decode(sd, z1, training)                             # :274
-    r2 = decode(sd, z2, training)                             # :275
+    r1 = decode(sd, z1, training, decisions, 0)               # :274
+    r2 = decode(sd, z2, training, decisions, 1)               # :275
     r1_hat = r1 + postnet(sd, r1, training)                   # :277
     r2_hat = r2 + postnet(sd, r2, training)                   # :278
     return r1, r2, r1_hat, r2_hat, q1_mu, q1_lv, q2_mu, q2_lv, z_s_mu, z_s_lv
 
 
 def loss_gvae2(x1, x2, r1, r2, r1_hat, r2_hat, q1_mu, q1_lv, q2_mu, q2_lv, s_mu, s_lv,
-               batch_size: int, mse_cof: float = 10.0, kl_cof: float = 10.0):
+               batch_size: int, mse_cof: float = 10.0, kl_cof: float = 10.0, signs: Optional[Sequence[Tensor]] = None):
     """ConvolutionalMulVAE.loss_functionGVAE2, model/disentangled_vae.py:310-327 -> 8-tuple.
 
     L1 sums are divided by the *constructor* batch_size; the style KL uses factor
     -1 and is reported only."""
-    l1 = lambda a, b: (a - b).abs().sum() / batch_size
-    m1, m2, m1h, m2h = l1(x1, r1), l1(x2, r2), l1(x1, r1_hat), l1(x2, r2_hat)
+    if signs is None:
+        l1 = lambda a, b, _s: (a - b).abs().sum() / batch_size
+        signs = [None] * 4
+    else:   # matched-decision mode (see relu_at): |b - a| written with the supplied sign(b - a)
+        l1 = lambda a, b, sg: (sg * (b - a)).sum() / batch_size
+    m1, m2, m1h, m2h = l1(x1, r1, signs[0]), l1(x2, r2, signs[1]), l1(x1, r1_hat, signs[2]), l1(x2, r2_hat, signs[3])
     kl = lambda mu, lv: -0.5 * torch.sum(1 + lv - mu.pow(2) - lv.exp(), dim=-1).mean()
     k1, k2 = kl(q1_mu, q1_lv), kl(q2_mu, q2_lv)
     ks = -1.0 * torch.sum(1 + s_lv - s_mu.pow(2) - s_lv.exp()) / batch_size
@@ -358,12 +377,13 @@ def clone_sd(sd: SD, requires_grad: bool = False, dtype=None, device=None) -> SD
 
 
 def train_step(sd: SD, x1, x2, eps, batch_size: int, mse_cof=10.0, kl_cof=10.0,
-               speaker_size: int = 4, latent_dim: int = 32):
+               speaker_size: int = 4, latent_dim: int = 32, decisions: Optional[dict] = None):
     """forward + loss + backward (the timed unit: model/variational_base_vae.py:62-68).
 
     `sd` floating tensors must be leaves with requires_grad.  Returns (fwd10, loss8, grads)."""
-    out = forward(sd, x1, x2, eps, True, True, speaker_size, latent_dim)
-    losses = loss_gvae2(x1, x2, *out, batch_size=batch_size, mse_cof=mse_cof, kl_cof=kl_cof)
+    out = forward(sd, x1, x2, eps, True, True, speaker_size, latent_dim, decisions)
+    losses = loss_gvae2(x1, x2, *out, batch_size=batch_size, mse_cof=mse_cof, kl_cof=kl_cof,
+                        signs=None if decisions is None else decisions.get("l1_signs"))
     names = [k for k, v in sd.items() if v.requires_grad]
     grads = torch.autograd.grad(losses[0], [sd[k] for k in names], allow_unused=True)
     return out, losses, dict(zip(names, grads))
