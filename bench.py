@@ -290,7 +290,7 @@ def run_ours(args):
                    "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                    "weights": "random init (reference initialisers), no checkpoint"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
-        "gpu_launches": launches * args.steps,
+        "gpu_launches": launches,
         "roofline": roofline,
         "step_tensor_frac": {"algorithmic_tflop_per_step": step_flops / 1e12, "achieved_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,
                              "of_sustained_peak": step_frac},

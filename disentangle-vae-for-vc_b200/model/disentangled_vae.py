@@ -92,6 +92,8 @@ class _NetworkFn(torch.autograd.Function):
         P, B = module._param_dict(), module._buffer_dict()
         outs, saved = module._engine.forward(W, P, B, x1, x2, (e1, e2, e3), module.training, sample_content, keep)
         ctx.engine, ctx.W, ctx.saved, ctx.names = module._engine, W, saved, module._param_names
+        if module._debug_keep_saved:
+            module._last_saved = saved      # diagnostics / parity tests only
         return outs
 
     @staticmethod
@@ -146,6 +148,8 @@ class DisentangledVAE(nn.Module):
         self._param_names = [n for n, _ in self.named_parameters()]
         self._prep_cache = None
         self.noise_hook = None
+        self._debug_keep_saved = False
+        self._last_saved = None
 
     # ------------------------------------------------------------------ plumbing
     def _param_dict(self):
