@@ -13,6 +13,8 @@
 // Linear :165-171,:194.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "host_common.h"
 #include "tc_gemm.cuh"
 
@@ -215,7 +217,26 @@ template <int H>
 struct LstmFwdBN {
   static constexpr int value = (4 * H >= 512) ? 128 : 256;  // H=64 -> one 256-wide tile holds all 4 gates of 64 units
 };
-static int lstm_fwd_bn(int H) { return H == 64 ? 256 : 128; }
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+// Gate tile of the forward recurrence (columns of one N tile = [i|f|g|o] x tile/4 hidden units).  Tunable for sweeps via
+// DVAE_LSTM_FWD_TILE / DVAE_LSTM_FWD_TILE_SMALL (read once; the weight permutation follows dvae_lstm_gate_tile()).
+static int lstm_fwd_bn(int H) {
+  static const int big = env_int("DVAE_LSTM_FWD_TILE", 128);
+  static const int small = env_int("DVAE_LSTM_FWD_TILE_SMALL", 256);
+  int t = (H == 64) ? small : big;
+  if (t != 64 && t != 128 && t != 256) t = 128;
+  while (t > 4 * H) t >>= 1;
+  return t;
+}
+static int lstm_bwd_bn(int H) {
+  static const int v = env_int("DVAE_LSTM_BWD_TILE", 64);
+  int t = (v == 64 || v == 128 || v == 256) ? v : 64;
+  while (t > H) t >>= 1;
+  return t;
+}
 
 template <typename AT>
 static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows, int T, int H, int D, cudaStream_t st) {
@@ -247,8 +268,9 @@ static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows
     ep.z_c_out = H + (long)(tr - tf) * D * H;
     ep.z_h = H + (long)(tr - tf) * D * H;
     dim3 grid(ceil_div(rows, 128), 4 * H / BN, D);
-    int e = (BN == 256) ? launch_gemm<256, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
-                        : launch_gemm<128, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    int e = (BN == 256)   ? launch_gemm<256, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+            : (BN == 128) ? launch_gemm<128, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                          : launch_gemm<64, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
     if (e) return e;
   }
   return 0;
@@ -262,7 +284,7 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
                       int rows, int T, int H, int D, cudaStream_t st) {
   constexpr int EB = sizeof(AT);
   constexpr int BK = 128 / EB;
-  constexpr int BN = 64;
+  const int BN = lstm_bwd_bn(H);
   DVAE_REQUIRE(H % 64 == 0 && (D == 1 || D == 2), "H must be a multiple of 64; D in {1,2}");
   CUtensorMap ta, tb;
   if (int e = encode_map3(&ta, da_all, EB, (uint64_t)D * 4 * H, T, rows, (uint64_t)D * 4 * H * EB,
@@ -292,7 +314,10 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
     ep.z_a = 4 * H + (long)(tr - tf) * D * 4 * H;
     ep.H = H; ep.fwd_units = lstm_fwd_bn(H) / 4; ep.dc_zero = (s == 0);
     dim3 grid(ceil_div(rows, 128), H / BN, D);
-    if (int e = launch_gemm<BN, false, true, EB, EpiLstmBwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)) return e;
+    int e = (BN == 256)   ? launch_gemm<256, false, true, EB, EpiLstmBwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+            : (BN == 128) ? launch_gemm<128, false, true, EB, EpiLstmBwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                          : launch_gemm<64, false, true, EB, EpiLstmBwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    if (e) return e;
   }
   return 0;
 }

@@ -251,23 +251,30 @@ __device__ __forceinline__ float act_grad_from_z(float z, int act) {
   return 1.f;
 }
 
-// out = act(y * scale[h] + shift[h])
+// out = act(y * scale[h] + shift[h]).  Block = 64 rows x C channels; a thread keeps the affine constants of its
+// 8 channels in registers and walks down its row lane, so the kernel is pure streaming (16-byte loads / stores).
 template <typename AT>
 __global__ void bn_apply_kernel(const AT* __restrict__ y, AT* __restrict__ out, const float* __restrict__ stat, long rows,
                                 int rows_half, int C, int act) {
   const int tpr = C >> 3;
-  const long total = rows * tpr;
-  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long row = i / tpr;
-    const int cg = static_cast<int>(i - row * tpr);
-    const int h = static_cast<int>(row / rows_half);
-    const float* sc = stat + (h * 4 + 2) * C + cg * 8;
-    const float* sh = stat + (h * 4 + 3) * C + cg * 8;
-    float v[8];
-    Act8<AT>::load(y + row * C + cg * 8, v);
+  const int lanes = blockDim.x / tpr;
+  const int rl = threadIdx.x / tpr, cg = threadIdx.x - rl * tpr;
+  if (rl >= lanes) return;
+  const long row0 = static_cast<long>(blockIdx.x) * kBnRowsPerBlock;
+  const int h = static_cast<int>(row0 / rows_half);
+  float sc[8], sh[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = apply_act(fmaf(v[k], __ldg(sc + k), __ldg(sh + k)), act);
-    Act8<AT>::store(out + row * C + cg * 8, v);
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = stat[(h * 4 + 2) * C + cg * 8 + k];
+    sh[k] = stat[(h * 4 + 3) * C + cg * 8 + k];
+  }
+  const long rend = min(rows, row0 + kBnRowsPerBlock);
+  for (long r = row0 + rl; r < rend; r += lanes) {
+    float v[8];
+    Act8<AT>::load(y + r * C + cg * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = apply_act(fmaf(v[k], sc[k], sh[k]), act);
+    Act8<AT>::store(out + r * C + cg * 8, v);
   }
 }
 
@@ -332,30 +339,40 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, float* _
   dgamma[c] = static_cast<float>(dg);
   dbeta[c] = static_cast<float>(db);
 }
-// backward pass 2: dy = scale * (dz - mean(dz) - xhat * mean(dz*xhat))
+// backward pass 2: dy = scale * (dz - mean(dz) - xhat * mean(dz*xhat)); same streaming structure as bn_apply_kernel
 template <typename AT>
 __global__ void bn_bwd_apply_kernel(const AT* __restrict__ dout, const AT* __restrict__ y, const float* __restrict__ stat,
                                     const float* __restrict__ coef, AT* __restrict__ dy, long rows, int rows_half, int C,
                                     int act) {
   const int tpr = C >> 3;
-  const long total = rows * tpr;
-  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const long row = i / tpr;
-    const int cg = static_cast<int>(i - row * tpr);
-    const int h = static_cast<int>(row / rows_half);
-    const int c0 = cg * 8;
+  const int lanes = blockDim.x / tpr;
+  const int rl = threadIdx.x / tpr, cg = threadIdx.x - rl * tpr;
+  if (rl >= lanes) return;
+  const long row0 = static_cast<long>(blockIdx.x) * kBnRowsPerBlock;
+  const int h = static_cast<int>(row0 / rows_half);
+  const int c0 = cg * 8;
+  float mean[8], rstd[8], sc[8], sh[8], k0[8], k1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    mean[k] = stat[(h * 4 + 0) * C + c0 + k];
+    rstd[k] = stat[(h * 4 + 1) * C + c0 + k];
+    sc[k] = stat[(h * 4 + 2) * C + c0 + k];
+    sh[k] = stat[(h * 4 + 3) * C + c0 + k];
+    k0[k] = coef[(h * 2 + 0) * C + c0 + k];
+    k1[k] = coef[(h * 2 + 1) * C + c0 + k];
+  }
+  const long rend = min(rows, row0 + kBnRowsPerBlock);
+  for (long r = row0 + rl; r < rend; r += lanes) {
     float v[8], d[8];
-    Act8<AT>::load(y + row * C + c0, v);
-    Act8<AT>::load(dout + row * C + c0, d);
+    Act8<AT>::load(y + r * C + c0, v);
+    Act8<AT>::load(dout + r * C + c0, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float mean = __ldg(stat + (h * 4 + 0) * C + c0 + k), rstd = __ldg(stat + (h * 4 + 1) * C + c0 + k);
-      const float sc = __ldg(stat + (h * 4 + 2) * C + c0 + k), sh = __ldg(stat + (h * 4 + 3) * C + c0 + k);
-      const float dz = d[k] * act_grad_from_z(fmaf(v[k], sc, sh), act);
-      const float xh = (v[k] - mean) * rstd;
-      d[k] = sc * (dz - __ldg(coef + (h * 2 + 0) * C + c0 + k) - xh * __ldg(coef + (h * 2 + 1) * C + c0 + k));
+      const float dz = d[k] * act_grad_from_z(fmaf(v[k], sc[k], sh[k]), act);
+      const float xh = (v[k] - mean[k]) * rstd[k];
+      d[k] = sc[k] * (dz - k0[k] - xh * k1[k]);
     }
-    Act8<AT>::store(dy + row * C + c0, d);
+    Act8<AT>::store(dy + r * C + c0, d);
   }
 }
 
@@ -502,7 +519,7 @@ int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, c
   DISPATCH_AT(dtype, bn_stats_kernel<AT><<<rows / kBnRowsPerBlock, threads, smem, st>>>((const AT*)y, ws, rows_half, C));
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, gamma, beta, stat, run_mean, run_var, num_batches, halves, C,
                                                         static_cast<double>(rows_half), eps, momentum);
-  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<grid_for(rows * tpr, 256), 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half, C, act));
+  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<rows / kBnRowsPerBlock, threads, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half, C, act));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -513,7 +530,8 @@ int dvae_bn_eval_fwd(int dtype, const void* y, void* out, const float* gamma, co
   bn_eval_stat_kernel<<<ceil_div(C, 128), 128, 0, st>>>(gamma, beta, run_mean, run_var, stat, C, eps);
   const int tpr = C / 8;
   const int rows_half = rows > 0x7fffffffL ? 0x7fffffff : static_cast<int>(rows);
-  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<grid_for(rows * tpr, 256), 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half > 0 ? rows_half : 1, C, act));
+  DVAE_REQUIRE(tpr <= 256, "C too large for one block");
+  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<ceil_div(rows, kBnRowsPerBlock), 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half > 0 ? rows_half : 1, C, act));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -529,7 +547,7 @@ int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* s
   const int smem = lanes * 2 * C * 4;
   DISPATCH_AT(dtype, bn_bwd_reduce_kernel<AT><<<rows / kBnRowsPerBlock, threads, smem, st>>>((const AT*)dout, (const AT*)y, stat, ws, rows_half, C, act));
   bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, coef, dgamma, dbeta, halves, C, static_cast<double>(rows_half));
-  DISPATCH_AT(dtype, bn_bwd_apply_kernel<AT><<<grid_for(rows * tpr, 256), 256, 0, st>>>((const AT*)dout, (const AT*)y, stat, coef, (AT*)dy, rows, rows_half, C, act));
+  DISPATCH_AT(dtype, bn_bwd_apply_kernel<AT><<<rows / kBnRowsPerBlock, threads, 0, st>>>((const AT*)dout, (const AT*)y, stat, coef, (AT*)dy, rows, rows_half, C, act));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
