@@ -25,10 +25,13 @@ struct Stages {
   static constexpr int value = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
 };
 
-template <int BN, bool A_MN, bool B_MN, int EB, class Epi>
+template <int BN, bool A_MN, bool B_MN, int EB, class Epi, int ST = Stages<BN>::value>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const OperandWalk& wa, const OperandWalk& wb,
                        const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream) {
-  constexpr int ST = Stages<BN>::value;
+  if (Epi::kFixup && shp.splits > 1 && (shp.splitk_ws == nullptr || shp.tickets == nullptr)) {
+    set_last_error("split-K with a full-sum epilogue needs a fix-up workspace and tickets");
+    return 1;
+  }
   auto kern = tc_gemm_kernel<BN, ST, A_MN, B_MN, EB, Epi>;
   constexpr int smem = gemm_smem_bytes<BN, ST>();
   static bool configured = false;  // one flag per template instantiation
@@ -225,7 +228,7 @@ static int env_int(const char* name, int dflt) {
 // DVAE_LSTM_FWD_TILE / DVAE_LSTM_FWD_TILE_SMALL (read once; the weight permutation follows dvae_lstm_gate_tile()).
 static int lstm_fwd_bn(int H) {
   static const int big = env_int("DVAE_LSTM_FWD_TILE", 128);
-  static const int small = env_int("DVAE_LSTM_FWD_TILE_SMALL", 256);
+  static const int small = env_int("DVAE_LSTM_FWD_TILE_SMALL", 64);
   int t = (H == 64) ? small : big;
   if (t != 64 && t != 128 && t != 256) t = 128;
   while (t > 4 * H) t >>= 1;
@@ -236,6 +239,15 @@ static int lstm_bwd_bn(int H) {
   int t = (v == 64 || v == 128 || v == 256) ? v : 64;
   while (t > H) t >>= 1;
   return t;
+}
+// split-K of the backward step GEMM (K = 4H is long, the grid is small): fill ~2 CTAs per SM, >= 4 k-blocks per split
+static int lstm_bwd_splits(int rows, int H, int D, int elem_bytes) {
+  static const int forced = env_int("DVAE_LSTM_BWD_SPLITS", 0);
+  const int tiles = ceil_div(rows, 128) * (H / lstm_bwd_bn(H)) * D;
+  const int num_kb = 4 * H / (128 / elem_bytes);
+  int s = forced > 0 ? forced : (2 * num_sms()) / (tiles > 0 ? tiles : 1);
+  if (s > num_kb / 4) s = num_kb / 4;
+  return s < 1 ? 1 : s;
 }
 
 template <typename AT>
@@ -281,7 +293,7 @@ static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows
 // natural-order copy [D][4H][H].  dc_ws: fp32 [D, rows, H] scratch.
 template <typename AT>
 static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, const AT* whh_n, AT* da_all, float* dc_ws,
-                      int rows, int T, int H, int D, cudaStream_t st) {
+                      float* splitk_ws, int* tickets, int rows, int T, int H, int D, cudaStream_t st) {
   constexpr int EB = sizeof(AT);
   constexpr int BK = 128 / EB;
   const int BN = lstm_bwd_bn(H);
@@ -297,7 +309,8 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
     OperandWalk wa = zero_walk(), wb = zero_walk();
     wa.base[1] = tf + 1; wa.per_j[0] = BK; wa.per_tile[2] = 128; wa.per_z[0] = 4 * H; wa.per_z[1] = (tr - 1) - (tf + 1);
     wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN; wb.per_z[2] = 1;
-    GemmShape shp{rows, H, s == 0 ? 0 : 4 * H / BK, 4 * H / BK, 1};
+    const int splits = (s == 0 || splitk_ws == nullptr) ? 1 : lstm_bwd_splits(rows, H, D, EB);
+    GemmShape shp{rows, H, s == 0 ? 0 : 4 * H / BK, 4 * H / BK, splits, splitk_ws, tickets};
     typename EpiLstmBwd<AT>::Params ep;
     ep.dh_out = dh_all + (long)tf * D * H;
     ep.gates = gates + (long)tf * D * 4 * H;
@@ -313,7 +326,7 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
     ep.z_dc = (long)rows * H;
     ep.z_a = 4 * H + (long)(tr - tf) * D * 4 * H;
     ep.H = H; ep.fwd_units = lstm_fwd_bn(H) / 4; ep.dc_zero = (s == 0);
-    dim3 grid(ceil_div(rows, 128), H / BN, D);
+    dim3 grid(ceil_div(rows, 128), H / BN, D * splits);
     int e = (BN == 256)   ? launch_gemm<256, false, true, EB, EpiLstmBwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
             : (BN == 128) ? launch_gemm<128, false, true, EB, EpiLstmBwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
                           : launch_gemm<64, false, true, EB, EpiLstmBwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -413,12 +426,24 @@ int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_
                  lstm_fwd_t<tf32_t>((tf32_t*)xg, (const tf32_t*)whh_p, (tf32_t*)h_all, c_all, rows, T, H, D, st));
 }
 
+// splitk_ws / tickets: fix-up workspace for the split-K backward step (sizes from dvae_lstm_bwd_workspace); may be
+// null (then no split-K).  tickets must be zero before the first use (they reset themselves afterwards).
 int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all,
-                  float* dc_ws, int rows, int T, int H, int D, void* stream) {
+                  float* dc_ws, float* splitk_ws, int* tickets, int rows, int T, int H, int D, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype,
-                 lstm_bwd_t<bf16>((const bf16*)dh_all, (const bf16*)gates, c_all, (const bf16*)whh_n, (bf16*)da_all, dc_ws, rows, T, H, D, st),
-                 lstm_bwd_t<tf32_t>((const tf32_t*)dh_all, (const tf32_t*)gates, c_all, (const tf32_t*)whh_n, (tf32_t*)da_all, dc_ws, rows, T, H, D, st));
+                 lstm_bwd_t<bf16>((const bf16*)dh_all, (const bf16*)gates, c_all, (const bf16*)whh_n, (bf16*)da_all, dc_ws, splitk_ws, tickets, rows, T, H, D, st),
+                 lstm_bwd_t<tf32_t>((const tf32_t*)dh_all, (const tf32_t*)gates, c_all, (const tf32_t*)whh_n, (tf32_t*)da_all, dc_ws, splitk_ws, tickets, rows, T, H, D, st));
+}
+// floats of fix-up workspace and number of tickets dvae_lstm_bwd wants for this shape (0 floats: no split-K)
+int dvae_lstm_bwd_workspace(int dtype, int rows, int H, int D, long* ws_floats, int* num_tickets) {
+  const int eb = dtype == kBF16 ? 2 : 4;
+  const int bn = lstm_bwd_bn(H);
+  const int tiles = ceil_div(rows, 128) * (H / bn) * D;
+  const int splits = lstm_bwd_splits(rows, H, D, eb);
+  *num_tickets = tiles;
+  *ws_floats = splits > 1 ? static_cast<long>(tiles) * splits * 128 * bn : 0;
+  return 0;
 }
 
 int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* dwhh, int rows, int T, int H, int D,

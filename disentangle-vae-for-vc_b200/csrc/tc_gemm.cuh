@@ -12,7 +12,11 @@
 // * the TMA box coordinates of k-block `kb` are an affine function of (j, tap, box, tile, z) described
 //   by OperandWalk.  Conv1d is an implicit GEMM: the 5 taps are 5 shifted reads of the same
 //   channels-last [R, T, C] tensor; rows that fall outside a sequence are zero-filled by TMA.
-// * split-K: gridDim.z = batches * splits, epilogue accumulates with red.global.add.
+// * split-K: gridDim.z = batches * splits.  Weight-gradient epilogues accumulate with red.global.add; epilogues that
+//   need the complete sum (LSTM cells, bias/activation stores) use an in-kernel fix-up: every split parks its fp32
+//   partial tile in a workspace, takes a ticket, and the LAST split to arrive adds the others and runs the epilogue.
+// * 8 epilogue warps (two per TMEM lane quarter, each owning half of the tile's columns); while the main loop runs
+//   they prefetch the epilogue's global operands into L2.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -22,7 +26,8 @@
 namespace dvae {
 
 constexpr int kBlockM = 128;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpilogueThreads = 256;
 constexpr int kSwizzleRow = 128;  // bytes per swizzle-128B row == BLOCK_K * ELEM_BYTES
 
 struct OperandWalk {
@@ -39,7 +44,50 @@ struct GemmShape {
   int num_kb;      // k-blocks per output tile (before split-K)
   int kb_per_tap;  // conv: k-blocks per tap; otherwise == num_kb
   int splits;      // split-K factor
+  float* splitk_ws;  // fix-up workspace [tiles][splits][128][BLOCK_N] fp32 (epilogues with kFixup, splits > 1)
+  int* tickets;      // [tiles] arrival counters, zero before first use, self-resetting
 };
+
+// Per-thread view of "this row's accumulator": TMEM, plus the parked partials of the other splits when this CTA is the
+// last split to arrive.
+struct AccSource {
+  uint32_t taddr;        // TMEM address of this warp's lane quarter, column 0 of the tile
+  bool has_acc;          // false: no MMA ran for this tile (first LSTM step) -> zeros
+  const float* partial;  // workspace row base of split 0 for this thread's row, or nullptr
+  int splits, my_split;
+  long split_stride;     // elements between consecutive splits in the workspace
+  template <int N>
+  __device__ __forceinline__ void load(int col, float* v) const {
+    if (has_acc) {
+      if constexpr (N == 32) ptx::tmem_ld_x32(taddr + col, v);
+      else ptx::tmem_ld_x8(taddr + col, v);
+      ptx::tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = 0.f;
+    }
+    if (partial != nullptr) {
+      for (int sp = 0; sp < splits; ++sp) {
+        if (sp == my_split) continue;
+        const float4* src = reinterpret_cast<const float4*>(partial + sp * split_stride + col);
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+          const float4 t = __ldcg(src + i);
+          v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+        }
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// prefetch `bytes` starting at p (128-byte lines)
+__device__ __forceinline__ void prefetch_l2_span(const void* p, int bytes) {
+  const char* c = static_cast<const char*>(p);
+  for (int o = 0; o < bytes; o += 128) prefetch_l2(c + o);
+}
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                               uint32_t layout_type) {
@@ -181,15 +229,55 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (num_local > 0 && lane == 0) ptx::umma_commit(tmem_full_bar);
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int m = tile_m * kBlockM + q * 32 + lane;
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns
+    const int row = q * 32 + lane;
+    const int m = tile_m * kBlockM + row;
+    const int n0 = tile_n * BLOCK_N;
+    const int col0 = half * (BLOCK_N / 2), col1 = col0 + BLOCK_N / 2;
+    Epi::template prefetch<BLOCK_N>(ep, m, n0, zb, col0, col1, shp);   // overlaps the main loop
+    AccSource acc;
+    acc.taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    acc.has_acc = num_local > 0;
+    acc.partial = nullptr;
+    acc.splits = shp.splits;
+    acc.my_split = split;
+    acc.split_stride = static_cast<long>(kBlockM) * BLOCK_N;
     if (num_local > 0) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
     }
-    Epi::template run<BLOCK_N>(ep, tmem_base + (static_cast<uint32_t>(q * 32) << 16), num_local > 0, m,
-                               tile_n * BLOCK_N, zb, shp);
+    bool run_epilogue = true;
+    if (Epi::kFixup && shp.splits > 1) {
+      const long tile_id = (static_cast<long>(zb) * gridDim.y + tile_n) * gridDim.x + tile_m;
+      float* ws_row = shp.splitk_ws + (tile_id * shp.splits * kBlockM + row) * BLOCK_N;
+      float* mine = ws_row + split * acc.split_stride;
+      for (int c = col0; c < col1; c += 32) {
+        __syncwarp();
+        float v[32];
+        acc.template load<32>(c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          __stcg(reinterpret_cast<float4*>(mine + c) + i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      int* last_flag = reinterpret_cast<int*>(smem + STAGES * (STAGE_A + STAGE_B) + 8 * (2 * STAGES + 2));
+      if (threadIdx.x == 64) {
+        const int old = atomicAdd(shp.tickets + tile_id, 1);
+        const int last = (old == shp.splits - 1) ? 1 : 0;
+        if (last) shp.tickets[tile_id] = 0;   // self-reset for the next launch
+        *last_flag = last;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      run_epilogue = (*last_flag != 0);
+      if (run_epilogue) {
+        __threadfence();
+        acc.partial = ws_row;
+      }
+    }
+    if (run_epilogue) Epi::template run<BLOCK_N>(ep, acc, m, n0, zb, col0, col1, shp);
     ptx::tc_fence_before();
   }
   __syncthreads();
@@ -206,6 +294,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---- out = act(acc + bias) -> activation dtype, optionally mirrored in fp32; optional relu-mask multiply
 template <typename OutT>
 struct EpiStore {
+  static constexpr bool kFixup = true;
   struct Params {
     OutT* out;            // may be null
     float* out_f32;       // may be null
@@ -216,22 +305,23 @@ struct EpiStore {
     int relu;
   };
   template <int BLOCK_N>
-  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, bool has_acc, int m, int n0, int zb,
-                                             const GemmShape& shp) {
+  static __device__ __forceinline__ void prefetch(const Params& p, int m, int n0, int zb, int col0, int col1,
+                                                  const GemmShape& shp) {
+    if (p.mask != nullptr && m < shp.M && n0 + col0 < shp.N)
+      prefetch_l2_span(p.mask + static_cast<long>(zb) * p.z_stride + static_cast<long>(m) * p.ldo + n0 + col0,
+                       (col1 - col0) * static_cast<int>(sizeof(OutT)));
+  }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const AccSource& acc, int m, int n0, int zb, int col0,
+                                             int col1, const GemmShape& shp) {
     const bool row_ok = m < shp.M;
     const long row_off = static_cast<long>(zb) * p.z_stride + static_cast<long>(m) * p.ldo;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
+    for (int c = col0; c < col1; c += 32) {
       if (n0 + c >= shp.N) break;
       __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the masked stores below
       float v[32];
-      if (has_acc) {
-        ptx::tmem_ld_x32(taddr + c, v);
-        ptx::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-      }
+      acc.template load<32>(c, v);
       const int nb = n0 + c;
       const bool full = (nb + 32 <= shp.N);
       if (p.bias != nullptr) {
@@ -244,67 +334,69 @@ struct EpiStore {
         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
       }
       if (row_ok) {
-      const bool vec = full && ((p.ldo & 7) == 0);
-      if (p.mask != nullptr) {
-        const OutT* mk = p.mask + row_off + nb;
-        if (vec) {
+        const bool vec = full && ((p.ldo & 7) == 0);
+        if (p.mask != nullptr) {
+          const OutT* mk = p.mask + row_off + nb;
+          if (vec) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float mv[8];
-            Act8<OutT>::load(mk + 8 * g, mv);
+            for (int g = 0; g < 4; ++g) {
+              float mv[8];
+              Act8<OutT>::load(mk + 8 * g, mv);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[8 * g + i] = mv[i] > 0.f ? v[8 * g + i] : 0.f;
+              for (int i = 0; i < 8; ++i) v[8 * g + i] = mv[i] > 0.f ? v[8 * g + i] : 0.f;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < shp.N) v[i] = to_f32(mk[i]) > 0.f ? v[i] : 0.f;
           }
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < shp.N) v[i] = to_f32(mk[i]) > 0.f ? v[i] : 0.f;
         }
-      }
-      if (p.out != nullptr) {
-        OutT* o = p.out + row_off + nb;
-        if (vec) {
+        if (p.out != nullptr) {
+          OutT* o = p.out + row_off + nb;
+          if (vec) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) Act8<OutT>::store(o + 8 * g, v + 8 * g);
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < shp.N) o[i] = from_f32<OutT>(v[i]);
+            for (int g = 0; g < 4; ++g) Act8<OutT>::store(o + 8 * g, v + 8 * g);
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < shp.N) o[i] = from_f32<OutT>(v[i]);
+          }
         }
-      }
-      if (p.out_f32 != nullptr) {
-        float* o = p.out_f32 + row_off + nb;
-        if (vec) {
+        if (p.out_f32 != nullptr) {
+          float* o = p.out_f32 + row_off + nb;
+          if (vec) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) Act8<float>::store(o + 8 * g, v + 8 * g);
-        } else {
-          for (int i = 0; i < 32; ++i)
-            if (nb + i < shp.N) o[i] = v[i];
+            for (int g = 0; g < 4; ++g) Act8<float>::store(o + 8 * g, v + 8 * g);
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (nb + i < shp.N) o[i] = v[i];
+          }
         }
       }
-      }  // row_ok
     }
   }
 };
 
-// ---- out_f32 += acc  (split-K weight gradients)
+// ---- out_f32 += acc  (split-K weight gradients; every split adds its own partial, no fix-up needed)
 struct EpiAtomic {
+  static constexpr bool kFixup = false;
   struct Params {
     float* out;
     long ldo;
     long z_stride;
   };
   template <int BLOCK_N>
-  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, bool has_acc, int m, int n0, int zb,
-                                             const GemmShape& shp) {
-    if (!has_acc) return;
+  static __device__ __forceinline__ void prefetch(const Params&, int, int, int, int, int, const GemmShape&) {}
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const AccSource& acc, int m, int n0, int zb, int col0,
+                                             int col1, const GemmShape& shp) {
+    if (!acc.has_acc) return;
     const bool row_ok = m < shp.M;
     float* row = p.out + static_cast<long>(zb) * p.z_stride + static_cast<long>(m) * p.ldo;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
+    for (int c = col0; c < col1; c += 32) {
       if (n0 + c >= shp.N) break;
       __syncwarp();
       float v[32];
-      ptx::tmem_ld_x32(taddr + c, v);
-      ptx::tmem_ld_wait();
+      acc.template load<32>(c, v);
       const int nb = n0 + c;
       if (row_ok) {
         if (nb + 32 <= shp.N && (p.ldo & 3) == 0) {
@@ -325,6 +417,7 @@ struct EpiAtomic {
 // h = s(o) tanh(c).  Saves the activated gates and c for the backward pass.
 template <typename ActT>
 struct EpiLstmFwd {
+  static constexpr bool kFixup = true;
   struct Params {
     const ActT* xproj;   // [rows, ldx] at time t (permuted gate layout), + zb * z_x
     const float* c_prev; // [rows, ldc] at the previous time step (null on the first step)
@@ -337,8 +430,19 @@ struct EpiLstmFwd {
     long z_x, z_c_prev, z_c_out, z_h;
   };
   template <int BLOCK_N>
-  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, bool has_acc, int m, int n0, int zb,
-                                             const GemmShape& shp) {
+  static __device__ __forceinline__ void prefetch(const Params& p, int m, int n0, int zb, int col0, int col1,
+                                                  const GemmShape& shp) {
+    if (m >= shp.M) return;
+    constexpr int UNITS = BLOCK_N / 4;
+    const int u0 = col0 / 4, nu = (col1 - col0) / 4;
+    const ActT* xp = p.xproj + zb * p.z_x + static_cast<long>(m) * p.ldx + n0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) prefetch_l2_span(xp + g * UNITS + u0, nu * static_cast<int>(sizeof(ActT)));
+    if (p.c_prev) prefetch_l2_span(p.c_prev + zb * p.z_c_prev + static_cast<long>(m) * p.ldc + n0 / 4 + u0, nu * 4);
+  }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const AccSource& acc, int m, int n0, int zb, int col0,
+                                             int col1, const GemmShape& shp) {
     constexpr int UNITS = BLOCK_N / 4;
     const bool row_ok = m < shp.M;
     const int unit0 = n0 / 4;
@@ -348,45 +452,38 @@ struct EpiLstmFwd {
     float* co = p.c_out + zb * p.z_c_out + static_cast<long>(m) * p.ldc + unit0;
     ActT* ho = p.h_out + zb * p.z_h + static_cast<long>(m) * p.ldh + unit0;
 #pragma unroll 1
-    for (int u = 0; u < UNITS; u += 8) {
+    for (int u = col0 / 4; u < col1 / 4; u += 8) {
       __syncwarp();
       float a[4][8];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (has_acc) ptx::tmem_ld_x8(taddr + g * UNITS + u, a[g]);
+      for (int g = 0; g < 4; ++g) acc.template load<8>(g * UNITS + u, a[g]);
+      if (row_ok) {
+        float cprev[8];
+        if (cp) Act8<float>::load(cp + u, cprev);
         else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) a[g][i] = 0.f;
+          for (int i = 0; i < 8; ++i) cprev[i] = 0.f;
         }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float x[8];
+          Act8<ActT>::load(xp + g * UNITS + u, x);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[g][i] += x[i];
+        }
+        float cn[8], hn[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ig = sigmoid_f(a[0][i]), fg = sigmoid_f(a[1][i]), gg = tanh_f(a[2][i]), og = sigmoid_f(a[3][i]);
+          a[0][i] = ig; a[1][i] = fg; a[2][i] = gg; a[3][i] = og;
+          cn[i] = fg * cprev[i] + ig * gg;
+          hn[i] = og * tanh_f(cn[i]);
+        }
+        Act8<float>::store(co + u, cn);
+        Act8<ActT>::store(ho + u, hn);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) Act8<ActT>::store(gs + g * UNITS + u, a[g]);
       }
-      if (has_acc) ptx::tmem_ld_wait();
-      if (row_ok) {
-      float cprev[8];
-      if (cp) Act8<float>::load(cp + u, cprev);
-      else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cprev[i] = 0.f;
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float x[8];
-        Act8<ActT>::load(xp + g * UNITS + u, x);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[g][i] += x[i];
-      }
-      float cn[8], hn[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float ig = sigmoid_f(a[0][i]), fg = sigmoid_f(a[1][i]), gg = tanh_f(a[2][i]), og = sigmoid_f(a[3][i]);
-        a[0][i] = ig; a[1][i] = fg; a[2][i] = gg; a[3][i] = og;
-        cn[i] = fg * cprev[i] + ig * gg;
-        hn[i] = og * tanh_f(cn[i]);
-      }
-      Act8<float>::store(co + u, cn);
-      Act8<ActT>::store(ho + u, hn);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) Act8<ActT>::store(gs + g * UNITS + u, a[g]);
-      }  // row_ok
     }
   }
 };
@@ -396,6 +493,7 @@ struct EpiLstmFwd {
 // dc carry.
 template <typename ActT>
 struct EpiLstmBwd {
+  static constexpr bool kFixup = true;
   struct Params {
     const ActT* dh_out;  // [rows, ldh] grad wrt this layer's output at time t (+ zb * z_h)
     const ActT* gates;   // activated gates at time t, forward's permuted layout with FWD_UNITS per tile
@@ -408,8 +506,24 @@ struct EpiLstmBwd {
     int H, fwd_units, dc_zero;                // dc_zero: treat incoming carry as zero (first processed step)
   };
   template <int BLOCK_N>
-  static __device__ __forceinline__ void run(const Params& p, uint32_t taddr, bool has_acc, int m, int n0, int zb,
-                                             const GemmShape& shp) {
+  static __device__ __forceinline__ void prefetch(const Params& p, int m, int n0, int zb, int col0, int col1,
+                                                  const GemmShape& shp) {
+    if (m >= shp.M || n0 + col0 >= shp.N) return;
+    const long r = m;
+    const int u = n0 + col0, nu = col1 - col0;
+    prefetch_l2_span(p.dh_out + zb * p.z_h + r * p.ldh + u, nu * static_cast<int>(sizeof(ActT)));
+    prefetch_l2_span(p.c_t + zb * p.z_c + r * p.ldc + u, nu * 4);
+    if (p.c_prev) prefetch_l2_span(p.c_prev + zb * p.z_c_prev + r * p.ldc + u, nu * 4);
+    if (!p.dc_zero) prefetch_l2_span(p.dc + zb * p.z_dc + r * p.H + u, nu * 4);
+    const ActT* gs = p.gates + zb * p.z_x + r * p.ldx;
+    for (int uu = u; uu < u + nu; uu += p.fwd_units) {   // the forward tile of fwd_units units holds its 4 gates contiguously
+      const long gbase = static_cast<long>(uu / p.fwd_units) * 4 * p.fwd_units;
+      prefetch_l2_span(gs + gbase, 4 * p.fwd_units * static_cast<int>(sizeof(ActT)));
+    }
+  }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const AccSource& accs, int m, int n0, int zb, int col0,
+                                             int col1, const GemmShape& shp) {
     const bool row_ok = m < shp.M;
     const long r = m;
     const ActT* dho = p.dh_out + zb * p.z_h + r * p.ldh;
@@ -419,55 +533,49 @@ struct EpiLstmBwd {
     float* dcp = p.dc + zb * p.z_dc + r * p.H;
     ActT* da = p.da + zb * p.z_a + r * p.lda;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 8) {
+    for (int c = col0; c < col1; c += 8) {
       const int u = n0 + c;
       if (u >= shp.N) break;
       __syncwarp();
       float acc[8];
-      if (has_acc) {
-        ptx::tmem_ld_x8(taddr + c, acc);
-        ptx::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      }
+      accs.template load<8>(c, acc);
       if (row_ok) {
-      float dh[8], g4[4][8], cc[8], cpv[8], dc[8];
-      Act8<ActT>::load(dho + u, dh);
-      const long gbase = static_cast<long>(u / p.fwd_units) * 4 * p.fwd_units + (u % p.fwd_units);
+        float dh[8], g4[4][8], cc[8], cpv[8], dc[8];
+        Act8<ActT>::load(dho + u, dh);
+        const long gbase = static_cast<long>(u / p.fwd_units) * 4 * p.fwd_units + (u % p.fwd_units);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) Act8<ActT>::load(gs + gbase + g * p.fwd_units, g4[g]);
-      Act8<float>::load(ct + u, cc);
-      if (cp) Act8<float>::load(cp + u, cpv);
-      else {
+        for (int g = 0; g < 4; ++g) Act8<ActT>::load(gs + gbase + g * p.fwd_units, g4[g]);
+        Act8<float>::load(ct + u, cc);
+        if (cp) Act8<float>::load(cp + u, cpv);
+        else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cpv[i] = 0.f;
+          for (int i = 0; i < 8; ++i) cpv[i] = 0.f;
+        }
+        if (p.dc_zero) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dc[i] = 0.f;
+        } else {
+          Act8<float>::load(dcp + u, dc);
+        }
+        float dai[8], daf[8], dag[8], dao[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ig = g4[0][i], fg = g4[1][i], gg = g4[2][i], og = g4[3][i];
+          const float tc = tanh_f(cc[i]);
+          const float dht = dh[i] + acc[i];
+          const float dct = dc[i] + dht * og * (1.f - tc * tc);
+          dao[i] = dht * tc * og * (1.f - og);
+          dai[i] = dct * gg * ig * (1.f - ig);
+          dag[i] = dct * ig * (1.f - gg * gg);
+          daf[i] = dct * cpv[i] * fg * (1.f - fg);
+          dc[i] = dct * fg;
+        }
+        Act8<float>::store(dcp + u, dc);
+        Act8<ActT>::store(da + 0 * p.H + u, dai);
+        Act8<ActT>::store(da + 1 * p.H + u, daf);
+        Act8<ActT>::store(da + 2 * p.H + u, dag);
+        Act8<ActT>::store(da + 3 * p.H + u, dao);
       }
-      if (p.dc_zero) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dc[i] = 0.f;
-      } else {
-        Act8<float>::load(dcp + u, dc);
-      }
-      float dai[8], daf[8], dag[8], dao[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float ig = g4[0][i], fg = g4[1][i], gg = g4[2][i], og = g4[3][i];
-        const float tc = tanh_f(cc[i]);
-        const float dht = dh[i] + acc[i];
-        const float dct = dc[i] + dht * og * (1.f - tc * tc);
-        dao[i] = dht * tc * og * (1.f - og);
-        dai[i] = dct * gg * ig * (1.f - ig);
-        dag[i] = dct * ig * (1.f - gg * gg);
-        daf[i] = dct * cpv[i] * fg * (1.f - fg);
-        dc[i] = dct * fg;
-      }
-      Act8<float>::store(dcp + u, dc);
-      Act8<ActT>::store(da + 0 * p.H + u, dai);
-      Act8<ActT>::store(da + 1 * p.H + u, daf);
-      Act8<ActT>::store(da + 2 * p.H + u, dag);
-      Act8<ActT>::store(da + 3 * p.H + u, dao);
-      }  // row_ok
     }
   }
 };

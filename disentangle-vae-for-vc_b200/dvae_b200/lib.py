@@ -36,7 +36,8 @@ _SIGNATURES = {
     "dvae_conv5_dgrad": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_conv5_wgrad": [_i, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_lstm_fwd": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
-    "dvae_lstm_bwd": [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dvae_lstm_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dvae_lstm_bwd_workspace": [_i, _i, _i, _i, _p, _p],
     "dvae_lstm_wgrad_hh": [_i, _p, _p, _p, _i, _i, _i, _i, _p],
     # weight preparation / layout
     "dvae_prep_cast": [_i, _p, _p, _l, _p],
@@ -99,7 +100,7 @@ def stream():
 # kernels launched per C-ABI call (bench.py reports the total as `gpu_launches`)
 LAUNCHES = 0
 _LAUNCHES_PER_CALL = {"dvae_bn_train_fwd": 3, "dvae_bn_train_bwd": 3, "dvae_bn_eval_fwd": 2, "dvae_segment_ids_sorted": 3}
-_TIME_STEP_ARG = {"dvae_lstm_fwd": 6, "dvae_lstm_bwd": 8}   # index of T: one GEMM launch per time step
+_TIME_STEP_ARG = {"dvae_lstm_fwd": 6, "dvae_lstm_bwd": 10}   # index of T: one GEMM launch per time step
 
 
 def call(name, *args):
@@ -112,6 +113,15 @@ def call(name, *args):
 
 def version() -> int:
     return _lib.dvae_version()
+
+
+def lstm_bwd_workspace(dt: int, rows: int, H: int, D: int):
+    """(floats of split-K fix-up workspace, number of int32 tickets) for dvae_lstm_bwd at this shape."""
+    ws, nt = C.c_long(0), C.c_int(0)
+    rc = _FUNCS["dvae_lstm_bwd_workspace"](dt, rows, H, D, C.cast(C.byref(ws), C.c_void_p), C.cast(C.byref(nt), C.c_void_p))
+    if rc != 0:
+        raise RuntimeError("dvae_lstm_bwd_workspace failed")
+    return ws.value, nt.value
 
 
 def lstm_gate_tile(hidden: int) -> int:

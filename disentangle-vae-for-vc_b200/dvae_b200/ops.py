@@ -122,8 +122,24 @@ def lstm_bwd(dt: int, dh_all: Tensor, gates: Tensor, c_all: Tensor, whh_n: Tenso
     rows, T, _ = dh_all.shape
     da = torch.empty((rows, T, D * 4 * H), device=dh_all.device, dtype=ad)
     dc = torch.empty((D, rows, H), device=dh_all.device, dtype=torch.float32)
-    call("dvae_lstm_bwd", dt, ptr(dh_all), ptr(gates), ptr(c_all), ptr(whh_n), ptr(da), ptr(dc), rows, T, H, D, stream())
+    ws, tickets = _splitk_workspace(dt, rows, H, D, dh_all.device)
+    call("dvae_lstm_bwd", dt, ptr(dh_all), ptr(gates), ptr(c_all), ptr(whh_n), ptr(da), ptr(dc), ptr(ws), ptr(tickets), rows, T,
+         H, D, stream())
     return da
+
+
+_SPLITK_CACHE = {}
+
+
+def _splitk_workspace(dt: int, rows: int, H: int, D: int, device):
+    """Fix-up workspace + self-resetting tickets of the split-K LSTM backward step, cached per shape and device."""
+    key = (dt, rows, H, D, str(device))
+    if key not in _SPLITK_CACHE:
+        n_ws, n_t = lib.lstm_bwd_workspace(dt, rows, H, D)
+        ws = torch.empty((n_ws,), device=device, dtype=torch.float32) if n_ws > 0 else None
+        tickets = torch.zeros((max(n_t, 1),), device=device, dtype=torch.int32)
+        _SPLITK_CACHE[key] = (ws, tickets)
+    return _SPLITK_CACHE[key]
 
 
 def lstm_wgrad_hh(dt: int, da_all: Tensor, h_all: Tensor, dwhh: Tensor, H: int, D: int) -> None:

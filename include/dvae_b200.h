@@ -44,7 +44,8 @@ int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R
 int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_all, int rows, int T, int H, int D,
                   void* stream);
 int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all,
-                  float* dc_ws, int rows, int T, int H, int D, void* stream);
+                  float* dc_ws, float* splitk_ws, int* tickets, int rows, int T, int H, int D, void* stream);
+int dvae_lstm_bwd_workspace(int dtype, int rows, int H, int D, long* ws_floats, int* num_tickets);
 int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* dwhh, int rows, int T, int H, int D,
                        void* stream);
 
