@@ -211,8 +211,8 @@ static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, in
 
 // ------------------------------------------------------------------------------------ LSTM
 // Layouts (rows = sequences, D = directions):
-//   xg    [rows, T, D*4H]  in: x-projection + biases, gate-interleaved per direction (tile of FWD_BN columns =
-//                          [i|f|g|o] x FWD_BN/4 units); out: activated gates (same layout, overwritten in place)
+//   xg    [rows, T, D*4H]  in: x-projection + biases, gate-interleaved per direction (column 4*u + g = gate g of
+//                          unit u); out: activated gates (same layout, overwritten in place)
 //   h_all [rows, T, D*H]   layer output, also the A operand of the next step (3-D TMA over {D*H, T, rows})
 //   c_all [rows, T, D*H]   fp32 cell state
 //   whh_p [D][4H][H]       recurrent weights, rows gate-interleaved like xg columns
@@ -325,7 +325,7 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
     ep.z_c_prev = H + (long)((tr + 1) - (tf - 1)) * D * H;
     ep.z_dc = (long)rows * H;
     ep.z_a = 4 * H + (long)(tr - tf) * D * 4 * H;
-    ep.H = H; ep.fwd_units = lstm_fwd_bn(H) / 4; ep.dc_zero = (s == 0);
+    ep.H = H; ep.dc_zero = (s == 0);
     dim3 grid(ceil_div(rows, 128), H / BN, D * splits);
     int e = (BN == 256)   ? launch_gemm<256, false, true, EB, EpiLstmBwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
             : (BN == 128) ? launch_gemm<128, false, true, EB, EpiLstmBwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)

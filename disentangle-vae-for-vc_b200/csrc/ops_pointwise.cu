@@ -59,12 +59,9 @@ __global__ void conv_wgrad_unpack_kernel(const float* __restrict__ dwk, float* _
   }
 }
 
-__device__ __forceinline__ int gate_perm_src(int n, int H, int tile) {
-  // destination row n of the gate-interleaved layout <- source row of the torch [i;f;g;o] layout
-  const int units = tile >> 2;
-  const int jn = n / tile, within = n - jn * tile;
-  const int g = within / units, u = jn * units + (within - g * units);
-  return g * H + u;
+__device__ __forceinline__ int gate_perm_src(int n, int H, int /*tile*/) {
+  // destination row n = 4*u + g of the gate-interleaved layout <- source row g*H + u of the torch [i;f;g;o] layout
+  return (n & 3) * H + (n >> 2);
 }
 template <typename AT>
 __global__ void lstm_weight_kernel(const float* __restrict__ w, AT* __restrict__ dst, int H, int In, int tile) {

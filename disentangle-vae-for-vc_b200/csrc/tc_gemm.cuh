@@ -111,7 +111,7 @@ constexpr int gemm_smem_bytes() {
 }
 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, (Epi::kCtasPerSm == 2 && STAGES * (kBlockM + BLOCK_N) * kSwizzleRow <= 100 * 1024) ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const OperandWalk wa, const OperandWalk wb, const GemmShape shp, const typename Epi::Params ep) {
   constexpr int BLOCK_K = kSwizzleRow / ELEM_BYTES;  // 64 bf16 / 32 tf32
@@ -295,6 +295,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <typename OutT>
 struct EpiStore {
   static constexpr bool kFixup = true;
+  static constexpr int kCtasPerSm = 2;
   struct Params {
     OutT* out;            // may be null
     float* out_f32;       // may be null
@@ -378,6 +379,7 @@ struct EpiStore {
 // ---- out_f32 += acc  (split-K weight gradients; every split adds its own partial, no fix-up needed)
 struct EpiAtomic {
   static constexpr bool kFixup = false;
+  static constexpr int kCtasPerSm = 2;
   struct Params {
     float* out;
     long ldo;
@@ -412,18 +414,20 @@ struct EpiAtomic {
   }
 };
 
-// ---- LSTM cell forward.  The N tile holds [i | f | g | o] pre-activations of BLOCK_N/4 hidden units
-// (gate-interleaved weight rows, see prep_lstm_weights).  a = acc + xproj;  c = s(f) c_prev + s(i) tanh(g);
-// h = s(o) tanh(c).  Saves the activated gates and c for the backward pass.
+// ---- LSTM cell forward.  Gate-interleaved layout: column 4*u + g of the [rows, 4H] pre-activation is gate g (i,f,g,o)
+// of hidden unit u (weight rows are permuted accordingly by prep_lstm_weight), so a thread's 8 units are 32 contiguous
+// columns: one tcgen05.ld.x32 and one 64-byte run of xproj / gates.  a = acc + xproj;  c = s(f) c_prev + s(i) tanh(g);
+// h = s(o) tanh(c).  Saves the activated gates (in place of xproj) and c for the backward pass.
 template <typename ActT>
 struct EpiLstmFwd {
   static constexpr bool kFixup = true;
+  static constexpr int kCtasPerSm = 2;
   struct Params {
-    const ActT* xproj;   // [rows, ldx] at time t (permuted gate layout), + zb * z_x
+    const ActT* xproj;   // [rows, ldx] at time t (gate-interleaved), + zb * z_x
     const float* c_prev; // [rows, ldc] at the previous time step (null on the first step)
     float* c_out;        // [rows, ldc] at time t
     ActT* h_out;         // [rows, ldh] at time t (+ zb * z_h: direction offset in the concat output)
-    ActT* gates;         // [rows, ldx] at time t, activated gates (same permuted layout), + zb * z_x
+    ActT* gates;         // [rows, ldx] at time t, activated gates (same layout), + zb * z_x
     long ldx, ldc, ldh;
     // element offsets applied when zb == 1 (reverse direction of a bidirectional layer: other weights,
     // other half of the concat output, and a different time index)
@@ -433,56 +437,50 @@ struct EpiLstmFwd {
   static __device__ __forceinline__ void prefetch(const Params& p, int m, int n0, int zb, int col0, int col1,
                                                   const GemmShape& shp) {
     if (m >= shp.M) return;
-    constexpr int UNITS = BLOCK_N / 4;
-    const int u0 = col0 / 4, nu = (col1 - col0) / 4;
-    const ActT* xp = p.xproj + zb * p.z_x + static_cast<long>(m) * p.ldx + n0;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) prefetch_l2_span(xp + g * UNITS + u0, nu * static_cast<int>(sizeof(ActT)));
-    if (p.c_prev) prefetch_l2_span(p.c_prev + zb * p.z_c_prev + static_cast<long>(m) * p.ldc + n0 / 4 + u0, nu * 4);
+    prefetch_l2_span(p.xproj + zb * p.z_x + static_cast<long>(m) * p.ldx + n0 + col0,
+                     (col1 - col0) * static_cast<int>(sizeof(ActT)));
+    if (p.c_prev)
+      prefetch_l2_span(p.c_prev + zb * p.z_c_prev + static_cast<long>(m) * p.ldc + (n0 + col0) / 4, (col1 - col0));
   }
   template <int BLOCK_N>
   static __device__ __forceinline__ void run(const Params& p, const AccSource& acc, int m, int n0, int zb, int col0,
                                              int col1, const GemmShape& shp) {
-    constexpr int UNITS = BLOCK_N / 4;
     const bool row_ok = m < shp.M;
-    const int unit0 = n0 / 4;
     const ActT* xp = p.xproj + zb * p.z_x + static_cast<long>(m) * p.ldx + n0;
     ActT* gs = p.gates + zb * p.z_x + static_cast<long>(m) * p.ldx + n0;
-    const float* cp = p.c_prev ? p.c_prev + zb * p.z_c_prev + static_cast<long>(m) * p.ldc + unit0 : nullptr;
-    float* co = p.c_out + zb * p.z_c_out + static_cast<long>(m) * p.ldc + unit0;
-    ActT* ho = p.h_out + zb * p.z_h + static_cast<long>(m) * p.ldh + unit0;
+    const float* cp = p.c_prev ? p.c_prev + zb * p.z_c_prev + static_cast<long>(m) * p.ldc + n0 / 4 : nullptr;
+    float* co = p.c_out + zb * p.z_c_out + static_cast<long>(m) * p.ldc + n0 / 4;
+    ActT* ho = p.h_out + zb * p.z_h + static_cast<long>(m) * p.ldh + n0 / 4;
 #pragma unroll 1
-    for (int u = col0 / 4; u < col1 / 4; u += 8) {
-      __syncwarp();
-      float a[4][8];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) acc.template load<8>(g * UNITS + u, a[g]);
+    for (int c = col0; c < col1; c += 32) {   // 32 columns = 8 hidden units x 4 gates
+      // global operands first (the epilogue is latency-bound: profiles/r01_ncu_gemm_v1.txt), then the accumulator
+      float x[32], cprev[8];
       if (row_ok) {
-        float cprev[8];
-        if (cp) Act8<float>::load(cp + u, cprev);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Act8<ActT>::load(xp + c + 8 * j, x + 8 * j);
+        if (cp) Act8<float>::load(cp + c / 4, cprev);
         else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) cprev[i] = 0.f;
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float x[8];
-          Act8<ActT>::load(xp + g * UNITS + u, x);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) a[g][i] += x[i];
-        }
+      }
+      __syncwarp();
+      float a[32];
+      acc.template load<32>(c, a);
+      if (row_ok) {
         float cn[8], hn[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float ig = sigmoid_f(a[0][i]), fg = sigmoid_f(a[1][i]), gg = tanh_f(a[2][i]), og = sigmoid_f(a[3][i]);
-          a[0][i] = ig; a[1][i] = fg; a[2][i] = gg; a[3][i] = og;
+          const float ig = sigmoid_f(a[4 * i] + x[4 * i]), fg = sigmoid_f(a[4 * i + 1] + x[4 * i + 1]);
+          const float gg = tanh_f(a[4 * i + 2] + x[4 * i + 2]), og = sigmoid_f(a[4 * i + 3] + x[4 * i + 3]);
+          a[4 * i] = ig; a[4 * i + 1] = fg; a[4 * i + 2] = gg; a[4 * i + 3] = og;
           cn[i] = fg * cprev[i] + ig * gg;
           hn[i] = og * tanh_f(cn[i]);
         }
-        Act8<float>::store(co + u, cn);
-        Act8<ActT>::store(ho + u, hn);
+        Act8<float>::store(co + c / 4, cn);
+        Act8<ActT>::store(ho + c / 4, hn);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) Act8<ActT>::store(gs + g * UNITS + u, a[g]);
+        for (int j = 0; j < 4; ++j) Act8<ActT>::store(gs + c + 8 * j, a + 8 * j);
       }
     }
   }
@@ -490,20 +488,21 @@ struct EpiLstmFwd {
 
 // ---- LSTM cell backward for one time step.  acc = dh_rec[m, unit] = da_{t+1} . W_hh (absent on the last
 // step).  dh = dh_out + acc; emits da_t (natural torch gate order i,f,g,o: column g*H + unit) and the new
-// dc carry.
+// dc carry.  The saved activated gates are in the forward's gate-interleaved layout (column 4*u + g).
 template <typename ActT>
 struct EpiLstmBwd {
   static constexpr bool kFixup = true;
+  static constexpr int kCtasPerSm = 1;   // register-heavy epilogue (two chunks of operands in flight); grids are small
   struct Params {
     const ActT* dh_out;  // [rows, ldh] grad wrt this layer's output at time t (+ zb * z_h)
-    const ActT* gates;   // activated gates at time t, forward's permuted layout with FWD_UNITS per tile
+    const ActT* gates;   // activated gates at time t, gate-interleaved
     const float* c_t;    // [rows, ldc] at time t
     const float* c_prev; // at the previous time step or null
     float* dc;           // [rows, H] carry, in/out (+ zb * z_dc)
     ActT* da;            // [rows, lda] at time t, natural gate order (+ zb * z_a)
     long ldh, ldx, ldc, lda;
     long z_h, z_x, z_c, z_c_prev, z_dc, z_a;  // element offsets applied when zb == 1 (reverse direction)
-    int H, fwd_units, dc_zero;                // dc_zero: treat incoming carry as zero (first processed step)
+    int H, dc_zero;                           // dc_zero: treat incoming carry as zero (first processed step)
   };
   template <int BLOCK_N>
   static __device__ __forceinline__ void prefetch(const Params& p, int m, int n0, int zb, int col0, int col1,
@@ -512,18 +511,15 @@ struct EpiLstmBwd {
     const long r = m;
     const int u = n0 + col0, nu = col1 - col0;
     prefetch_l2_span(p.dh_out + zb * p.z_h + r * p.ldh + u, nu * static_cast<int>(sizeof(ActT)));
+    prefetch_l2_span(p.gates + zb * p.z_x + r * p.ldx + 4 * u, 4 * nu * static_cast<int>(sizeof(ActT)));
     prefetch_l2_span(p.c_t + zb * p.z_c + r * p.ldc + u, nu * 4);
     if (p.c_prev) prefetch_l2_span(p.c_prev + zb * p.z_c_prev + r * p.ldc + u, nu * 4);
     if (!p.dc_zero) prefetch_l2_span(p.dc + zb * p.z_dc + r * p.H + u, nu * 4);
-    const ActT* gs = p.gates + zb * p.z_x + r * p.ldx;
-    for (int uu = u; uu < u + nu; uu += p.fwd_units) {   // the forward tile of fwd_units units holds its 4 gates contiguously
-      const long gbase = static_cast<long>(uu / p.fwd_units) * 4 * p.fwd_units;
-      prefetch_l2_span(gs + gbase, 4 * p.fwd_units * static_cast<int>(sizeof(ActT)));
-    }
   }
   template <int BLOCK_N>
   static __device__ __forceinline__ void run(const Params& p, const AccSource& accs, int m, int n0, int zb, int col0,
                                              int col1, const GemmShape& shp) {
+    constexpr int CH = 2;   // 8-unit chunks per iteration (BLOCK_N / 2 columns per thread is always >= 32)
     const bool row_ok = m < shp.M;
     const long r = m;
     const ActT* dho = p.dh_out + zb * p.z_h + r * p.ldh;
@@ -533,48 +529,57 @@ struct EpiLstmBwd {
     float* dcp = p.dc + zb * p.z_dc + r * p.H;
     ActT* da = p.da + zb * p.z_a + r * p.lda;
 #pragma unroll 1
-    for (int c = col0; c < col1; c += 8) {
-      const int u = n0 + c;
-      if (u >= shp.N) break;
-      __syncwarp();
-      float acc[8];
-      accs.template load<8>(c, acc);
+    for (int c = col0; c < col1; c += 8 * CH) {
+      if (n0 + c >= shp.N) break;
+      // all global operands of both chunks first (latency-bound epilogue: maximise loads in flight)
+      float dh[CH][8], g4[CH][32], cc[CH][8], cpv[CH][8], dc[CH][8];
       if (row_ok) {
-        float dh[8], g4[4][8], cc[8], cpv[8], dc[8];
-        Act8<ActT>::load(dho + u, dh);
-        const long gbase = static_cast<long>(u / p.fwd_units) * 4 * p.fwd_units + (u % p.fwd_units);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) Act8<ActT>::load(gs + gbase + g * p.fwd_units, g4[g]);
-        Act8<float>::load(ct + u, cc);
-        if (cp) Act8<float>::load(cp + u, cpv);
-        else {
+        for (int k = 0; k < CH; ++k) {
+          const int u = n0 + c + 8 * k;
+          Act8<ActT>::load(dho + u, dh[k]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) cpv[i] = 0.f;
+          for (int j = 0; j < 4; ++j) Act8<ActT>::load(gs + 4 * u + 8 * j, g4[k] + 8 * j);
+          Act8<float>::load(ct + u, cc[k]);
+          if (cp) Act8<float>::load(cp + u, cpv[k]);
+          else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cpv[k][i] = 0.f;
+          }
+          if (p.dc_zero) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dc[k][i] = 0.f;
+          } else {
+            Act8<float>::load(dcp + u, dc[k]);
+          }
         }
-        if (p.dc_zero) {
+      }
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dc[i] = 0.f;
-        } else {
-          Act8<float>::load(dcp + u, dc);
-        }
-        float dai[8], daf[8], dag[8], dao[8];
+      for (int k = 0; k < CH; ++k) {
+        const int u = n0 + c + 8 * k;
+        __syncwarp();
+        float acc[8];
+        accs.template load<8>(c + 8 * k, acc);
+        if (row_ok) {
+          float dai[8], daf[8], dag[8], dao[8], dcn[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float ig = g4[0][i], fg = g4[1][i], gg = g4[2][i], og = g4[3][i];
-          const float tc = tanh_f(cc[i]);
-          const float dht = dh[i] + acc[i];
-          const float dct = dc[i] + dht * og * (1.f - tc * tc);
-          dao[i] = dht * tc * og * (1.f - og);
-          dai[i] = dct * gg * ig * (1.f - ig);
-          dag[i] = dct * ig * (1.f - gg * gg);
-          daf[i] = dct * cpv[i] * fg * (1.f - fg);
-          dc[i] = dct * fg;
+          for (int i = 0; i < 8; ++i) {
+            const float ig = g4[k][4 * i], fg = g4[k][4 * i + 1], gg = g4[k][4 * i + 2], og = g4[k][4 * i + 3];
+            const float tc = tanh_f(cc[k][i]);
+            const float dht = dh[k][i] + acc[i];
+            const float dct = dc[k][i] + dht * og * (1.f - tc * tc);
+            dao[i] = dht * tc * og * (1.f - og);
+            dai[i] = dct * gg * ig * (1.f - ig);
+            dag[i] = dct * ig * (1.f - gg * gg);
+            daf[i] = dct * cpv[k][i] * fg * (1.f - fg);
+            dcn[i] = dct * fg;
+          }
+          Act8<float>::store(dcp + u, dcn);
+          Act8<ActT>::store(da + 0 * p.H + u, dai);
+          Act8<ActT>::store(da + 1 * p.H + u, daf);
+          Act8<ActT>::store(da + 2 * p.H + u, dag);
+          Act8<ActT>::store(da + 3 * p.H + u, dao);
         }
-        Act8<float>::store(dcp + u, dc);
-        Act8<ActT>::store(da + 0 * p.H + u, dai);
-        Act8<ActT>::store(da + 1 * p.H + u, daf);
-        Act8<ActT>::store(da + 2 * p.H + u, dag);
-        Act8<ActT>::store(da + 3 * p.H + u, dao);
       }
     }
   }

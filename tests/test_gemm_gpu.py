@@ -110,12 +110,9 @@ def test_conv5(name, R, Cin, Cout):
     assert (dwk - ref_dw).abs().max().item() <= 2e-5 * ref_dw.abs().max().item() + 1e-5
 
 
-def _gate_perm(H, tile):
-    units = tile // 4
+def _gate_perm(H, tile=None):
     n = torch.arange(4 * H)
-    jn, within = n // tile, n % tile
-    g, u = within // units, jn * units + within % units
-    return g * H + u            # dst row n  <-  src row perm[n]
+    return (n % 4) * H + n // 4            # dst row n = 4*u + g  <-  src row g*H + u
 
 
 def _lstm_ref(xproj_nat, whh, D, H):
