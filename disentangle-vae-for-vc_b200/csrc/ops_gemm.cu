@@ -455,4 +455,12 @@ int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* 
 
 int dvae_lstm_gate_tile(int H) { return lstm_fwd_bn(H); }
 
+// debugging aid: install (or remove, buf = NULL) a device buffer of capacity*5 uint64 phase stamps written by every
+// tc_gemm_kernel CTA (see phase_stamp in tc_gemm.cuh)
+int dvae_debug_timing(unsigned long long* buf, int capacity) {
+  DVAE_CHECK_CUDA(cudaMemcpyToSymbol(dvae::g_phase_stamps, &buf, sizeof(buf)));
+  DVAE_CHECK_CUDA(cudaMemcpyToSymbol(dvae::g_phase_capacity, &capacity, sizeof(capacity)));
+  return 0;
+}
+
 }  // extern "C"

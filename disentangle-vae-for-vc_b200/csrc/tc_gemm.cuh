@@ -80,6 +80,18 @@ struct AccSource {
   }
 };
 
+// Optional per-CTA phase stamps (globaltimer ns): [cta][0]=entry [1]=setup done [2]=producer done [3]=accumulator ready
+// [4]=epilogue done.  Off (nullptr) unless dvae_debug_timing() installs a buffer; one predictable branch per stamp.
+__device__ unsigned long long* g_phase_stamps = nullptr;
+__device__ int g_phase_capacity = 0;
+__device__ __forceinline__ void phase_stamp(int slot) {
+  unsigned long long* buf = g_phase_stamps;
+  if (buf != nullptr) {
+    const long cta = (static_cast<long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (cta < g_phase_capacity) buf[cta * 5 + slot] = ptx::globaltimer_ns();
+  }
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -150,6 +162,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_end = min(shp.num_kb, kb_begin + kb_chunk);
   const int num_local = max(0, kb_end - kb_begin);
 
+  if (threadIdx.x == 0) phase_stamp(0);
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -168,6 +181,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) phase_stamp(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -201,6 +215,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tma_load_3d(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
         }
       }
+      phase_stamp(2);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
@@ -248,6 +263,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
     }
+    if (threadIdx.x == 64) phase_stamp(3);
     bool run_epilogue = true;
     if (Epi::kFixup && shp.splits > 1) {
       const long tile_id = (static_cast<long>(zb) * gridDim.y + tile_n) * gridDim.x + tile_m;
@@ -278,6 +294,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (run_epilogue) Epi::template run<BLOCK_N>(ep, acc, m, n0, zb, col0, col1, shp);
+    if (threadIdx.x == 64) phase_stamp(4);
     ptx::tc_fence_before();
   }
   __syncthreads();

@@ -21,7 +21,8 @@ extern "C" {
 const char* dvae_last_error(void);
 int dvae_version(void);
 int dvae_sm_arch(void);              /* 100: built for sm_100a only */
-int dvae_lstm_gate_tile(int H);      /* gate-interleave tile (columns) used by the LSTM forward for hidden size H */
+int dvae_lstm_gate_tile(int H);
+int dvae_debug_timing(unsigned long long* buf, int capacity);   /* optional per-CTA phase stamps of the GEMM kernel (debug) */      /* gate-interleave tile (columns) used by the LSTM forward for hidden size H */
 
 /* ---- nn.Linear (model/disentangled_vae.py:98-100 LinearNorm.forward; :165-171, :194, :211-213, :232-233, :247) */
 int dvae_linear_fwd(int dtype, const void* x, long ldx, const void* w, const float* bias, void* out, float* out_f32,
