@@ -245,7 +245,8 @@ static int lstm_bwd_splits(int rows, int H, int D, int elem_bytes) {
   static const int forced = env_int("DVAE_LSTM_BWD_SPLITS", 0);
   const int tiles = ceil_div(rows, 128) * (H / lstm_bwd_bn(H)) * D;
   const int num_kb = 4 * H / (128 / elem_bytes);
-  int s = forced > 0 ? forced : (2 * num_sms()) / (tiles > 0 ? tiles : 1);
+  (void)tiles;
+  int s = forced > 0 ? forced : 1;   // measured (profiles/r01_lstm_tile_sweep_v2.txt): splitting does not pay for these shapes
   if (s > num_kb / 4) s = num_kb / 4;
   return s < 1 ? 1 : s;
 }
@@ -288,9 +289,58 @@ static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows
   return 0;
 }
 
+// LSTM cell backward for one time step, elementwise over [rows, H] (both directions: blockIdx.y).  dh = dh_out + dh_rec;
+// see EpiLstmBwd for the math.  One thread = 8 hidden units of one row: every access is a 16/32/64-byte run and
+// consecutive threads touch consecutive runs, so the kernel streams at HBM/L2 bandwidth with full occupancy -- unlike the
+// same arithmetic inside the GEMM epilogue, which is latency-bound on 8 warps (profiles/r01_phase_timing_v2.txt).
+template <typename AT>
+__global__ void lstm_cell_bwd_kernel(const AT* __restrict__ dh_out, const float* __restrict__ dh_rec,
+                                     const AT* __restrict__ gates, const float* __restrict__ c_t,
+                                     const float* __restrict__ c_prev, float* __restrict__ dc, AT* __restrict__ da,
+                                     int rows, int H, long ldh, long ldx, long z_h, long z_x, long z_cprev, long z_rec,
+                                     int dc_zero) {
+  const int d = blockIdx.y;
+  const int upr = H >> 3;  // 8-unit chunks per row
+  const long total = static_cast<long>(rows) * upr;
+  dh_out += d * z_h; gates += d * z_x; c_t += d * z_h; da += d * z_x; dc += d * z_rec;
+  if (c_prev) c_prev += d * z_cprev;
+  if (dh_rec) dh_rec += d * z_rec;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / upr;
+    const int u = static_cast<int>(i - r * upr) * 8;
+    float dh[8], g4[32], cc[8], cpv[8], dcv[8], rec[8];
+    Act8<AT>::load(dh_out + r * ldh + u, dh);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Act8<AT>::load(gates + r * ldx + 4 * u + 8 * j, g4 + 8 * j);
+    Act8<float>::load(c_t + r * ldh + u, cc);
+    if (c_prev) Act8<float>::load(c_prev + r * ldh + u, cpv);
+    if (dh_rec) Act8<float>::load(dh_rec + r * H + u, rec);
+    if (!dc_zero) Act8<float>::load(dc + r * H + u, dcv);
+    float dai[8], daf[8], dag[8], dao[8], dcn[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float ig = g4[4 * k], fg = g4[4 * k + 1], gg = g4[4 * k + 2], og = g4[4 * k + 3];
+      const float tc = tanh_f(cc[k]);
+      const float dht = dh[k] + (dh_rec ? rec[k] : 0.f);
+      const float dct = (dc_zero ? 0.f : dcv[k]) + dht * og * (1.f - tc * tc);
+      dao[k] = dht * tc * og * (1.f - og);
+      dai[k] = dct * gg * ig * (1.f - ig);
+      dag[k] = dct * ig * (1.f - gg * gg);
+      daf[k] = dct * (c_prev ? cpv[k] : 0.f) * fg * (1.f - fg);
+      dcn[k] = dct * fg;
+    }
+    Act8<float>::store(dc + r * H + u, dcn);
+    AT* o = da + r * ldx + u;
+    Act8<AT>::store(o, dai);
+    Act8<AT>::store(o + H, daf);
+    Act8<AT>::store(o + 2 * H, dag);
+    Act8<AT>::store(o + 3 * H, dao);
+  }
+}
+
 // Backward through time.  dh_all [rows,T,D*H] is the gradient wrt the layer output; produces da_all
 // [rows,T,D*4H] (pre-activation gate gradients, natural torch order i,f,g,o per direction).  whh_n is the
-// natural-order copy [D][4H][H].  dc_ws: fp32 [D, rows, H] scratch.
+// natural-order copy [D][4H][H].  dc_ws: fp32 [2][D, rows, H] scratch (dc carry, then the dh_rec buffer of the split path).
 template <typename AT>
 static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, const AT* whh_n, AT* da_all, float* dc_ws,
                       float* splitk_ws, int* tickets, int rows, int T, int H, int D, cudaStream_t st) {
@@ -304,6 +354,39 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
     return e;
   if (int e = encode_map3(&tb, whh_n, EB, H, 4 * H, D, (uint64_t)H * EB, (uint64_t)4 * H * H * EB, BK, BK, 1, true)) return e;
   const long ldh = (long)T * D * H, ldx = (long)T * D * 4 * H;
+  static const int fused = env_int("DVAE_LSTM_BWD_FUSED", 0);
+  if (!fused) {
+    // Two kernels per step: (1) dh_rec[d][rows][H] (fp32) = da_{t+1} . W_hh with a plain store epilogue,
+    // (2) the elementwise cell backward.  dc_ws holds [D][rows][H] carry followed by [D][rows][H] dh_rec.
+    float* dh_rec = dc_ws + (long)D * rows * H;
+    for (int s = 0; s < T; ++s) {
+      const int tf = T - 1 - s, tr = s;
+      if (s > 0) {
+        OperandWalk wa = zero_walk(), wb = zero_walk();
+        wa.base[1] = tf + 1; wa.per_j[0] = BK; wa.per_tile[2] = 128; wa.per_z[0] = 4 * H; wa.per_z[1] = (tr - 1) - (tf + 1);
+        wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN; wb.per_z[2] = 1;
+        const int splits = splitk_ws == nullptr ? 1 : lstm_bwd_splits(rows, H, D, EB);
+        GemmShape shp{rows, H, 4 * H / BK, 4 * H / BK, splits, splitk_ws, tickets};
+        typename EpiStore<AT>::Params ep{nullptr, dh_rec, nullptr, nullptr, (long)H, (long)rows * H, 0};
+        dim3 grid(ceil_div(rows, 128), H / BN, D * splits);
+        int e = (BN == 256)   ? launch_gemm<256, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                : (BN == 128) ? launch_gemm<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                              : launch_gemm<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+        if (e) return e;
+      }
+      const long total = (long)rows * (H / 8);
+      long gx = (total + 255) / 256;
+      if (gx > 148 * 8) gx = 148 * 8;
+      dim3 cgrid((unsigned)gx, D);
+      lstm_cell_bwd_kernel<AT><<<cgrid, 256, 0, st>>>(
+          dh_all + (long)tf * D * H, s > 0 ? dh_rec : nullptr, gates + (long)tf * D * 4 * H, c_all + (long)tf * D * H,
+          (s == T - 1) ? nullptr : c_all + (long)(tf - 1) * D * H, dc_ws, da_all + (long)tf * D * 4 * H, rows, H, ldh, ldx,
+          H + (long)(tr - tf) * D * H, 4 * H + (long)(tr - tf) * D * 4 * H, H + (long)((tr + 1) - (tf - 1)) * D * H,
+          (long)rows * H, s == 0);
+      DVAE_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
   for (int s = 0; s < T; ++s) {
     const int tf = T - 1 - s, tr = s;  // forward direction walks time backwards, reverse direction forwards
     OperandWalk wa = zero_walk(), wb = zero_walk();

@@ -101,12 +101,15 @@ def stream():
 # kernels launched per C-ABI call (bench.py reports the total as `gpu_launches`)
 LAUNCHES = 0
 _LAUNCHES_PER_CALL = {"dvae_bn_train_fwd": 3, "dvae_bn_train_bwd": 3, "dvae_bn_eval_fwd": 2, "dvae_segment_ids_sorted": 3}
-_TIME_STEP_ARG = {"dvae_lstm_fwd": 6, "dvae_lstm_bwd": 10}   # index of T: one GEMM launch per time step
+_TIME_STEP_ARG = {"dvae_lstm_fwd": 6, "dvae_lstm_bwd": 10}   # (lstm_bwd: 2 kernels per step, counted below)   # index of T: one GEMM launch per time step
 
 
 def call(name, *args):
     global LAUNCHES
-    LAUNCHES += args[_TIME_STEP_ARG[name]] if name in _TIME_STEP_ARG else _LAUNCHES_PER_CALL.get(name, 1)
+    if name in _TIME_STEP_ARG:
+        LAUNCHES += args[_TIME_STEP_ARG[name]] * (2 if name == "dvae_lstm_bwd" else 1)
+    else:
+        LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
     rc = _FUNCS[name](*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (status {rc}): {_lib.dvae_last_error().decode()}")

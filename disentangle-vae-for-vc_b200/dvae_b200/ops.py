@@ -121,7 +121,7 @@ def lstm_bwd(dt: int, dh_all: Tensor, gates: Tensor, c_all: Tensor, whh_n: Tenso
     _chk(dh_all, ad), _chk(gates, ad), _chk(c_all, torch.float32), _chk(whh_n, ad)
     rows, T, _ = dh_all.shape
     da = torch.empty((rows, T, D * 4 * H), device=dh_all.device, dtype=ad)
-    dc = torch.empty((D, rows, H), device=dh_all.device, dtype=torch.float32)
+    dc = torch.empty((2, D, rows, H), device=dh_all.device, dtype=torch.float32)   # [0] dc carry, [1] dh_rec scratch
     ws, tickets = _splitk_workspace(dt, rows, H, D, dh_all.device)
     call("dvae_lstm_bwd", dt, ptr(dh_all), ptr(gates), ptr(c_all), ptr(whh_n), ptr(da), ptr(dc), ptr(ws), ptr(tickets), rows, T,
          H, D, stream())
