@@ -25,15 +25,21 @@ struct Stages {
   static constexpr int value = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
 };
 
-template <int BN, bool A_MN, bool B_MN, int EB, class Epi, int ST = Stages<BN>::value>
+// stages that fit 227 KB with the 256-row (two-accumulator) tile
+template <int BN>
+struct Stages2 {
+  static constexpr int value = (BN == 256) ? 3 : (BN == 128 ? 4 : 5);
+};
+
+template <int BN, bool A_MN, bool B_MN, int EB, class Epi, int MT = 1, int ST = (MT == 2 ? Stages2<BN>::value : Stages<BN>::value)>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const OperandWalk& wa, const OperandWalk& wb,
                        const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream) {
   if (Epi::kFixup && shp.splits > 1 && (shp.splitk_ws == nullptr || shp.tickets == nullptr)) {
     set_last_error("split-K with a full-sum epilogue needs a fix-up workspace and tickets");
     return 1;
   }
-  auto kern = tc_gemm_kernel<BN, ST, A_MN, B_MN, EB, Epi>;
-  constexpr int smem = gemm_smem_bytes<BN, ST>();
+  auto kern = tc_gemm_kernel<BN, ST, A_MN, B_MN, EB, Epi, MT>;
+  constexpr int smem = gemm_smem_bytes<BN, ST, MT>();
   static bool configured = false;  // one flag per template instantiation
   if (!configured) {
     DVAE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -53,6 +59,15 @@ static OperandWalk zero_walk() {
 
 static int pick_bn(int N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }
 
+// 256-row CTA tiles (two accumulators sharing the B stage) when the grid still fills the chip; DVAE_GEMM_MT=1|2 forces.
+static int pick_mt(long M, int n_tiles_total) {
+  const char* v = getenv("DVAE_GEMM_MT");
+  if (v && *v == '1') return 1;
+  if (v && *v == '2') return 2;
+  const long ctas = ((M + 255) / 256) * n_tiles_total;
+  return ctas >= 2L * num_sms() ? 2 : 1;
+}
+
 // ------------------------------------------------------------------------------------ Linear
 template <typename AT>
 static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, AT* out, float* out_f32, long ldo, int M,
@@ -68,7 +83,15 @@ static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, A
   wb.per_j[0] = BK; wb.per_tile[1] = BN;
   GemmShape shp{M, N, ceil_div(K, BK), ceil_div(K, BK), 1};
   typename EpiStore<AT>::Params ep{out, out_f32, bias, nullptr, ldo, 0, relu};
-  dim3 grid(ceil_div(M, 128), ceil_div(N, BN), 1);
+  const int mt = pick_mt(M, ceil_div(N, BN));
+  dim3 grid(ceil_div(M, 128 * mt), ceil_div(N, BN), 1);
+  if (mt == 2) {
+    switch (BN) {
+      case 64: return launch_gemm<64, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 128: return launch_gemm<128, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+      default: return launch_gemm<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+    }
+  }
   switch (BN) {
     case 64: return launch_gemm<64, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
     case 128: return launch_gemm<128, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -91,7 +114,15 @@ static int linear_dgrad_t(const AT* dy, long lddy, const AT* w, AT* dx, float* d
   wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN;
   GemmShape shp{M, K, ceil_div(N, BK), ceil_div(N, BK), 1};
   typename EpiStore<AT>::Params ep{dx, dx_f32, nullptr, relu_mask, ldx, 0, 0};
-  dim3 grid(ceil_div(M, 128), ceil_div(K, BN), 1);
+  const int mt = pick_mt(M, ceil_div(K, BN));
+  dim3 grid(ceil_div(M, 128 * mt), ceil_div(K, BN), 1);
+  if (mt == 2) {
+    switch (BN) {
+      case 64: return launch_gemm<64, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 128: return launch_gemm<128, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+      default: return launch_gemm<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+    }
+  }
   switch (BN) {
     case 64: return launch_gemm<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
     case 128: return launch_gemm<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -170,7 +201,22 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
   const int kpt = ceil_div(Ca, BK);
   GemmShape shp{R * T, Cn, 5 * kpt, kpt, 1};
   typename EpiStore<AT>::Params ep{y, y_f32, bias, nullptr, (long)Cn, 0, 0};
-  dim3 grid(ceil_div((long)R * T, 128), ceil_div(Cn, BN), 1);
+  const int mt = pick_mt((long)R * T, ceil_div(Cn, BN));
+  dim3 grid(ceil_div((long)R * T, 128 * mt), ceil_div(Cn, BN), 1);
+  if (mt == 2) {
+    if (!dgrad) {
+      switch (BN) {
+        case 64: return launch_gemm<64, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+        case 128: return launch_gemm<128, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+        default: return launch_gemm<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+      }
+    }
+    switch (BN) {
+      case 64: return launch_gemm<64, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 128: return launch_gemm<128, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+      default: return launch_gemm<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+    }
+  }
   if (!dgrad) {
     switch (BN) {
       case 64: return launch_gemm<64, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);

@@ -117,23 +117,29 @@ __host__ __device__ constexpr uint32_t instr_desc() {
          (static_cast<uint32_t>(BLOCK_N >> 3) << 17) | (static_cast<uint32_t>(kBlockM >> 4) << 24);
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int M_TILES = 1>
 constexpr int gemm_smem_bytes() {
-  return STAGES * (kBlockM * kSwizzleRow + BLOCK_N * kSwizzleRow) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return STAGES * (M_TILES * kBlockM * kSwizzleRow + BLOCK_N * kSwizzleRow) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, (Epi::kCtasPerSm == 2 && STAGES * (kBlockM + BLOCK_N) * kSwizzleRow <= 100 * 1024) ? 2 : 1)
+// M_TILES = 2: the CTA owns 256 output rows as two 128-row accumulators that share every B stage.  ncu shows the
+// 128 x 256 tile already pulls ~11.6 TB/s from L2 (profiles/r01_ncu_gemm_v1.txt), i.e. the big GEMMs are bound by L2->SM
+// bandwidth, not by the tensor pipe; the 256 x 256 tile moves 1/3 fewer operand bytes per FLOP.
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi, int M_TILES = 1>
+__global__ void __launch_bounds__(kGemmThreads, (Epi::kCtasPerSm == 2 && STAGES * (M_TILES * kBlockM + BLOCK_N) * kSwizzleRow <= 100 * 1024) ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const OperandWalk wa, const OperandWalk wb, const GemmShape shp, const typename Epi::Params ep) {
   constexpr int BLOCK_K = kSwizzleRow / ELEM_BYTES;  // 64 bf16 / 32 tf32
   constexpr int UMMA_K = 32 / ELEM_BYTES;            // 16 / 8
-  constexpr int STAGE_A = kBlockM * kSwizzleRow;
+  constexpr int TILE_A = kBlockM * kSwizzleRow;      // one 128-row A tile
+  constexpr int STAGE_A = M_TILES * TILE_A;
+  constexpr int TMEM_COLS = M_TILES * BLOCK_N;
+  static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
   constexpr int STAGE_B = BLOCK_N * kSwizzleRow;
   constexpr int A_BOXES = A_MN ? (kBlockM * ELEM_BYTES / kSwizzleRow) : 1;
   constexpr int B_BOXES = B_MN ? (BLOCK_N * ELEM_BYTES / kSwizzleRow) : 1;
   constexpr int MN_BOX_BYTES = BLOCK_K * kSwizzleRow;  // one MN-major box: BLOCK_K rows of 128 B
-  constexpr int A_BOX_BYTES = A_MN ? MN_BOX_BYTES : STAGE_A;
+  constexpr int A_BOX_BYTES = A_MN ? MN_BOX_BYTES : TILE_A;
   constexpr int B_BOX_BYTES = B_MN ? MN_BOX_BYTES : STAGE_B;
   constexpr uint32_t ADV_A = (A_MN ? UMMA_K * kSwizzleRow : 32) >> 4;  // descriptor advance per MMA (16 B units)
   constexpr uint32_t ADV_B = (B_MN ? UMMA_K * kSwizzleRow : 32) >> 4;
@@ -174,7 +180,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), BLOCK_N);
+    ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -197,13 +203,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
         const uint32_t sb = sa + STAGE_A;
 #pragma unroll
-        for (int i = 0; i < A_BOXES; ++i) {
-          int c[3];
+        for (int mt = 0; mt < M_TILES; ++mt) {
 #pragma unroll
-          for (int d = 0; d < 3; ++d)
-            c[d] = wa.base[d] + j * wa.per_j[d] + tap * wa.per_tap[d] + i * wa.per_box[d] + tile_m * wa.per_tile[d] +
-                   zb * wa.per_z[d];
-          ptx::tma_load_3d(sa + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
+          for (int i = 0; i < A_BOXES; ++i) {
+            int c[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+              c[d] = wa.base[d] + j * wa.per_j[d] + tap * wa.per_tap[d] + i * wa.per_box[d] +
+                     (tile_m * M_TILES + mt) * wa.per_tile[d] + zb * wa.per_z[d];
+            ptx::tma_load_3d(sa + mt * TILE_A + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
+          }
         }
 #pragma unroll
         for (int i = 0; i < B_BOXES; ++i) {
@@ -232,11 +241,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // only exist in the 32-byte-atom swizzle (4 k-rows per atom): layout type 1, SBO 512.
         constexpr uint32_t MN_LAYOUT = (ELEM_BYTES == 4) ? 1u : 2u;
         constexpr uint32_t MN_SBO = (ELEM_BYTES == 4) ? 512u : 1024u;
-        const uint64_t adesc = A_MN ? smem_desc(sa, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sa, 16, 1024, 2);
         const uint64_t bdesc = B_MN ? smem_desc(sb, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sb, 16, 1024, 2);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-          ptx::umma<ELEM_BYTES>(tmem_base, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        for (int mt = 0; mt < M_TILES; ++mt) {
+          const uint32_t sam = sa + mt * TILE_A;
+          const uint64_t adesc = A_MN ? smem_desc(sam, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sam, 16, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            ptx::umma<ELEM_BYTES>(tmem_base + mt * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
+                                  (it > 0 || k > 0) ? 1u : 0u);
+        }
         ptx::umma_commit(empty_bar(s));  // frees the smem slot once these MMAs retire
       }
       __syncwarp();
@@ -246,19 +260,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;  // which half of the tile's columns
-    const int row = q * 32 + lane;
-    const int m = tile_m * kBlockM + row;
+    const int half = (warp - 2) >> 2;  // M_TILES == 1: which half of the tile's columns; M_TILES == 2: which accumulator
+    const int mt = (M_TILES == 2) ? half : 0;
+    const int row = mt * kBlockM + q * 32 + lane;             // row inside the CTA tile
+    const int m = tile_m * (M_TILES * kBlockM) + row;
     const int n0 = tile_n * BLOCK_N;
-    const int col0 = half * (BLOCK_N / 2), col1 = col0 + BLOCK_N / 2;
+    const int col0 = (M_TILES == 2) ? 0 : half * (BLOCK_N / 2);
+    const int col1 = (M_TILES == 2) ? BLOCK_N : col0 + BLOCK_N / 2;
     Epi::template prefetch<BLOCK_N>(ep, m, n0, zb, col0, col1, shp);   // overlaps the main loop
     AccSource acc;
-    acc.taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    acc.taddr = tmem_base + mt * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
     acc.has_acc = num_local > 0;
     acc.partial = nullptr;
     acc.splits = shp.splits;
     acc.my_split = split;
-    acc.split_stride = static_cast<long>(kBlockM) * BLOCK_N;
+    acc.split_stride = static_cast<long>(M_TILES * kBlockM) * BLOCK_N;
     if (num_local > 0) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
@@ -267,7 +283,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     bool run_epilogue = true;
     if (Epi::kFixup && shp.splits > 1) {
       const long tile_id = (static_cast<long>(zb) * gridDim.y + tile_n) * gridDim.x + tile_m;
-      float* ws_row = shp.splitk_ws + (tile_id * shp.splits * kBlockM + row) * BLOCK_N;
+      float* ws_row = shp.splitk_ws + (tile_id * shp.splits * (M_TILES * kBlockM) + row) * BLOCK_N;
       float* mine = ws_row + split * acc.split_stride;
       for (int c = col0; c < col1; c += 32) {
         __syncwarp();
@@ -300,7 +316,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, BLOCK_N);
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

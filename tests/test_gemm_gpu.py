@@ -36,10 +36,17 @@ def _tol(name, ref):
     return (2.0 ** -8 if name == "bf16" else 2.0 ** -11) * ref.abs().max().item() + 1e-6
 
 
+@pytest.fixture(params=["1", "2"], ids=["rows128", "rows256"])
+def mt(request, monkeypatch):
+    """Force the 128-row (one accumulator) or 256-row (two accumulators sharing B) CTA tile of the GEMM kernel."""
+    monkeypatch.setenv("DVAE_GEMM_MT", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", DTS)
 @pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 0), (200, 80, 96, 0), (256, 256, 512, 0), (256, 256, 512, 128),
                                       (256, 256, 512, 64), (1024, 2048, 1024, 0), (130, 56, 32, 0), (64, 4096, 128, 128)])
-def test_linear_fwd(name, M, N, K, bn):
+def test_linear_fwd(name, M, N, K, bn, mt):
     _setup()
     from dvae_b200 import ops
     dt = _dt(name)
@@ -54,7 +61,7 @@ def test_linear_fwd(name, M, N, K, bn):
 @pytest.mark.parametrize("name", DTS)
 @pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 0), (200, 80, 96, 0), (256, 512, 256, 0), (256, 512, 256, 128),
                                       (512, 2048, 8192 // 8, 0), (130, 2048, 32, 0), (300, 64, 2048, 0)])
-def test_linear_dgrad(name, M, N, K, bn):
+def test_linear_dgrad(name, M, N, K, bn, mt):
     _setup()
     from dvae_b200 import ops
     dt = _dt(name)
@@ -83,7 +90,7 @@ def test_linear_wgrad(name, M, N, K):
 
 @pytest.mark.parametrize("name", DTS)
 @pytest.mark.parametrize("R,Cin,Cout", [(2, 64, 64), (3, 80, 512), (8, 512, 512), (5, 512, 80), (16, 512, 512)])
-def test_conv5(name, R, Cin, Cout):
+def test_conv5(name, R, Cin, Cout, mt):
     _setup()
     from dvae_b200 import ops
     dt = _dt(name)
