@@ -273,9 +273,9 @@ static int env_int(const char* name, int dflt) {
 // Gate tile of the forward recurrence (columns of one N tile = [i|f|g|o] x tile/4 hidden units).  Tunable for sweeps via
 // DVAE_LSTM_FWD_TILE / DVAE_LSTM_FWD_TILE_SMALL (read once; the weight permutation follows dvae_lstm_gate_tile()).
 static int lstm_fwd_bn(int H) {
-  static const int big = env_int("DVAE_LSTM_FWD_TILE", 128);
+  static const int big = env_int("DVAE_LSTM_FWD_TILE", 0);   // 0: by hidden size (profiles/r01_lstm_tile_sweep_v2.txt)
   static const int small = env_int("DVAE_LSTM_FWD_TILE_SMALL", 64);
-  int t = (H == 64) ? small : big;
+  int t = (H == 64) ? small : (big ? big : (H >= 1024 ? 256 : 128));
   if (t != 64 && t != 128 && t != 256) t = 128;
   while (t > 4 * H) t >>= 1;
   return t;

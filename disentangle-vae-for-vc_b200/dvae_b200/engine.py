@@ -122,6 +122,9 @@ class GradSink:
 class Engine:
     def __init__(self, dt: int, latent_dim: int, speaker_size: int, bn_eps: float = 1e-5, bn_momentum: float = 0.1):
         self.buckets = None   # set to a parallel.GradBuckets for data-parallel training
+        self.side_stream = None     # created lazily; weight-gradient GEMMs that are off the critical path run here
+        self.use_side_stream = True
+        self._keepalive: List[tuple] = []
         self.dt = dt
         self.L = latent_dim
         self.S = speaker_size
@@ -226,6 +229,24 @@ class Engine:
         outs = (recon[:R], recon[R:], hat[:R], hat[R:], q[0], q[1], q[2], q[3], zs[0], zs[1])
         return outs, saved
 
+    def _side_stream_ctx(self):
+        """Context that enqueues on the side stream, ordered after everything already enqueued on the current stream."""
+        import contextlib
+        if not self.use_side_stream:
+            return contextlib.nullcontext()
+        cur = torch.cuda.current_stream()
+        if self.side_stream is None or self.side_stream.device != cur.device:
+            self.side_stream = torch.cuda.Stream(device=cur.device)
+        if self.buckets is not None:
+            self.buckets.extra_streams = [self.side_stream]   # bucket all-reduces must also wait for side-stream gradients
+        self.side_stream.wait_stream(cur)
+        return torch.cuda.stream(self.side_stream)
+
+    def _join_side_stream(self):
+        if self.use_side_stream and self.side_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+        self._keepalive.clear()
+
     @staticmethod
     def discrete_decisions(saved: dict, outs, x1: Tensor, x2: Tensor) -> dict:
         """The branch decisions this forward took at the network's kinks: ReLU masks (reference layout [R, C, T] per
@@ -273,6 +294,9 @@ class Engine:
         return dout
 
     def _lstm_bwd(self, W, prefix: str, dh: Tensor, saved_layers: list, sink: GradSink, need_dx: bool):
+        """Back-propagation through time, layer by layer.  Only dX (needed by the layer below) is on the critical path:
+        the weight / bias gradient GEMMs of a layer are enqueued on a side stream so that they fill the SMs left idle by
+        the next layer's (small, latency-bound) recurrence kernels."""
         dt = self.dt
         for l in range(len(saved_layers) - 1, -1, -1):
             s = saved_layers[l]
@@ -282,6 +306,21 @@ class Engine:
             da = ops.lstm_bwd(dt, dh.reshape(rows, T, D * H), s["gates"], s["c_all"], lw["whh_n"], H, D)
             da2 = da.view(rows * T, D * 4 * H)
             x2 = s["x_in"].reshape(rows * T, In)
+            if l > 0 or need_dx:
+                dh, _ = ops.linear_dgrad(dt, da2, lw["wih_n"])
+                dh = dh.view(rows, T, In)
+            else:
+                dh = None
+            self._keepalive.append((da, x2))
+            with self._side_stream_ctx():
+                self._lstm_wgrads(prefix, l, s, da, da2, x2, sink)
+        return dh
+
+    def _lstm_wgrads(self, prefix: str, l: int, s: dict, da: Tensor, da2: Tensor, x2: Tensor, sink: GradSink):
+        dt = self.dt
+        D, H, lw = s["D"], s["H"], s["lw"]
+        In = lw["In"]
+        if True:
             if D == 1:   # gradients land directly in their final buffers
                 n_ih, n_hh = f"{prefix}.weight_ih_l{l}", f"{prefix}.weight_hh_l{l}"
                 ops.linear_wgrad(dt, da2, x2, sink.buf(n_ih, (4 * H, In)))
@@ -307,12 +346,6 @@ class Engine:
                     sink.put(f"{prefix}.weight_hh_l{l}{suf}", dwhh[d])
                     sink.put(f"{prefix}.bias_ih_l{l}{suf}", db[sl])
                     sink.put(f"{prefix}.bias_hh_l{l}{suf}", db[sl].clone())
-            if l > 0 or need_dx:
-                dh, _ = ops.linear_dgrad(dt, da2, lw["wih_n"])
-                dh = dh.view(rows, T, In)
-            else:
-                dh = None
-        return dh
 
     def _linear_bwd(self, name: str, W_act: Tensor, dy: Tensor, x: Tensor, sink: GradSink, relu_mask=None,
                     want_f32=False, need_dx: bool = True):
@@ -371,4 +404,5 @@ class Engine:
         d_flat = self._linear_bwd("enc_linear.linear_layer", W.lin["enc_linear.linear_layer"], d_e, saved["flat"], grads)
         dh = self._lstm_bwd(W, "enc_lstm", d_flat.view(R2, T_FRAMES, 128), saved["enc_lstm"], grads, need_dx=True)
         self._conv_stack_bwd(W, dh, saved["enc_convs"], grads, 2, need_dx=False)
+        self._join_side_stream()
         return sink.finish()

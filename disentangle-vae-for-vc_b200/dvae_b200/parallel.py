@@ -93,6 +93,7 @@ class GradBuckets:
         self.comm_stream = comm_stream if comm_stream is not None else (torch.cuda.Stream(self.device) if self.use_cuda else None)
         self._pending: List[set] = []
         self._works = []
+        self.extra_streams: List["torch.cuda.Stream"] = []   # other streams that also produce gradients (engine side stream)
         self.begin()
 
     @staticmethod
@@ -125,6 +126,8 @@ class GradBuckets:
         buf = self.flat[b]
         if self.use_cuda:
             self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+            for st in self.extra_streams:
+                self.comm_stream.wait_stream(st)
             with torch.cuda.stream(self.comm_stream):
                 dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg)
         else:
