@@ -20,6 +20,8 @@
 
 namespace dvae {
 
+static int env_int(const char* name, int dflt);
+
 template <int BN>
 struct Stages {
   static constexpr int value = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
@@ -46,8 +48,18 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const Opera
     configured = true;
   }
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
-  kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, wa, wb, shp, ep);
-  DVAE_CHECK_CUDA(cudaGetLastError());
+  static const int use_pdl = env_int("DVAE_PDL", 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  DVAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, wa, wb, shp, ep));
   return 0;
 }
 
@@ -345,6 +357,8 @@ __global__ void lstm_cell_bwd_kernel(const AT* __restrict__ dh_out, const float*
                                      const float* __restrict__ c_prev, float* __restrict__ dc, AT* __restrict__ da,
                                      int rows, int H, long ldh, long ldx, long z_h, long z_x, long z_cprev, long z_rec,
                                      int dc_zero) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int d = blockIdx.y;
   const int upr = H >> 3;  // 8-unit chunks per row
   const long total = static_cast<long>(rows) * upr;
@@ -424,12 +438,24 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
       long gx = (total + 255) / 256;
       if (gx > 148 * 8) gx = 148 * 8;
       dim3 cgrid((unsigned)gx, D);
-      lstm_cell_bwd_kernel<AT><<<cgrid, 256, 0, st>>>(
-          dh_all + (long)tf * D * H, s > 0 ? dh_rec : nullptr, gates + (long)tf * D * 4 * H, c_all + (long)tf * D * H,
-          (s == T - 1) ? nullptr : c_all + (long)(tf - 1) * D * H, dc_ws, da_all + (long)tf * D * 4 * H, rows, H, ldh, ldx,
-          H + (long)(tr - tf) * D * H, 4 * H + (long)(tr - tf) * D * 4 * H, H + (long)((tr + 1) - (tf - 1)) * D * H,
-          (long)rows * H, s == 0);
-      DVAE_CHECK_CUDA(cudaGetLastError());
+      {
+        static const int use_pdl = env_int("DVAE_PDL", 1);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = cgrid;
+        cfg.blockDim = dim3(256);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = use_pdl ? 1 : 0;
+        DVAE_CHECK_CUDA(cudaLaunchKernelEx(
+            &cfg, lstm_cell_bwd_kernel<AT>, (const AT*)(dh_all + (long)tf * D * H), (const float*)(s > 0 ? dh_rec : nullptr),
+            (const AT*)(gates + (long)tf * D * 4 * H), (const float*)(c_all + (long)tf * D * H),
+            (const float*)((s == T - 1) ? nullptr : c_all + (long)(tf - 1) * D * H), dc_ws, da_all + (long)tf * D * 4 * H, rows, H,
+            ldh, ldx, H + (long)(tr - tf) * D * H, 4 * H + (long)(tr - tf) * D * 4 * H,
+            H + (long)((tr + 1) - (tf - 1)) * D * H, (long)rows * H, (int)(s == 0)));
+      }
     }
     return 0;
   }

@@ -187,6 +187,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the set-up above overlapped the previous kernel; from here on we read / write its data
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   if (threadIdx.x == 0) phase_stamp(1);
 
   if (warp == 0) {
