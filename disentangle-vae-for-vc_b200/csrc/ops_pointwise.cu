@@ -99,6 +99,24 @@ __global__ void add_inplace_kernel(AT* __restrict__ a, const AT* __restrict__ b,
   }
 }
 
+// out (fp32) = a (fp32) + b (activation dtype): residual output that stays channels-last (AutoVC replica)
+template <typename AT>
+__global__ void add_f32_act_kernel(const float* __restrict__ a, const AT* __restrict__ b, float* __restrict__ out, long n) {
+  const long stride = static_cast<long>(gridDim.x) * blockDim.x * 8;
+  for (long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float u[8], v[8];
+      Act8<float>::load(a + i, u);
+      Act8<AT>::load(b + i, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] += v[k];
+      Act8<float>::store(out + i, u);
+    } else {
+      for (long j = i; j < n; ++j) out[j] = a[j] + to_f32(b[j]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ layout packing
 // x fp32 [R][C][T] (reference NCL) -> y act [R][T][C] (channels-last, the GEMM A-operand layout)
 template <typename AT>
@@ -422,6 +440,12 @@ extern "C" {
 int dvae_prep_cast(int dtype, const float* src, void* dst, long n, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_AT(dtype, cast_kernel<AT><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>(src, (AT*)dst, n));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int dvae_add_f32_act(int dtype, const float* a, const void* b, float* out, long n, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_AT(dtype, add_f32_act_kernel<AT><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>(a, (const AT*)b, out, n));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -360,34 +360,46 @@ __global__ void group_accumulate_kernel(const float* __restrict__ a, const float
   }
 }
 
-// rows <- group results.  PoG: var_g = 1/acc0 (exact zero -> 1e-6), mu_g = acc1 * var_g, logvar_g = log var_g.
-// Mean: acc / cnt.
+// group results, computed ONCE per group (not per row as in the reference's Python loop):
+// PoG: var_g = 1/acc0 (exact zero -> 1e-6), mu_g = acc1 * var_g, logvar_g = log var_g.   Mean: acc / cnt.
+__global__ void group_table_kernel(const float* __restrict__ acc, const float* __restrict__ cnt, float* __restrict__ table,
+                                   long G, int D, int mode) {
+  const long total = G * D;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long g = i / D;
+    const int d = static_cast<int>(i - g * D);
+    const float u = acc[(g * 2 + 0) * D + d], v = acc[(g * 2 + 1) * D + d];
+    float oa, ob;
+    if (mode == kModePoG) {
+      float var = 1.f / u;
+      oa = v * var;
+      var = var == 0.f ? 1e-6f : var;
+      ob = logf(var);
+    } else {
+      const float inv = 1.f / cnt[g];
+      oa = u * inv;
+      ob = v * inv;
+    }
+    table[(g * 2 + 0) * D + d] = oa;
+    table[(g * 2 + 1) * D + d] = ob;
+  }
+}
+// rows <- their group's entry: a pure gather / streaming-store pass (the table is small and stays in L2)
 template <int CPR>
-__global__ void group_finalize_kernel(const float* __restrict__ acc, const float* __restrict__ cnt,
-                                      const int* __restrict__ gid, float* __restrict__ out_a, float* __restrict__ out_b,
-                                      long B, int mode) {
+__global__ void group_broadcast_kernel(const float* __restrict__ table, const int* __restrict__ gid,
+                                       float* __restrict__ out_a, float* __restrict__ out_b, long B) {
   constexpr int D = CPR * 4;
   const long total = B * CPR;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const long r = i / CPR;
     const int c = static_cast<int>(i - r * CPR);
-    const int g = gid[r];
-    const float4 u = reinterpret_cast<const float4*>(acc + (static_cast<long>(g) * 2 + 0) * D)[c];
-    const float4 v = reinterpret_cast<const float4*>(acc + (static_cast<long>(g) * 2 + 1) * D)[c];
-    float4 oa, ob;
-    if (mode == kModePoG) {
-      float4 var = make_float4(1.f / u.x, 1.f / u.y, 1.f / u.z, 1.f / u.w);
-      oa = make_float4(v.x * var.x, v.y * var.y, v.z * var.z, v.w * var.w);
-      var.x = var.x == 0.f ? 1e-6f : var.x; var.y = var.y == 0.f ? 1e-6f : var.y;
-      var.z = var.z == 0.f ? 1e-6f : var.z; var.w = var.w == 0.f ? 1e-6f : var.w;
-      ob = make_float4(logf(var.x), logf(var.y), logf(var.z), logf(var.w));
-    } else {
-      const float inv = 1.f / cnt[g];
-      oa = make_float4(u.x * inv, u.y * inv, u.z * inv, u.w * inv);
-      ob = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    const int g = __ldg(gid + r);
+    const float4 oa = __ldg(reinterpret_cast<const float4*>(table + (static_cast<long>(g) * 2 + 0) * D) + c);
+    __stcs(reinterpret_cast<float4*>(out_a + r * D) + c, oa);
+    if (out_b != nullptr) {
+      const float4 ob = __ldg(reinterpret_cast<const float4*>(table + (static_cast<long>(g) * 2 + 1) * D) + c);
+      __stcs(reinterpret_cast<float4*>(out_b + r * D) + c, ob);
     }
-    reinterpret_cast<float4*>(out_a + r * D)[c] = oa;
-    if (out_b != nullptr) reinterpret_cast<float4*>(out_b + r * D)[c] = ob;
   }
 }
 
@@ -545,11 +557,13 @@ int dvae_group_accumulate(int mode, const float* a, const float* b, const int* g
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
-int dvae_group_finalize(int mode, const float* acc, const float* cnt, const int* gid, float* out_a, float* out_b, long B,
-                        int D, void* stream) {
+// table: fp32 [G][2][D] scratch that receives the per-group results; rows then gather from it
+int dvae_group_finalize(int mode, const float* acc, const float* cnt, const int* gid, float* table, float* out_a,
+                        float* out_b, long B, long G, int D, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  if (B == 0) return 0;
-  DISPATCH_CPR(D, { group_finalize_kernel<CPR><<<blocks_for(B * CPR, 256), 256, 0, st>>>(acc, cnt, gid, out_a, out_b, B, mode); });
+  if (B == 0 || G == 0) return 0;
+  group_table_kernel<<<blocks_for(G * D, 256), 256, 0, st>>>(acc, cnt, table, G, D, mode);
+  DISPATCH_CPR(D, { group_broadcast_kernel<CPR><<<blocks_for(B * CPR, 256), 256, 0, st>>>(table, gid, out_a, out_b, B); });
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

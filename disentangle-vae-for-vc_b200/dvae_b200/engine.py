@@ -34,37 +34,45 @@ LINEARS = ["enc_linear.linear_layer", "dec_pre_linear1", "dec_pre_linear2", "dec
 
 
 class PreparedWeights:
-    """Tensor-core copies of the fp32 parameters (rebuilt whenever the parameters change)."""
+    """Tensor-core copies of the fp32 parameters (rebuilt whenever the parameters change).
 
-    def __init__(self, dt: int, P: Dict[str, Tensor]):
+    The defaults describe DisentangledVAE; other networks built from the same layer kinds (the AutoVC replica) pass
+    their own lists of conv / linear / LSTM parameter prefixes."""
+
+    def __init__(self, dt: int, P: Dict[str, Tensor], convs=None, linears=None, lstms=None, fused_heads: bool = True):
         ad = ops.act_dtype(dt)
         self.dt = dt
         self.conv: Dict[str, Tensor] = {}
         self.lin: Dict[str, Tensor] = {}
         self.lstm: Dict[str, dict] = {}
-        for conv, _, _ in ENC_CONVS + DEC_CONVS + POST_CONVS:
+        convs = [c for c, _, _ in ENC_CONVS + DEC_CONVS + POST_CONVS] if convs is None else convs
+        linears = LINEARS if linears is None else linears
+        lstms = LSTMS if lstms is None else lstms
+        for conv in convs:
             self.conv[conv] = ops.prep_conv_weight(dt, P[conv + ".weight"])
-        for name in LINEARS:
+        for name in linears:
             w = P[name + ".weight"]
             c = torch.empty_like(w, dtype=ad)   # bf16 copy, or fp32 rounded onto the tf32 grid
             ops.prep_cast(dt, w, c)
             self.lin[name] = c
-        # style + content heads fused into one [2L, 2048] GEMM (rows: style_mu, style_logvar, content_mu, content_logvar)
-        ws, wc = P["style.linear_layer.weight"], P["content.linear_layer.weight"]
-        n_s, n_c = ws.shape[0], wc.shape[0]
-        heads_w = torch.empty((n_s + n_c, ws.shape[1]), device=ws.device, dtype=ad)
-        ops.prep_cast(dt, ws, heads_w[:n_s])
-        ops.prep_cast(dt, wc, heads_w[n_s:])
-        heads_b = torch.empty((n_s + n_c,), device=ws.device, dtype=torch.float32)
-        ops.copy_f32(P["style.linear_layer.bias"], heads_b[:n_s])
-        ops.copy_f32(P["content.linear_layer.bias"], heads_b[n_s:])
-        self.heads_w, self.heads_b, self.n_style = heads_w, heads_b, n_s
-        for prefix, (layers, D, H) in LSTMS.items():
+        if fused_heads:
+            # style + content heads fused into one [2L, 2048] GEMM (rows: style_mu, style_logvar, content_mu, content_logvar)
+            ws, wc = P["style.linear_layer.weight"], P["content.linear_layer.weight"]
+            n_s, n_c = ws.shape[0], wc.shape[0]
+            heads_w = torch.empty((n_s + n_c, ws.shape[1]), device=ws.device, dtype=ad)
+            ops.prep_cast(dt, ws, heads_w[:n_s])
+            ops.prep_cast(dt, wc, heads_w[n_s:])
+            heads_b = torch.empty((n_s + n_c,), device=ws.device, dtype=torch.float32)
+            ops.copy_f32(P["style.linear_layer.bias"], heads_b[:n_s])
+            ops.copy_f32(P["content.linear_layer.bias"], heads_b[n_s:])
+            self.heads_w, self.heads_b, self.n_style = heads_w, heads_b, n_s
+        dev0 = next(iter(P.values())).device
+        for prefix, (layers, D, H) in lstms.items():
             tile = lib.lstm_gate_tile(H)
             per_layer = []
             for l in range(layers):
                 In = P[f"{prefix}.weight_ih_l{l}"].shape[1]
-                dev = ws.device
+                dev = dev0
                 wih_p = torch.empty((D * 4 * H, In), device=dev, dtype=ad)
                 wih_n = torch.empty((D * 4 * H, In), device=dev, dtype=ad)
                 whh_p = torch.empty((D, 4 * H, H), device=dev, dtype=ad)

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "dvae_prep_cast": [_i, _p, _p, _l, _p],
     "dvae_add_inplace": [_i, _p, _p, _l, _p],
     "dvae_copy_f32": [_p, _p, _l, _p],
+    "dvae_add_f32_act": [_i, _p, _p, _p, _l, _p],
     "dvae_prep_conv_weight": [_i, _p, _p, _i, _i, _p],
     "dvae_conv_wgrad_unpack": [_p, _p, _i, _i, _p],
     "dvae_prep_lstm_weight": [_i, _p, _p, _i, _i, _i, _p],
@@ -63,7 +64,7 @@ _SIGNATURES = {
     "dvae_loss_bwd": [_p] * 6 + [_l] + [_p] * 4 + [_i, _i, _p, _p, _i, _f, _f, _f] + [_p] * 11 + [_p],
     "dvae_segment_ids_sorted": [_p, _p, _p, _p, _l, _p],
     "dvae_group_accumulate": [_i, _p, _p, _p, _p, _p, _l, _i, _p],
-    "dvae_group_finalize": [_i, _p, _p, _p, _p, _p, _l, _i, _p],
+    "dvae_group_finalize": [_i, _p, _p, _p, _p, _p, _p, _l, _l, _i, _p],
     "dvae_group_pog_bwd": [_p] * 7 + [_l, _i, _p],
     "dvae_group_reparam": [_p] * 5 + [_l, _i, _p],
 }
@@ -100,7 +101,8 @@ def stream():
 
 # kernels launched per C-ABI call (bench.py reports the total as `gpu_launches`)
 LAUNCHES = 0
-_LAUNCHES_PER_CALL = {"dvae_bn_train_fwd": 3, "dvae_bn_train_bwd": 3, "dvae_bn_eval_fwd": 2, "dvae_segment_ids_sorted": 3}
+_LAUNCHES_PER_CALL = {"dvae_bn_train_fwd": 3, "dvae_bn_train_bwd": 3, "dvae_bn_eval_fwd": 2, "dvae_segment_ids_sorted": 3,
+                      "dvae_group_finalize": 2}
 _TIME_STEP_ARG = {"dvae_lstm_fwd": 6, "dvae_lstm_bwd": 10}   # (lstm_bwd: 2 kernels per step, counted below)   # index of T: one GEMM launch per time step
 
 

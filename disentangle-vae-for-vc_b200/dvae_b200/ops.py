@@ -164,6 +164,14 @@ def prep_cast(dt: int, src: Tensor, dst: Tensor) -> None:
     call("dvae_prep_cast", dt, ptr(src), ptr(dst), src.numel(), stream())
 
 
+def add_f32_act(dt: int, a: Tensor, b: Tensor) -> Tensor:
+    """fp32 out = a (fp32) + b (activation dtype), same shape."""
+    _chk(a, torch.float32), _chk(b, act_dtype(dt))
+    out = torch.empty_like(a)
+    call("dvae_add_f32_act", dt, ptr(a), ptr(b), ptr(out), a.numel(), stream())
+    return out
+
+
 def add_inplace(dt: int, a: Tensor, b: Tensor) -> None:
     _chk(a, act_dtype(dt)), _chk(b, act_dtype(dt))
     assert a.numel() == b.numel()
@@ -363,7 +371,8 @@ def group_accumulate(mode: int, a: Tensor, b: Tensor, gid: Tensor, G: int):
 def group_finalize(mode: int, acc: Tensor, cnt: Tensor, gid: Tensor, B: int, D: int, want_b: bool = True):
     out_a = torch.empty((B, D), device=acc.device, dtype=torch.float32)
     out_b = torch.empty((B, D), device=acc.device, dtype=torch.float32) if want_b else None
-    call("dvae_group_finalize", mode, ptr(acc), ptr(cnt), ptr(gid), ptr(out_a), ptr(out_b), B, D, stream())
+    table = torch.empty_like(acc)
+    call("dvae_group_finalize", mode, ptr(acc), ptr(cnt), ptr(gid), ptr(table), ptr(out_a), ptr(out_b), B, acc.shape[0], D, stream())
     return out_a, out_b
 
 

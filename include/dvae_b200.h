@@ -54,6 +54,7 @@ int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* 
 int dvae_prep_cast(int dtype, const float* src, void* dst, long n, void* stream);
 int dvae_copy_f32(const float* src, float* dst, long n, void* stream);
 int dvae_add_inplace(int dtype, void* a, const void* b, long n, void* stream);
+int dvae_add_f32_act(int dtype, const float* a, const void* b, float* out, long n, void* stream);  /* residual, channels-last */
 int dvae_prep_conv_weight(int dtype, const float* w, void* wk, int Co, int Ci, void* stream);
 int dvae_conv_wgrad_unpack(const float* dwk, float* dw, int Co, int Ci, void* stream);
 int dvae_prep_lstm_weight(int dtype, const float* w, void* dst, int H, int In, int tile, void* stream);
@@ -102,8 +103,8 @@ int dvae_loss_bwd(const float* x1, const float* x2, const float* r1, const float
 int dvae_segment_ids_sorted(const long long* labels, int* gid, int* scratch, int* num_groups, long B, void* stream);
 int dvae_group_accumulate(int mode, const float* a, const float* b, const int* gid, float* acc, float* cnt, long B, int D,
                           void* stream);
-int dvae_group_finalize(int mode, const float* acc, const float* cnt, const int* gid, float* out_a, float* out_b, long B,
-                        int D, void* stream);
+int dvae_group_finalize(int mode, const float* acc, const float* cnt, const int* gid, float* table, float* out_a,
+                        float* out_b, long B, long G, int D, void* stream);
 int dvae_group_pog_bwd(const float* mu, const float* logvar, const int* gid, const float* acc_f, const float* acc_g,
                        float* dmu, float* dlv, long B, int D, void* stream);
 int dvae_group_reparam(const float* mu, const float* logvar, const int* gid, const float* eps_group, float* z, long B, int D,

@@ -174,6 +174,32 @@ def main():
                        "gid": torch.from_numpy(gid), "counts": torch.from_numpy(counts)}
         print(f"[PoG {name}] oracle vs reference max-abs {d:.3e}")
     torch.save(cases, os.path.join(out_dir, "pog_cases.pt"))
+    # ---------------- AutoVC-style generator (autovc_replicate/proposed_autovc.py, BASELINE config 5) ---------------
+    import io, contextlib
+    from oracle import autovc_oracle as A
+    with contextlib.redirect_stdout(io.StringIO()):       # the reference module runs a forward + print at import (:223-227)
+        import autovc_replicate.proposed_autovc as ref_avc
+    gen = ref_avc.Generator()
+    asd = A.synth_state_dict(0)
+    assert list(gen.state_dict().keys()) == list(asd.keys()), "autovc state_dict inventory / order mismatch"
+    gen.load_state_dict(asd)
+    gen.train()
+    ax, _, _ = O.synth_inputs(4, seed=4321)
+    mel, mel_post = gen(ax)
+    loss = A.sq_loss(ax, mel, mel_post)
+    loss.backward()
+    agr = {k: p.grad for k, p in gen.named_parameters()}
+    osd = O.clone_sd(asd, requires_grad=True)
+    (o_mel, o_post), o_loss, o_gr = A.train_step(osd, ax)
+    w = max((mel - o_mel).abs().max().item(), (mel_post - o_post).abs().max().item())
+    gw = max((agr[k] - o_gr[k]).norm().item() / (agr[k].norm().item() + 1e-20) for k in agr)
+    print(f"[autovc R=4] oracle vs reference: outputs max-abs {w:.3e}, loss rel {abs(loss.item() - o_loss.item()) / abs(loss.item()):.3e}, grad rel-L2 {gw:.3e}")
+    assert w < 1e-5 and gw < 1e-4
+    torch.save({"R": 4, "inputs_seed": 4321, "mel": mel.detach().clone(), "mel_postnet": mel_post.detach().clone(),
+                "loss": loss.detach().clone(), "grad_digest": {k: grad_digest(g, k) for k, g in agr.items()},
+                "state_dict_keys": list(asd.keys()),
+                "bn_buffers_after": {k: v.clone() for k, v in gen.state_dict().items() if "running_" in k}},
+               os.path.join(out_dir, "autovc_R4.pt"))
     for f in sorted(os.listdir(out_dir)):
         print(f, os.path.getsize(os.path.join(out_dir, f)))
 

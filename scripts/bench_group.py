@@ -20,6 +20,7 @@ assert int(ng.item()) == G
 acc = torch.zeros(G, 2, D, device="cuda")
 cnt = torch.zeros(G, device="cuda")
 out_a, out_b = torch.empty_like(mu), torch.empty_like(mu)
+table = torch.empty_like(acc)
 from dvae_b200.lib import call, ptr, stream
 
 
@@ -29,7 +30,7 @@ def accumulate():
 
 
 def finalize():
-    call("dvae_group_finalize", ops.MODE_POG, ptr(acc), ptr(cnt), ptr(gid), ptr(out_a), ptr(out_b), B, D, stream())
+    call("dvae_group_finalize", ops.MODE_POG, ptr(acc), ptr(cnt), ptr(gid), ptr(table), ptr(out_a), ptr(out_b), B, G, D, stream())
 
 
 def timeit(fn, n=10):

@@ -1,0 +1,88 @@
+"""AutoVC-style generator (BASELINE config 5; reference autovc_replicate/proposed_autovc.py): oracle vs the golden vectors
+frozen from the reference (CPU), and the dvae_b200 drop-in vs the oracle (GPU, matched ReLU decisions for gradients)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import autovc_oracle as A
+from oracle import dvae_oracle as O
+
+
+def test_oracle_matches_reference_golden(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "autovc_R4.pt"))
+    sd = A.synth_state_dict(0)
+    assert list(sd.keys()) == gold["state_dict_keys"] and len(sd) == 111
+    assert sum(v.numel() for k, v in sd.items() if v.is_floating_point() and "running" not in k) == 31807040
+    x, _, _ = O.synth_inputs(gold["R"], seed=gold["inputs_seed"])
+    osd = O.clone_sd(sd, requires_grad=True)
+    (mel, post), loss, grads = A.train_step(osd, x)
+    assert tuple(mel.shape) == (4, 1, 64, 80) and tuple(post.shape) == (4, 1, 64, 80)
+    assert torch.allclose(mel, gold["mel"], atol=1e-5) and torch.allclose(post, gold["mel_postnet"], atol=1e-5)
+    assert abs(loss.item() - gold["loss"].item()) <= 1e-5 * abs(gold["loss"].item())
+    for k, d in gold["grad_digest"].items():
+        g = grads[k].detach().reshape(-1).double()
+        assert abs(g.norm().item() - d["norm"]) <= 1e-3 * d["norm"] + 1e-9, k
+    for k, v in gold["bn_buffers_after"].items():
+        assert torch.allclose(osd[k].float(), v.float(), atol=1e-6), k
+
+
+def test_dropin_surface():
+    import inspect
+    from autovc_replicate.proposed_autovc import Decoder, Encoder, Generator, Postnet
+    assert list(inspect.signature(Generator.__init__).parameters)[1:4] == ["dim_neck", "dim_emb", "dim_pre"]
+    g = Generator()
+    assert list(g.state_dict().keys()) == list(A.param_and_buffer_shapes().keys())
+    g.load_state_dict(A.synth_state_dict(0))
+    assert isinstance(g.encoder, Encoder) and isinstance(g.decoder, Decoder) and isinstance(g.postnet, Postnet)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        g(torch.rand(2, 80, 64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["bf16", "tf32"])
+def test_generator_parity_gpu(name):
+    from autovc_replicate.proposed_autovc import Generator
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    R = 6
+    sd = A.synth_state_dict(0)
+    x, _, _ = O.synth_inputs(R, seed=99)
+    x = x.cuda()
+    g = Generator(precision=name).cuda()
+    g.load_state_dict(sd)
+    g.train()
+    g._debug_keep_saved = True
+    mel, post = g(x)
+    A.sq_loss(x, mel, post).backward()
+    saved = g._last_saved
+    dec = {}
+    for group, key in (("enc_convs", "encoder.convolutions"), ("dec_convs", "decoder.convolutions")):
+        for i, s in enumerate(saved[group]):
+            z = s["y"].float() * s["stat"][0, 2] + s["stat"][0, 3]
+            dec[f"{key}.{i}:0"] = (z > 0).transpose(1, 2)
+    osd = O.clone_sd(sd, requires_grad=True, device="cuda")
+    (o_mel, o_post), o_loss, _ = A.train_step(osd, x)
+    osd2 = O.clone_sd(sd, requires_grad=True, device="cuda")
+    _, _, o_grads = A.train_step(osd2, x, decisions=dec)
+    tol, hat_tol = ({"bf16": 1.5e-2, "tf32": 2e-3}[name], {"bf16": 4e-2, "tf32": 5e-3}[name])
+    assert (mel - o_mel).norm().item() / o_mel.norm().item() <= tol
+    assert (post - o_post).norm().item() / o_post.norm().item() <= hat_tol
+    worst, dot, na, nb = (1.0, ""), 0.0, 0.0, 0.0
+    wscale = max(v.norm().item() for v in o_grads.values())
+    for k, p in g.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape, k
+        if k.endswith(".0.conv.bias"):          # feeds a train-mode BatchNorm: gradient identically zero
+            assert p.grad.norm().item() <= 1e-4 * wscale, k
+            continue
+        a, b = p.grad.flatten().double(), o_grads[k].flatten().double()
+        worst = min(worst, (F.cosine_similarity(a, b, dim=0).item(), k))
+        dot, na, nb = dot + (a * b).sum().item(), na + (a * a).sum().item(), nb + (b * b).sum().item()
+    assert worst[0] > {"bf16": 0.96, "tf32": 0.999}[name], worst
+    assert dot / (na * nb) ** 0.5 > {"bf16": 0.997, "tf32": 0.9999}[name]
+    for k, b in g.named_buffers():
+        if k.endswith("num_batches_tracked"):
+            assert int(b.item()) == 1
+        else:
+            assert torch.allclose(b, osd[k], atol=5e-3 if name == "bf16" else 5e-4, rtol=1e-2), k
