@@ -63,6 +63,51 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const Opera
   return 0;
 }
 
+// Persistent launch: one CTA per SM looping over all (m, n, batch x split) tiles.  Used when there are at least two
+// tiles per SM; smaller problems (LSTM steps, M = 1024 linears) keep the one-tile-per-CTA kernel.
+template <int BN, bool A_MN, bool B_MN, int EB, class Epi>
+static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const OperandWalk& wa, const OperandWalk& wb,
+                                  const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream) {
+  static_assert(BN <= 256, "");
+  constexpr int ST = Stages<BN>::value + (BN == 128 ? 3 : (BN == 64 ? 4 : 0));   // 1 CTA / SM: use the whole 227 KB
+  auto kern = tc_gemm_persistent_kernel<BN, ST, A_MN, B_MN, EB, Epi>;
+  constexpr int smem = gemm_smem_bytes<BN, ST>();
+  static_assert(smem <= 227 * 1024, "persistent GEMM shared memory");
+  static bool configured = false;
+  if (!configured) {
+    DVAE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles_m = grid.x, tiles_n = grid.y;
+  const long num_tiles = static_cast<long>(grid.x) * grid.y * grid.z;
+  if (num_tiles == 0) return 0;
+  if (shp.num_kb <= 0 || (Epi::kFixup && shp.splits > 1)) {
+    set_last_error("persistent GEMM needs K > 0 and supports split-K only for accumulate epilogues");
+    return 1;
+  }
+  static const int use_pdl = env_int("DVAE_PDL", 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(num_tiles < num_sms() ? num_tiles : num_sms()));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  DVAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, wa, wb, shp, ep, tiles_m, tiles_n, static_cast<int>(num_tiles)));
+  return 0;
+}
+
+// DVAE_GEMM_PERSISTENT = 0 disables, 1 forces (tests); default: when the grid has >= 2 tiles per SM
+static bool want_persistent(dim3 grid) {
+  const char* v = getenv("DVAE_GEMM_PERSISTENT");
+  if (v && *v == '0') return false;
+  if (v && *v == '1') return true;
+  return static_cast<long>(grid.x) * grid.y * grid.z >= 2L * num_sms();
+}
+
 static OperandWalk zero_walk() {
   OperandWalk w;
   for (int d = 0; d < 3; ++d) w.base[d] = w.per_j[d] = w.per_tap[d] = w.per_box[d] = w.per_tile[d] = w.per_z[d] = 0;
@@ -76,8 +121,8 @@ static int pick_mt(long M, int n_tiles_total) {
   const char* v = getenv("DVAE_GEMM_MT");
   if (v && *v == '1') return 1;
   if (v && *v == '2') return 2;
-  const long ctas = ((M + 255) / 256) * n_tiles_total;
-  return ctas >= 2L * num_sms() ? 2 : 1;
+  (void)M; (void)n_tiles_total;
+  return 1;   // measured: the 256-row tile is not faster (profiles/): the persistent 128-row kernel is the default
 }
 
 // ------------------------------------------------------------------------------------ Linear
@@ -102,6 +147,13 @@ static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, A
       case 64: return launch_gemm<64, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
       case 128: return launch_gemm<128, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
       default: return launch_gemm<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+    }
+  }
+  if (want_persistent(grid)) {
+    switch (BN) {
+      case 64: return launch_gemm_persistent<64, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 128: return launch_gemm_persistent<128, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      default: return launch_gemm_persistent<256, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
     }
   }
   switch (BN) {
@@ -133,6 +185,13 @@ static int linear_dgrad_t(const AT* dy, long lddy, const AT* w, AT* dx, float* d
       case 64: return launch_gemm<64, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
       case 128: return launch_gemm<128, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
       default: return launch_gemm<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+    }
+  }
+  if (want_persistent(grid)) {
+    switch (BN) {
+      case 64: return launch_gemm_persistent<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 128: return launch_gemm_persistent<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      default: return launch_gemm_persistent<256, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
     }
   }
   switch (BN) {
@@ -168,6 +227,10 @@ static int linear_wgrad_t(const AT* dy, long lddy, const AT* x, long ldx, float*
   GemmShape shp{N, K, num_kb, num_kb, pick_splits(tiles, num_kb)};
   EpiAtomic::Params ep{dw, lddw, 0};
   dim3 grid(ceil_div(N, 128), ceil_div(K, BN), shp.splits);
+  if (want_persistent(grid)) {
+    if (BN == 64) return launch_gemm_persistent<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
+    return launch_gemm_persistent<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
+  }
   if (BN == 64) return launch_gemm<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
   return launch_gemm<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
 }
@@ -229,6 +292,20 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
       default: return launch_gemm<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
     }
   }
+  if (want_persistent(grid)) {
+    if (!dgrad) {
+      switch (BN) {
+        case 64: return launch_gemm_persistent<64, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+        case 128: return launch_gemm_persistent<128, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+        default: return launch_gemm_persistent<256, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      }
+    }
+    switch (BN) {
+      case 64: return launch_gemm_persistent<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 128: return launch_gemm_persistent<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      default: return launch_gemm_persistent<256, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    }
+  }
   if (!dgrad) {
     switch (BN) {
       case 64: return launch_gemm<64, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -263,6 +340,10 @@ static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, in
   GemmShape shp{Cout, Cin, num_kb, kpt, pick_splits(tiles, num_kb)};
   EpiAtomic::Params ep{dwk, (long)5 * Cin, (long)Cin};
   dim3 grid(ceil_div(Cout, 128), ceil_div(Cin, BN), 5 * shp.splits);
+  if (want_persistent(grid)) {
+    if (BN == 64) return launch_gemm_persistent<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
+    return launch_gemm_persistent<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
+  }
   if (BN == 64) return launch_gemm<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
   return launch_gemm<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
 }

@@ -324,6 +324,192 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // =====================================================================================
+// Persistent variant for the large contractions (conv / linear / x-projection, forward, dgrad and wgrad): one CTA per
+// SM loops over output tiles; the accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile
+// i overlaps the main loop of tile i+1, and the TMA ring keeps running across tile boundaries (no cold start per tile).
+// ncu on the one-tile-per-CTA kernel: tensor pipe active 52 %, of which the un-overlapped epilogue + tile start cost
+// ~30 % (profiles/r01_phase_timing_v2.txt).  Split-K is supported for accumulate-type epilogues only (no fix-up).
+// =====================================================================================
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const OperandWalk wa, const OperandWalk wb, const GemmShape shp, const typename Epi::Params ep,
+                          const int tiles_m, const int tiles_n, const int num_tiles) {
+  constexpr int BLOCK_K = kSwizzleRow / ELEM_BYTES;
+  constexpr int UMMA_K = 32 / ELEM_BYTES;
+  constexpr int STAGE_A = kBlockM * kSwizzleRow;
+  constexpr int STAGE_B = BLOCK_N * kSwizzleRow;
+  constexpr int A_BOXES = A_MN ? (kBlockM * ELEM_BYTES / kSwizzleRow) : 1;
+  constexpr int B_BOXES = B_MN ? (BLOCK_N * ELEM_BYTES / kSwizzleRow) : 1;
+  constexpr int MN_BOX_BYTES = BLOCK_K * kSwizzleRow;
+  constexpr int A_BOX_BYTES = A_MN ? MN_BOX_BYTES : STAGE_A;
+  constexpr int B_BOX_BYTES = B_MN ? MN_BOX_BYTES : STAGE_B;
+  constexpr uint32_t ADV_A = (A_MN ? UMMA_K * kSwizzleRow : 32) >> 4;
+  constexpr uint32_t ADV_B = (B_MN ? UMMA_K * kSwizzleRow : 32) >> 4;
+  constexpr uint32_t IDESC = instr_desc<ELEM_BYTES, BLOCK_N, A_MN, B_MN>();
+  constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "two accumulators must fit TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t smem_base = raw_addr + pad;
+  const uint32_t bar_base = smem_base + STAGES * (STAGE_A + STAGE_B);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * (STAGE_A + STAGE_B) + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kb_chunk = (shp.num_kb + shp.splits - 1) / shp.splits;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tmem_full_bar(a), 1);
+      ptx::mbar_init(tmem_empty_bar(a), kEpilogueThreads / 32);   // one arrival per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+
+  // tile -> (tile_m, tile_n, batch zb, split): m fastest, so CTAs running side by side share the B (weight) tile in L2
+  auto decode = [&](int tile, int& tm, int& tn, int& zb, int& split) {
+    tm = tile % tiles_m;
+    const int rest = tile / tiles_m;
+    tn = rest % tiles_n;
+    const int zz = rest / tiles_n;
+    zb = zz / shp.splits;
+    split = zz - zb * shp.splits;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;   // running k-block counter of this CTA: the ring never drains between tiles
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int tm, tn, zb, split;
+        decode(tile, tm, tn, zb, split);
+        const int kb_begin = split * kb_chunk;
+        const int kb_end = min(shp.num_kb, kb_begin + kb_chunk);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(empty_bar(s), ph ^ 1u);
+          ptx::mbar_expect_tx(full_bar(s), STAGE_A + STAGE_B);
+          const int tap = kb / shp.kb_per_tap;
+          const int j = kb - tap * shp.kb_per_tap;
+          const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
+          const uint32_t sb = sa + STAGE_A;
+#pragma unroll
+          for (int i = 0; i < A_BOXES; ++i) {
+            int c[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+              c[d] = wa.base[d] + j * wa.per_j[d] + tap * wa.per_tap[d] + i * wa.per_box[d] + tm * wa.per_tile[d] +
+                     zb * wa.per_z[d];
+            ptx::tma_load_3d(sa + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
+          }
+#pragma unroll
+          for (int i = 0; i < B_BOXES; ++i) {
+            int c[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+              c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + i * wb.per_box[d] + tn * wb.per_tile[d] +
+                     zb * wb.per_z[d];
+            ptx::tma_load_3d(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t MN_LAYOUT = (ELEM_BYTES == 4) ? 1u : 2u;
+    constexpr uint32_t MN_SBO = (ELEM_BYTES == 4) ? 512u : 1024u;
+    int it = 0, local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      int tm, tn, zb, split;
+      decode(tile, tm, tn, zb, split);
+      const int kb_begin = split * kb_chunk;
+      const int num_local = max(0, min(shp.num_kb, kb_begin + kb_chunk) - kb_begin);
+      const int as = local & 1;
+      ptx::mbar_wait(tmem_empty_bar(as), ((local >> 1) & 1) ^ 1u);   // epilogue has drained this accumulator
+      ptx::tc_fence_after();
+      for (int k0 = 0; k0 < num_local; ++k0, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        ptx::mbar_wait(full_bar(s), ph);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
+          const uint32_t sb = sa + STAGE_A;
+          const uint64_t adesc = A_MN ? smem_desc(sa, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sa, 16, 1024, 2);
+          const uint64_t bdesc = B_MN ? smem_desc(sb, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sb, 16, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            ptx::umma<ELEM_BYTES>(tmem_base + as * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
+                                  (k0 > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit(empty_bar(s));
+        }
+        __syncwarp();
+      }
+      if (lane == 0) ptx::umma_commit(tmem_full_bar(as));
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int col0 = half * (BLOCK_N / 2), col1 = col0 + BLOCK_N / 2;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      int tm, tn, zb, split;
+      decode(tile, tm, tn, zb, split);
+      const int as = local & 1;
+      const int m = tm * kBlockM + q * 32 + lane;
+      const int n0 = tn * BLOCK_N;
+      Epi::template prefetch<BLOCK_N>(ep, m, n0, zb, col0, col1, shp);
+      const int kb_begin = split * kb_chunk;
+      AccSource acc;
+      acc.taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      acc.has_acc = min(shp.num_kb, kb_begin + kb_chunk) > kb_begin;   // an empty trailing split contributes nothing
+      acc.partial = nullptr;
+      acc.splits = shp.splits;
+      acc.my_split = split;
+      acc.split_stride = 0;
+      ptx::mbar_wait(tmem_full_bar(as), (local >> 1) & 1);
+      ptx::tc_fence_after();
+      Epi::template run<BLOCK_N>(ep, acc, m, n0, zb, col0, col1, shp);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));   // this warp no longer reads accumulator `as`
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// =====================================================================================
 // Epilogues.  Each receives the TMEM address of its warp's 32-lane slice; thread `lane` owns
 // output row m and reads BLOCK_N fp32 columns in chunks.
 // =====================================================================================

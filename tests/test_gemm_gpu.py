@@ -36,10 +36,16 @@ def _tol(name, ref):
     return (2.0 ** -8 if name == "bf16" else 2.0 ** -11) * ref.abs().max().item() + 1e-6
 
 
-@pytest.fixture(params=["1", "2"], ids=["rows128", "rows256"])
+@pytest.fixture(params=["1", "2", "p"], ids=["rows128", "rows256", "persistent"])
 def mt(request, monkeypatch):
-    """Force the 128-row (one accumulator) or 256-row (two accumulators sharing B) CTA tile of the GEMM kernel."""
-    monkeypatch.setenv("DVAE_GEMM_MT", request.param)
+    """GEMM kernel variant: one tile per CTA with a 128-row or a 256-row (two accumulators sharing B) tile, or the
+    persistent kernel (one CTA per SM, double-buffered TMEM accumulators)."""
+    if request.param == "p":
+        monkeypatch.setenv("DVAE_GEMM_MT", "1")
+        monkeypatch.setenv("DVAE_GEMM_PERSISTENT", "1")
+    else:
+        monkeypatch.setenv("DVAE_GEMM_MT", request.param)
+        monkeypatch.setenv("DVAE_GEMM_PERSISTENT", "0")
     return request.param
 
 
@@ -75,7 +81,7 @@ def test_linear_dgrad(name, M, N, K, bn, mt):
 
 @pytest.mark.parametrize("name", DTS)
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 80, 96), (4096, 256, 512), (1024, 2048, 32), (777, 64, 2048)])
-def test_linear_wgrad(name, M, N, K):
+def test_linear_wgrad(name, M, N, K, mt):
     _setup()
     from dvae_b200 import ops
     dt = _dt(name)
