@@ -100,11 +100,16 @@ static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, 
   return 0;
 }
 
+// Background mode (dvae_set_background): GEMMs that run on a side stream next to latency-critical kernels keep the
+// one-tile-per-CTA kernel (96 KB CTAs that co-reside with the LSTM step kernels) instead of taking whole SMs.
+static thread_local int g_background = 0;
+
 // DVAE_GEMM_PERSISTENT = 0 disables, 1 forces (tests); default: when the grid has >= 2 tiles per SM
 static bool want_persistent(dim3 grid) {
   const char* v = getenv("DVAE_GEMM_PERSISTENT");
   if (v && *v == '0') return false;
   if (v && *v == '1') return true;
+  if (g_background) return false;
   return static_cast<long>(grid.x) * grid.y * grid.z >= 2L * num_sms();
 }
 
@@ -690,6 +695,12 @@ int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* 
 }
 
 int dvae_lstm_gate_tile(int H) { return lstm_fwd_bn(H); }
+
+// 1: subsequent GEMM launches from this host thread are background work (see want_persistent); 0: normal
+int dvae_set_background(int on) {
+  g_background = on;
+  return 0;
+}
 
 // debugging aid: install (or remove, buf = NULL) a device buffer of capacity*5 uint64 phase stamps written by every
 // tc_gemm_kernel CTA (see phase_stamp in tc_gemm.cuh)

@@ -321,7 +321,11 @@ class Engine:
                 dh = None
             self._keepalive.append((da, x2))
             with self._side_stream_ctx():
-                self._lstm_wgrads(prefix, l, s, da, da2, x2, sink)
+                lib.call("dvae_set_background", 1)
+                try:
+                    self._lstm_wgrads(prefix, l, s, da, da2, x2, sink)
+                finally:
+                    lib.call("dvae_set_background", 0)
         return dh
 
     def _lstm_wgrads(self, prefix: str, l: int, s: dict, da: Tensor, da2: Tensor, x2: Tensor, sink: GradSink):

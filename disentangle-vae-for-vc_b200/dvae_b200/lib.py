@@ -39,6 +39,7 @@ _SIGNATURES = {
     "dvae_lstm_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_lstm_bwd_workspace": [_i, _i, _i, _i, _p, _p],
     "dvae_debug_timing": [_p, _i],
+    "dvae_set_background": [_i],
     "dvae_lstm_wgrad_hh": [_i, _p, _p, _p, _i, _i, _i, _i, _p],
     # weight preparation / layout
     "dvae_prep_cast": [_i, _p, _p, _l, _p],

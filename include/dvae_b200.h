@@ -22,6 +22,7 @@ const char* dvae_last_error(void);
 int dvae_version(void);
 int dvae_sm_arch(void);              /* 100: built for sm_100a only */
 int dvae_lstm_gate_tile(int H);
+int dvae_set_background(int on);   /* GEMMs launched while on: small-footprint kernels that co-run with a latency-critical stream */
 int dvae_debug_timing(unsigned long long* buf, int capacity);   /* optional per-CTA phase stamps of the GEMM kernel (debug) */      /* gate-interleave tile (columns) used by the LSTM forward for hidden size H */
 
 /* ---- nn.Linear (model/disentangled_vae.py:98-100 LinearNorm.forward; :165-171, :194, :211-213, :232-233, :247) */
