@@ -145,6 +145,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     os.environ["DVAE_B200_PRECISION"] = args.precision
     from dvae_b200 import lib, ops
