@@ -11,6 +11,16 @@ template <typename T>
 struct Act8;  // pack / unpack 8 consecutive activations
 template <>
 struct Act8<float> {
+  struct raw_t { float4 a, b; };   // 8 values still "in flight": loads can be issued long before they are consumed
+  static __device__ __forceinline__ raw_t load_raw(const float* p) {
+    raw_t r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
+  }
+  static __device__ __forceinline__ void unpack(const raw_t& r, float* v) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
   static __device__ __forceinline__ void load(const float* p, float* v) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -22,6 +32,16 @@ struct Act8<float> {
 };
 template <>
 struct Act8<__nv_bfloat16> {
+  using raw_t = uint4;
+  static __device__ __forceinline__ raw_t load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const raw_t& u, float* v) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
     const uint4 u = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -52,6 +72,9 @@ __device__ __forceinline__ float round_tf32(float v) {
 }
 template <>
 struct Act8<tf32_t> {
+  using raw_t = Act8<float>::raw_t;
+  static __device__ __forceinline__ raw_t load_raw(const tf32_t* p) { return Act8<float>::load_raw(reinterpret_cast<const float*>(p)); }
+  static __device__ __forceinline__ void unpack(const raw_t& r, float* v) { Act8<float>::unpack(r, v); }
   static __device__ __forceinline__ void load(const tf32_t* p, float* v) {
     Act8<float>::load(reinterpret_cast<const float*>(p), v);
   }

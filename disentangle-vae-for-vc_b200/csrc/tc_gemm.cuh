@@ -271,6 +271,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int col0 = (M_TILES == 2) ? 0 : half * (BLOCK_N / 2);
     const int col1 = (M_TILES == 2) ? BLOCK_N : col0 + BLOCK_N / 2;
     Epi::template prefetch<BLOCK_N>(ep, m, n0, zb, col0, col1, shp);   // overlaps the main loop
+    typename Epi::template Regs<BLOCK_N> regs;
+    Epi::template preload<BLOCK_N>(ep, regs, m, n0, zb, col0, col1, shp);   // operands that do not depend on the MMA
     AccSource acc;
     acc.taddr = tmem_base + mt * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
     acc.has_acc = num_local > 0;
@@ -312,7 +314,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc.partial = ws_row;
       }
     }
-    if (run_epilogue) Epi::template run<BLOCK_N>(ep, acc, m, n0, zb, col0, col1, shp);
+    if (run_epilogue) Epi::template run<BLOCK_N>(ep, acc, regs, m, n0, zb, col0, col1, shp);
     if (threadIdx.x == 64) phase_stamp(4);
     ptx::tc_fence_before();
   }
@@ -486,6 +488,8 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const int m = tm * kBlockM + q * 32 + lane;
       const int n0 = tn * BLOCK_N;
       Epi::template prefetch<BLOCK_N>(ep, m, n0, zb, col0, col1, shp);
+      typename Epi::template Regs<BLOCK_N> regs;
+      Epi::template preload<BLOCK_N>(ep, regs, m, n0, zb, col0, col1, shp);
       const int kb_begin = split * kb_chunk;
       AccSource acc;
       acc.taddr = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
@@ -496,7 +500,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       acc.split_stride = 0;
       ptx::mbar_wait(tmem_full_bar(as), (local >> 1) & 1);
       ptx::tc_fence_after();
-      Epi::template run<BLOCK_N>(ep, acc, m, n0, zb, col0, col1, shp);
+      Epi::template run<BLOCK_N>(ep, acc, regs, m, n0, zb, col0, col1, shp);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));   // this warp no longer reads accumulator `as`
@@ -534,9 +538,12 @@ struct EpiStore {
       prefetch_l2_span(p.mask + static_cast<long>(zb) * p.z_stride + static_cast<long>(m) * p.ldo + n0 + col0,
                        (col1 - col0) * static_cast<int>(sizeof(OutT)));
   }
+  template <int BLOCK_N> struct Regs {};
   template <int BLOCK_N>
-  static __device__ __forceinline__ void run(const Params& p, const AccSource& acc, int m, int n0, int zb, int col0,
-                                             int col1, const GemmShape& shp) {
+  static __device__ __forceinline__ void preload(const Params&, Regs<BLOCK_N>&, int, int, int, int, int, const GemmShape&) {}
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const AccSource& acc, const Regs<BLOCK_N>&, int m, int n0,
+                                             int zb, int col0, int col1, const GemmShape& shp) {
     const bool row_ok = m < shp.M;
     const long row_off = static_cast<long>(zb) * p.z_stride + static_cast<long>(m) * p.ldo;
 #pragma unroll 1
@@ -609,9 +616,12 @@ struct EpiAtomic {
   };
   template <int BLOCK_N>
   static __device__ __forceinline__ void prefetch(const Params&, int, int, int, int, int, const GemmShape&) {}
+  template <int BLOCK_N> struct Regs {};
   template <int BLOCK_N>
-  static __device__ __forceinline__ void run(const Params& p, const AccSource& acc, int m, int n0, int zb, int col0,
-                                             int col1, const GemmShape& shp) {
+  static __device__ __forceinline__ void preload(const Params&, Regs<BLOCK_N>&, int, int, int, int, int, const GemmShape&) {}
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const AccSource& acc, const Regs<BLOCK_N>&, int m, int n0,
+                                             int zb, int col0, int col1, const GemmShape& shp) {
     if (!acc.has_acc) return;
     const bool row_ok = m < shp.M;
     float* row = p.out + static_cast<long>(zb) * p.z_stride + static_cast<long>(m) * p.ldo;
@@ -664,32 +674,48 @@ struct EpiLstmFwd {
     if (p.c_prev)
       prefetch_l2_span(p.c_prev + zb * p.z_c_prev + static_cast<long>(m) * p.ldc + (n0 + col0) / 4, (col1 - col0));
   }
+  // everything the cell needs besides the accumulator, requested while the main loop is still running
   template <int BLOCK_N>
-  static __device__ __forceinline__ void run(const Params& p, const AccSource& acc, int m, int n0, int zb, int col0,
-                                             int col1, const GemmShape& shp) {
+  struct Regs {
+    static constexpr int NCH = BLOCK_N / 2 / 32;   // 32-column (8-unit) chunks owned by this thread
+    typename Act8<ActT>::raw_t x[NCH][4];
+    typename Act8<float>::raw_t c[NCH];
+  };
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void preload(const Params& p, Regs<BLOCK_N>& r, int m, int n0, int zb, int col0,
+                                                 int col1, const GemmShape& shp) {
+    if (m >= shp.M) return;
+    const ActT* xp = p.xproj + zb * p.z_x + static_cast<long>(m) * p.ldx + n0 + col0;
+    const float* cp = p.c_prev ? p.c_prev + zb * p.z_c_prev + static_cast<long>(m) * p.ldc + (n0 + col0) / 4 : nullptr;
+#pragma unroll
+    for (int k = 0; k < Regs<BLOCK_N>::NCH; ++k) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r.x[k][j] = Act8<ActT>::load_raw(xp + 32 * k + 8 * j);
+      if (cp) r.c[k] = Act8<float>::load_raw(cp + 8 * k);
+    }
+  }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const AccSource& acc, const Regs<BLOCK_N>& r, int m, int n0,
+                                             int zb, int col0, int col1, const GemmShape& shp) {
     const bool row_ok = m < shp.M;
-    const ActT* xp = p.xproj + zb * p.z_x + static_cast<long>(m) * p.ldx + n0;
     ActT* gs = p.gates + zb * p.z_x + static_cast<long>(m) * p.ldx + n0;
-    const float* cp = p.c_prev ? p.c_prev + zb * p.z_c_prev + static_cast<long>(m) * p.ldc + n0 / 4 : nullptr;
     float* co = p.c_out + zb * p.z_c_out + static_cast<long>(m) * p.ldc + n0 / 4;
     ActT* ho = p.h_out + zb * p.z_h + static_cast<long>(m) * p.ldh + n0 / 4;
-#pragma unroll 1
-    for (int c = col0; c < col1; c += 32) {   // 32 columns = 8 hidden units x 4 gates
-      // global operands first (the epilogue is latency-bound: profiles/r01_ncu_gemm_v1.txt), then the accumulator
-      float x[32], cprev[8];
-      if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) Act8<ActT>::load(xp + c + 8 * j, x + 8 * j);
-        if (cp) Act8<float>::load(cp + c / 4, cprev);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) cprev[i] = 0.f;
-        }
-      }
+    for (int k = 0; k < Regs<BLOCK_N>::NCH; ++k) {   // 32 columns = 8 hidden units x 4 gates
+      const int c = col0 + 32 * k;
       __syncwarp();
       float a[32];
       acc.template load<32>(c, a);
       if (row_ok) {
+        float x[32], cprev[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Act8<ActT>::unpack(r.x[k][j], x + 8 * j);
+        if (p.c_prev) Act8<float>::unpack(r.c[k], cprev);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cprev[i] = 0.f;
+        }
         float cn[8], hn[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -738,9 +764,12 @@ struct EpiLstmBwd {
     if (p.c_prev) prefetch_l2_span(p.c_prev + zb * p.z_c_prev + r * p.ldc + u, nu * 4);
     if (!p.dc_zero) prefetch_l2_span(p.dc + zb * p.z_dc + r * p.H + u, nu * 4);
   }
+  template <int BLOCK_N> struct Regs {};
   template <int BLOCK_N>
-  static __device__ __forceinline__ void run(const Params& p, const AccSource& accs, int m, int n0, int zb, int col0,
-                                             int col1, const GemmShape& shp) {
+  static __device__ __forceinline__ void preload(const Params&, Regs<BLOCK_N>&, int, int, int, int, int, const GemmShape&) {}
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const AccSource& accs, const Regs<BLOCK_N>&, int m, int n0,
+                                             int zb, int col0, int col1, const GemmShape& shp) {
     constexpr int CH = 2;   // 8-unit chunks per iteration (BLOCK_N / 2 columns per thread is always >= 32)
     const bool row_ok = m < shp.M;
     const long r = m;

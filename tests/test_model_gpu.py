@@ -158,3 +158,40 @@ def test_cpu_module_fails_loudly():
     m = DisentangledVAE(4, latent_dim=32)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.rand(2, 80, 64), torch.rand(2, 80, 64))
+
+
+class _PairDataset(torch.utils.data.Dataset):
+    """Stand-in for preprocessing/dataset.py:SpeechDatasetGVAE: (mel1 [80,64], mel2 [80,64], speaker id) + shuffle_data()."""
+
+    def __init__(self, n=8):
+        g = torch.Generator().manual_seed(0)
+        self.a, self.b = torch.rand(n, 80, 64, generator=g), torch.rand(n, 80, 64, generator=g)
+        self.shuffles = 0
+
+    def __len__(self):
+        return self.a.shape[0]
+
+    def __getitem__(self, i):
+        return self.a[i], self.b[i], torch.tensor(i // 2)
+
+    def shuffle_data(self):
+        self.shuffles += 1
+
+
+def test_trainer_loop_checkpoint_and_resume(tmp_path):
+    """The call sequence of the reference's train.py:89-99: build the wrapper, run_training (epoch loop, step, Adam,
+    checkpoint + estimate), then resume from the checkpoint."""
+    from oracle import dvae_oracle as O
+    ds = _PairDataset(8)
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=True, pin_memory=True)
+    w = _build("bf16", 4, O.synth_state_dict(0))
+    ck, logs, img, est = (str(tmp_path / d) for d in ("checkpoints", "logs", "images", "estimation"))
+    before = w.model.dec_linear2.linear_layer.weight.detach().clone()
+    w.run_training(loader, loader, 1, 1, 64, reload_model=True, checkpoints_path=ck, images_path=img, logs_path=logs,
+                   estimation_dir=est)
+    assert os.path.exists(os.path.join(ck, "DisentangledVAE_VCTK_1.pth")) and ds.shuffles == 1
+    assert not torch.equal(before, w.model.dec_linear2.linear_layer.weight.detach())     # Adam moved the weights
+    assert len(os.listdir(est)) == 8                                                      # 4 originals + 4 reconstructions
+    w2 = _build("bf16", 4, O.synth_state_dict(1))
+    assert w2.load_last_model(ck) == 2
+    assert torch.equal(w2.model.dec_linear2.linear_layer.weight, w.model.dec_linear2.linear_layer.weight)
