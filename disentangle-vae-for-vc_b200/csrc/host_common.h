@@ -44,4 +44,12 @@ inline int ceil_div(long a, long b) { return static_cast<int>((a + b - 1) / b); 
 
 int num_sms();
 
+// Sequence-resident LSTM recurrence (ops_lstm_seq.cu): one launch for all T steps when W_hh fits in shared memory.
+bool lstm_seq_supported(int H, int T);
+void lstm_seq_set_stamps(long long* buf);
+int lstm_seq_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_all, int rows, int T, int H, int D,
+                 cudaStream_t st);
+int lstm_seq_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all,
+                 int rows, int T, int H, int D, cudaStream_t st);
+
 }  // namespace dvae

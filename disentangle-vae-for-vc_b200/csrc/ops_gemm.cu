@@ -663,6 +663,7 @@ int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R
 int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_all, int rows, int T, int H, int D,
                   void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (lstm_seq_supported(H, T)) return lstm_seq_fwd(dtype, xg, whh_p, h_all, c_all, rows, T, H, D, st);
   DISPATCH_DTYPE(dtype, lstm_fwd_t<bf16>((bf16*)xg, (const bf16*)whh_p, (bf16*)h_all, c_all, rows, T, H, D, st),
                  lstm_fwd_t<tf32_t>((tf32_t*)xg, (const tf32_t*)whh_p, (tf32_t*)h_all, c_all, rows, T, H, D, st));
 }
@@ -672,6 +673,7 @@ int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_
 int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all,
                   float* dc_ws, float* splitk_ws, int* tickets, int rows, int T, int H, int D, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (lstm_seq_supported(H, T)) return lstm_seq_bwd(dtype, dh_all, gates, c_all, whh_n, da_all, rows, T, H, D, st);
   DISPATCH_DTYPE(dtype,
                  lstm_bwd_t<bf16>((const bf16*)dh_all, (const bf16*)gates, c_all, (const bf16*)whh_n, (bf16*)da_all, dc_ws, splitk_ws, tickets, rows, T, H, D, st),
                  lstm_bwd_t<tf32_t>((const tf32_t*)dh_all, (const tf32_t*)gates, c_all, (const tf32_t*)whh_n, (tf32_t*)da_all, dc_ws, splitk_ws, tickets, rows, T, H, D, st));
@@ -696,6 +698,13 @@ int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* 
 
 int dvae_lstm_gate_tile(int H) { return lstm_fwd_bn(H); }
 
+// kernel launches dvae_lstm_fwd / dvae_lstm_bwd enqueue for this shape (host-side launch accounting)
+int dvae_lstm_launches(int H, int T, int backward) {
+  if (lstm_seq_supported(H, T)) return 1;
+  static const int fused = env_int("DVAE_LSTM_BWD_FUSED", 0);
+  return backward ? (fused ? T : 2 * T - 1) : T;
+}
+
 // 1: subsequent GEMM launches from this host thread are background work (see want_persistent); 0: normal
 int dvae_set_background(int on) {
   g_background = on;
@@ -707,6 +716,12 @@ int dvae_set_background(int on) {
 int dvae_debug_timing(unsigned long long* buf, int capacity) {
   DVAE_CHECK_CUDA(cudaMemcpyToSymbol(dvae::g_phase_stamps, &buf, sizeof(buf)));
   DVAE_CHECK_CUDA(cudaMemcpyToSymbol(dvae::g_phase_capacity, &capacity, sizeof(capacity)));
+  return 0;
+}
+
+// debug: per-step SM-clock stamps [T][8] of CTA (0,0) of the sequence-resident LSTM kernels (nullptr: off)
+int dvae_debug_seq_stamps(long long* buf) {
+  lstm_seq_set_stamps(buf);
   return 0;
 }
 

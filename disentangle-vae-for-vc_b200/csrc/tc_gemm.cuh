@@ -22,13 +22,12 @@
 
 #include "act_types.cuh"
 #include "ptx.cuh"
+#include "umma_desc.cuh"
 
 namespace dvae {
 
-constexpr int kBlockM = 128;
 constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpilogueThreads = 256;
-constexpr int kSwizzleRow = 128;  // bytes per swizzle-128B row == BLOCK_K * ELEM_BYTES
 
 struct OperandWalk {
   int base[3];
@@ -99,22 +98,6 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 __device__ __forceinline__ void prefetch_l2_span(const void* p, int bytes) {
   const char* c = static_cast<const char*>(p);
   for (int o = 0; o < bytes; o += 128) prefetch_l2(c + o);
-}
-
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                              uint32_t layout_type) {
-  // sm_100 shared-memory matrix descriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
-  // version=1 [46,48) | layout [61,64): SWIZZLE_128B = 2, SWIZZLE_128B_BASE32B = 1
-  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
-         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46) | (static_cast<uint64_t>(layout_type) << 61);
-}
-
-template <int ELEM_BYTES, int BLOCK_N, bool A_MN, bool B_MN>
-__host__ __device__ constexpr uint32_t instr_desc() {
-  // c_format F32 [4,6) | a_format [7,10) | b_format [10,13) | a_major 15 | b_major 16 | N>>3 [17,23) | M>>4 [24,29)
-  const uint32_t fmt = (ELEM_BYTES == 2) ? 1u : 2u;  // BF16 : TF32
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-         (static_cast<uint32_t>(BLOCK_N >> 3) << 17) | (static_cast<uint32_t>(kBlockM >> 4) << 24);
 }
 
 template <int BLOCK_N, int STAGES, int M_TILES = 1>

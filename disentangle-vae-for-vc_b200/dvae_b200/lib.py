@@ -39,6 +39,7 @@ _SIGNATURES = {
     "dvae_lstm_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_lstm_bwd_workspace": [_i, _i, _i, _i, _p, _p],
     "dvae_debug_timing": [_p, _i],
+    "dvae_debug_seq_stamps": [_p],
     "dvae_set_background": [_i],
     "dvae_lstm_wgrad_hh": [_i, _p, _p, _p, _i, _i, _i, _i, _p],
     # weight preparation / layout
@@ -85,8 +86,9 @@ def register(name, argtypes):
 
 
 _FUNCS = {n: _bind(n, a) for n, a in _SIGNATURES.items()}
-for _n in ("dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile"):
+for _n in ("dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile", "dvae_lstm_launches"):
     getattr(_lib, _n).restype = C.c_int
+_lib.dvae_lstm_launches.argtypes = [C.c_int, C.c_int, C.c_int]
 
 
 def ptr(t):
@@ -104,13 +106,14 @@ def stream():
 LAUNCHES = 0
 _LAUNCHES_PER_CALL = {"dvae_bn_train_fwd": 3, "dvae_bn_train_bwd": 3, "dvae_bn_eval_fwd": 2, "dvae_segment_ids_sorted": 3,
                       "dvae_group_finalize": 2}
-_TIME_STEP_ARG = {"dvae_lstm_fwd": 6, "dvae_lstm_bwd": 10}   # (lstm_bwd: 2 kernels per step, counted below)   # index of T: one GEMM launch per time step
+_LSTM_SHAPE_ARGS = {"dvae_lstm_fwd": (7, 6), "dvae_lstm_bwd": (11, 10)}   # indices of (H, T): the library says how many launches
 
 
 def call(name, *args):
     global LAUNCHES
-    if name in _TIME_STEP_ARG:
-        LAUNCHES += args[_TIME_STEP_ARG[name]] * (2 if name == "dvae_lstm_bwd" else 1)
+    if name in _LSTM_SHAPE_ARGS:
+        iH, iT = _LSTM_SHAPE_ARGS[name]
+        LAUNCHES += _lib.dvae_lstm_launches(args[iH], args[iT], 1 if name == "dvae_lstm_bwd" else 0)
     else:
         LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
     rc = _FUNCS[name](*args)
@@ -136,4 +139,5 @@ def lstm_gate_tile(hidden: int) -> int:
 
 
 def exported_symbols():
-    return sorted(_SIGNATURES.keys()) + ["dvae_last_error", "dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile"]
+    return sorted(_SIGNATURES.keys()) + ["dvae_last_error", "dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile",
+                                             "dvae_lstm_launches"]

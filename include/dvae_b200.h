@@ -22,6 +22,8 @@ const char* dvae_last_error(void);
 int dvae_version(void);
 int dvae_sm_arch(void);              /* 100: built for sm_100a only */
 int dvae_lstm_gate_tile(int H);
+int dvae_debug_seq_stamps(long long* buf);   /* optional per-step SM-clock stamps [T][8] of the sequence-resident LSTM kernels (debug) */
+int dvae_lstm_launches(int H, int T, int backward);   /* kernels dvae_lstm_fwd / dvae_lstm_bwd enqueue for this shape */
 int dvae_set_background(int on);   /* GEMMs launched while on: small-footprint kernels that co-run with a latency-critical stream */
 int dvae_debug_timing(unsigned long long* buf, int capacity);   /* optional per-CTA phase stamps of the GEMM kernel (debug) */      /* gate-interleave tile (columns) used by the LSTM forward for hidden size H */
 
