@@ -24,8 +24,22 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
+static int encode_map3_impl(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                            uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool mn_major,
+                            bool narrow);
+
 int encode_map3(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool mn_major) {
+  return encode_map3_impl(out, base, elem_bytes, d0, d1, d2, stride1_bytes, stride2_bytes, b0, b1, b2, mn_major, false);
+}
+int encode_map3_narrow(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  return encode_map3_impl(out, base, elem_bytes, d0, d1, d2, stride1_bytes, stride2_bytes, b0, b1, b2, false, true);
+}
+
+static int encode_map3_impl(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                            uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, bool mn_major,
+                            bool narrow) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -33,15 +47,17 @@ int encode_map3(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0,
   }
   DVAE_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base address must be 16-byte aligned");
   DVAE_REQUIRE(stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0, "TMA strides must be multiples of 16 bytes");
-  DVAE_REQUIRE(b0 * elem_bytes == 128, "inner box must span one 128-byte swizzle row");
+  if (narrow) DVAE_REQUIRE(b0 * elem_bytes < 128 && (b0 * elem_bytes) % 16 == 0, "narrow box: inner extent must be a multiple of 16 bytes below 128");
+  else DVAE_REQUIRE(b0 * elem_bytes == 128, "inner box must span one 128-byte swizzle row");
   DVAE_REQUIRE(b1 <= 256 && b2 <= 256 && b1 >= 1 && b2 >= 1, "TMA box dims must be in [1,256]");
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
   cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  const CUtensorMapSwizzle sw =
-      (mn_major && elem_bytes == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle sw = narrow ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : (mn_major && elem_bytes == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                                : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = fn(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];

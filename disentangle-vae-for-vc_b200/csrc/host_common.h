@@ -39,6 +39,9 @@ void set_last_error(const std::string& msg);
 int encode_map3(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2,
                 bool mn_major = false);
+// same, for boxes narrower than one swizzle row (inner box < 128 bytes, a multiple of 16): no swizzle
+int encode_map3_narrow(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                       uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
 
 inline int ceil_div(long a, long b) { return static_cast<int>((a + b - 1) / b); }
 

@@ -407,27 +407,55 @@ static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows
     return e;
   if (int e = encode_map3(&tb, whh_p, EB, H, 4 * H, D, (uint64_t)H * EB, (uint64_t)4 * H * H * EB, BK, BN, 1)) return e;
   const long ldx = (long)T * D * 4 * H, ldc = (long)T * D * H;
+  // staged (TMA) stores of gates / c / h for the wide tiles; DVAE_LSTM_FWD_TMA=0 keeps the direct row-per-lane stores
+  static const int tma_env = env_int("DVAE_LSTM_FWD_TMA", 1);
+  const bool staged = tma_env != 0 && BN >= 128;
+  CUtensorMap tg, tc, th;
+  if (staged) {
+    if (int e = encode_map3(&tg, xg, EB, (uint64_t)D * 4 * H, T, rows, (uint64_t)D * 4 * H * EB, (uint64_t)T * D * 4 * H * EB, BK, 1, 128))
+      return e;
+    if (int e = encode_map3(&tc, c_all, 4, (uint64_t)D * H, T, rows, (uint64_t)D * H * 4, (uint64_t)T * D * H * 4, 32, 1, 128)) return e;
+    const int h_row_bytes = BN / 4 * EB;
+    if (int e = h_row_bytes >= 128
+                    ? encode_map3(&th, h_all, EB, (uint64_t)D * H, T, rows, (uint64_t)D * H * EB, (uint64_t)T * D * H * EB, BK, 1, 128)
+                    : encode_map3_narrow(&th, h_all, EB, (uint64_t)D * H, T, rows, (uint64_t)D * H * EB, (uint64_t)T * D * H * EB,
+                                         BN / 4, 1, 128))
+      return e;
+  }
   for (int s = 0; s < T; ++s) {
     const int tf = s, tr = T - 1 - s;
     OperandWalk wa = zero_walk(), wb = zero_walk();
     wa.base[1] = tf - 1; wa.per_j[0] = BK; wa.per_tile[2] = 128; wa.per_z[0] = H; wa.per_z[1] = (tr + 1) - (tf - 1);
     wb.per_j[0] = BK; wb.per_tile[1] = BN; wb.per_z[2] = 1;
     GemmShape shp{rows, 4 * H, s == 0 ? 0 : H / BK, H / BK, 1};
-    typename EpiLstmFwd<AT>::Params ep;
-    ep.xproj = xg + (long)tf * D * 4 * H;
-    ep.gates = xg + (long)tf * D * 4 * H;
-    ep.c_prev = s == 0 ? nullptr : c_all + (long)(tf - 1) * D * H;
-    ep.c_out = c_all + (long)tf * D * H;
-    ep.h_out = h_all + (long)tf * D * H;
-    ep.ldx = ldx; ep.ldc = ldc; ep.ldh = ldc;
-    ep.z_x = 4 * H + (long)(tr - tf) * D * 4 * H;
-    ep.z_c_prev = H + (long)((tr + 1) - (tf - 1)) * D * H;
-    ep.z_c_out = H + (long)(tr - tf) * D * H;
-    ep.z_h = H + (long)(tr - tf) * D * H;
+    auto fill = [&](typename EpiLstmFwd<AT>::Params& ep) {
+      ep.xproj = xg + (long)tf * D * 4 * H;
+      ep.gates = xg + (long)tf * D * 4 * H;
+      ep.c_prev = s == 0 ? nullptr : c_all + (long)(tf - 1) * D * H;
+      ep.c_out = c_all + (long)tf * D * H;
+      ep.h_out = h_all + (long)tf * D * H;
+      ep.ldx = ldx; ep.ldc = ldc; ep.ldh = ldc;
+      ep.z_x = 4 * H + (long)(tr - tf) * D * 4 * H;
+      ep.z_c_prev = H + (long)((tr + 1) - (tf - 1)) * D * H;
+      ep.z_c_out = H + (long)(tr - tf) * D * H;
+      ep.z_h = H + (long)(tr - tf) * D * H;
+    };
     dim3 grid(ceil_div(rows, 128), 4 * H / BN, D);
-    int e = (BN == 256)   ? launch_gemm<256, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
-            : (BN == 128) ? launch_gemm<128, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
-                          : launch_gemm<64, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    int e;
+    if (staged) {
+      typename EpiLstmFwdTma<AT>::Params ep;
+      fill(ep);
+      ep.tm_g = tg; ep.tm_c = tc; ep.tm_h = th;
+      ep.t[0] = tf; ep.t[1] = tr; ep.H = H;
+      e = (BN == 256) ? launch_gemm<256, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                      : launch_gemm<128, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    } else {
+      typename EpiLstmFwd<AT>::Params ep;
+      fill(ep);
+      e = (BN == 256)   ? launch_gemm<256, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+          : (BN == 128) ? launch_gemm<128, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                        : launch_gemm<64, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    }
     if (e) return e;
   }
   return 0;
@@ -438,11 +466,11 @@ static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows
 // consecutive threads touch consecutive runs, so the kernel streams at HBM/L2 bandwidth with full occupancy -- unlike the
 // same arithmetic inside the GEMM epilogue, which is latency-bound on 8 warps (profiles/r01_phase_timing_v2.txt).
 template <typename AT>
-__global__ void lstm_cell_bwd_kernel(const AT* __restrict__ dh_out, const float* __restrict__ dh_rec,
+__global__ void lstm_cell_bwd_kernel(const AT* __restrict__ dh_out, float* __restrict__ dh_rec,
                                      const AT* __restrict__ gates, const float* __restrict__ c_t,
                                      const float* __restrict__ c_prev, float* __restrict__ dc, AT* __restrict__ da,
                                      int rows, int H, long ldh, long ldx, long z_h, long z_x, long z_cprev, long z_rec,
-                                     int dc_zero) {
+                                     int dc_zero, int zero_rec) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   const int d = blockIdx.y;
@@ -460,7 +488,13 @@ __global__ void lstm_cell_bwd_kernel(const AT* __restrict__ dh_out, const float*
     for (int j = 0; j < 4; ++j) Act8<AT>::load(gates + r * ldx + 4 * u + 8 * j, g4 + 8 * j);
     Act8<float>::load(c_t + r * ldh + u, cc);
     if (c_prev) Act8<float>::load(c_prev + r * ldh + u, cpv);
-    if (dh_rec) Act8<float>::load(dh_rec + r * H + u, rec);
+    if (dh_rec) {
+      Act8<float>::load(dh_rec + r * H + u, rec);
+      if (zero_rec) {   // the next step's split-K GEMM accumulates into this buffer with TMA reduce-adds
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        Act8<float>::store(dh_rec + r * H + u, z);
+      }
+    }
     if (!dc_zero) Act8<float>::load(dc + r * H + u, dcv);
     float dai[8], daf[8], dag[8], dao[8], dcn[8];
 #pragma unroll
@@ -502,23 +536,54 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
   const long ldh = (long)T * D * H, ldx = (long)T * D * 4 * H;
   static const int fused = env_int("DVAE_LSTM_BWD_FUSED", 0);
   if (!fused) {
-    // Two kernels per step: (1) dh_rec[d][rows][H] (fp32) = da_{t+1} . W_hh with a plain store epilogue,
-    // (2) the elementwise cell backward.  dc_ws holds [D][rows][H] carry followed by [D][rows][H] dh_rec.
+    // Two kernels per step: (1) dh_rec[d][rows][H] (fp32) = da_{t+1} . W_hh, (2) the elementwise cell backward.
+    // dc_ws holds [D][rows][H] carry followed by [D][rows][H] dh_rec.
+    //
+    // (1) is a K-heavy GEMM (K = 4H, N = H).  With one CTA per 128 x 64 output tile every CTA streams the whole K extent
+    // of both operands and the step is bound by L2->SM bandwidth (192 MB per step at H = 1024).  "reduce" mode instead uses
+    // wide tiles (128 x 256 / 128 x 128) and splits K over gridDim.z: the same SM count moves half the operand bytes, and
+    // the partial sums meet in L2 through TMA reduce-adds of the staged tiles.  The cell kernel consumes dh_rec and
+    // leaves it zeroed for the next step.
     float* dh_rec = dc_ws + (long)D * rows * H;
+    static const int reduce_env = env_int("DVAE_LSTM_BWD_REDUCE", 1);
+    const bool reduce = reduce_env != 0 && H >= 256 && H % 128 == 0;
+    const int RBN = (H % 256 == 0) ? 256 : 128;
+    int rsplits = 1;
+    CUtensorMap trec;
+    if (reduce) {
+      static const int forced = env_int("DVAE_LSTM_BWD_SPLITS", 0);
+      const int tiles = ceil_div(rows, 128) * (H / RBN) * D;
+      const int num_kb = 4 * H / BK;
+      rsplits = forced > 0 ? forced : 1;
+      if (forced <= 0)
+        while (tiles * rsplits * 2 <= num_sms() && num_kb / (rsplits * 2) >= 4) rsplits *= 2;
+      if (int e = encode_map3(&trec, dh_rec, 4, H, rows, D, (uint64_t)H * 4, (uint64_t)rows * H * 4, 32, 128, 1)) return e;
+      DVAE_CHECK_CUDA(cudaMemsetAsync(dh_rec, 0, sizeof(float) * D * rows * H, st));
+    }
     for (int s = 0; s < T; ++s) {
       const int tf = T - 1 - s, tr = s;
       if (s > 0) {
         OperandWalk wa = zero_walk(), wb = zero_walk();
         wa.base[1] = tf + 1; wa.per_j[0] = BK; wa.per_tile[2] = 128; wa.per_z[0] = 4 * H; wa.per_z[1] = (tr - 1) - (tf + 1);
-        wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN; wb.per_z[2] = 1;
-        const int splits = splitk_ws == nullptr ? 1 : lstm_bwd_splits(rows, H, D, EB);
-        GemmShape shp{rows, H, 4 * H / BK, 4 * H / BK, splits, splitk_ws, tickets};
-        typename EpiStore<AT>::Params ep{nullptr, dh_rec, nullptr, nullptr, (long)H, (long)rows * H, 0};
-        dim3 grid(ceil_div(rows, 128), H / BN, D * splits);
-        int e = (BN == 256)   ? launch_gemm<256, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
-                : (BN == 128) ? launch_gemm<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
-                              : launch_gemm<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
-        if (e) return e;
+        if (reduce) {
+          wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = RBN; wb.per_z[2] = 1;
+          GemmShape shp{rows, H, 4 * H / BK, 4 * H / BK, rsplits, nullptr, nullptr};
+          EpiReduceTma::Params ep{trec};
+          dim3 grid(ceil_div(rows, 128), H / RBN, D * rsplits);
+          int e = (RBN == 256) ? launch_gemm<256, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st)
+                               : launch_gemm<128, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st);
+          if (e) return e;
+        } else {
+          wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN; wb.per_z[2] = 1;
+          const int splits = splitk_ws == nullptr ? 1 : lstm_bwd_splits(rows, H, D, EB);
+          GemmShape shp{rows, H, 4 * H / BK, 4 * H / BK, splits, splitk_ws, tickets};
+          typename EpiStore<AT>::Params ep{nullptr, dh_rec, nullptr, nullptr, (long)H, (long)rows * H, 0};
+          dim3 grid(ceil_div(rows, 128), H / BN, D * splits);
+          int e = (BN == 256)   ? launch_gemm<256, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                  : (BN == 128) ? launch_gemm<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                                : launch_gemm<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+          if (e) return e;
+        }
       }
       const long total = (long)rows * (H / 8);
       long gx = (total + 255) / 256;
@@ -536,11 +601,11 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
         cfg.attrs = attr;
         cfg.numAttrs = use_pdl ? 1 : 0;
         DVAE_CHECK_CUDA(cudaLaunchKernelEx(
-            &cfg, lstm_cell_bwd_kernel<AT>, (const AT*)(dh_all + (long)tf * D * H), (const float*)(s > 0 ? dh_rec : nullptr),
+            &cfg, lstm_cell_bwd_kernel<AT>, (const AT*)(dh_all + (long)tf * D * H), (float*)(s > 0 ? dh_rec : nullptr),
             (const AT*)(gates + (long)tf * D * 4 * H), (const float*)(c_all + (long)tf * D * H),
             (const float*)((s == T - 1) ? nullptr : c_all + (long)(tf - 1) * D * H), dc_ws, da_all + (long)tf * D * 4 * H, rows, H,
             ldh, ldx, H + (long)(tr - tf) * D * H, 4 * H + (long)(tr - tf) * D * 4 * H,
-            H + (long)((tr + 1) - (tf - 1)) * D * H, (long)rows * H, (int)(s == 0)));
+            H + (long)((tr + 1) - (tf - 1)) * D * H, (long)rows * H, (int)(s == 0), (int)reduce));
       }
     }
     return 0;

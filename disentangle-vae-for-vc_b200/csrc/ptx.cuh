@@ -117,6 +117,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem
                "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// same, but every element is added (fp32) to what is in global memory: the reduction happens in L2
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still have shared-memory reads outstanding
 template <int N>

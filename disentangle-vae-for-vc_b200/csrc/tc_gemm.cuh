@@ -79,6 +79,12 @@ struct AccSource {
   }
 };
 
+// epilogues that define `static constexpr bool kStaged = true` write through shared-memory staging + TMA
+template <class Epi, class = void>
+struct epi_is_staged { static constexpr bool value = false; };
+template <class Epi>
+struct epi_is_staged<Epi, decltype((void)Epi::kStaged)> { static constexpr bool value = Epi::kStaged; };
+
 // Optional per-CTA phase stamps (globaltimer ns): [cta][0]=entry [1]=setup done [2]=producer done [3]=accumulator ready
 // [4]=epilogue done.  Off (nullptr) unless dvae_debug_timing() installs a buffer; one predictable branch per stamp.
 __device__ unsigned long long* g_phase_stamps = nullptr;
@@ -111,7 +117,8 @@ constexpr int gemm_smem_bytes() {
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi, int M_TILES = 1>
 __global__ void __launch_bounds__(kGemmThreads, (Epi::kCtasPerSm == 2 && STAGES * (M_TILES * kBlockM + BLOCK_N) * kSwizzleRow <= 100 * 1024) ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const OperandWalk wa, const OperandWalk wb, const GemmShape shp, const typename Epi::Params ep) {
+               const OperandWalk wa, const OperandWalk wb, const GemmShape shp,
+               const __grid_constant__ typename Epi::Params ep) {
   constexpr int BLOCK_K = kSwizzleRow / ELEM_BYTES;  // 64 bf16 / 32 tf32
   constexpr int UMMA_K = 32 / ELEM_BYTES;            // 16 / 8
   constexpr int TILE_A = kBlockM * kSwizzleRow;      // one 128-row A tile
@@ -297,7 +304,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         acc.partial = ws_row;
       }
     }
-    if (run_epilogue) Epi::template run<BLOCK_N>(ep, acc, regs, m, n0, zb, col0, col1, shp);
+    if constexpr (epi_is_staged<Epi>::value) {
+      // Staged epilogue: the accumulator is complete, so every MMA has retired and every TMA load has landed -- the
+      // operand ring is free.  The threads deposit their results there as 128-byte-swizzled boxes (row-per-lane
+      // st.shared.v4 is conflict free, unlike row-per-lane global accesses, which cost one LSU transaction per lane),
+      // and one thread hands the boxes to the TMA engine.
+      static_assert(M_TILES == 1, "staged epilogues use the single-accumulator tile");
+      static_assert(Epi::template staging_bytes<BLOCK_N>() <= STAGES * (STAGE_A + STAGE_B), "staging exceeds the ring");
+      if (run_epilogue) Epi::template run_staged<BLOCK_N>(ep, acc, regs, row, m, n0, zb, col0, col1, shp, smem_base);
+      ptx::fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) {
+        if (run_epilogue) Epi::template flush<BLOCK_N>(ep, smem_base, tile_m, tile_n, zb, shp);
+        ptx::bulk_commit();
+        ptx::bulk_wait_read<0>();   // shared memory must stay alive until the TMA engine has read it; the writes themselves
+                                    // are ordered before grid completion, which is what the dependent kernel (PDL) waits for
+      }
+    } else {
+      if (run_epilogue) Epi::template run<BLOCK_N>(ep, acc, regs, m, n0, zb, col0, col1, shp);
+    }
     if (threadIdx.x == 64) phase_stamp(4);
     ptx::tc_fence_before();
   }
@@ -500,6 +525,52 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 // Epilogues.  Each receives the TMEM address of its warp's 32-lane slice; thread `lane` owns
 // output row m and reads BLOCK_N fp32 columns in chunks.
 // =====================================================================================
+// ---- out_f32[zb][m][n] += acc, as a TMA reduce-add of the staged tile (split-K partial sums meet in L2; no tickets,
+// no row-per-lane atomics).  Staging: [BLOCK_N / 32 boxes][128 rows][128 B] fp32, swizzle-128B.
+struct EpiReduceTma {
+  static constexpr bool kFixup = false;
+  static constexpr bool kStaged = true;
+  static constexpr int kCtasPerSm = 1;
+  struct Params {
+    CUtensorMap tm_out;   // fp32 {N, M, batches}, box {32, 128, 1}
+  };
+  template <int BLOCK_N>
+  static __host__ __device__ constexpr int staging_bytes() { return BLOCK_N * 4 * kBlockM; }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void prefetch(const Params& p, int, int, int, int, int, const GemmShape&) {
+    if ((threadIdx.x & 255) == 64) ptx::prefetch_tmap(&p.tm_out);
+  }
+  template <int BLOCK_N> struct Regs {};
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void preload(const Params&, Regs<BLOCK_N>&, int, int, int, int, int, const GemmShape&) {}
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run_staged(const Params&, const AccSource& acc, const Regs<BLOCK_N>&, int row, int m,
+                                                    int n0, int zb, int col0, int col1, const GemmShape& shp,
+                                                    uint32_t stage) {
+#pragma unroll 1
+    for (int c = col0; c < col1; c += 32) {
+      __syncwarp();
+      float v[32];
+      acc.template load<32>(c, v);
+      const uint32_t box = stage + static_cast<uint32_t>((c >> 5) * (kBlockM * 128) + row * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        ptx::st_shared_v4(box + ((j ^ (row & 7)) << 4),
+                          make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                     __float_as_uint(v[4 * j + 3])));
+    }
+  }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void flush(const Params& p, uint32_t stage, int tile_m, int tile_n, int zb,
+                                               const GemmShape& shp) {
+#pragma unroll 1
+    for (int b = 0; b < BLOCK_N / 32; ++b) {
+      if (tile_n * BLOCK_N + b * 32 >= shp.N) break;
+      ptx::tma_reduce_add_3d(&p.tm_out, stage + b * (kBlockM * 128), tile_n * BLOCK_N + b * 32, tile_m * kBlockM, zb);
+    }
+  }
+};
+
 // ---- out = act(acc + bias) -> activation dtype, optionally mirrored in fp32; optional relu-mask multiply
 template <typename OutT>
 struct EpiStore {
@@ -714,6 +785,126 @@ struct EpiLstmFwd {
         for (int j = 0; j < 4; ++j) Act8<ActT>::store(gs + c + 8 * j, a + 8 * j);
       }
     }
+  }
+};
+
+// ---- LSTM cell forward with staged stores: same arithmetic and the same (preloaded) global reads as EpiLstmFwd, but
+// the three outputs of the step (activated gates, c, h) leave through shared-memory staging and TMA stores.  With one
+// row per lane the direct version issues 28 16-byte stores per thread at BLOCK_N = 256, each touching 32 different
+// 128-byte lines per warp: ~7000 LSU transactions per CTA and step, the largest item of the step's critical path.
+template <typename ActT>
+struct EpiLstmFwdTma : EpiLstmFwd<ActT> {
+  using Base = EpiLstmFwd<ActT>;
+  static constexpr bool kStaged = true;
+  static constexpr int kCtasPerSm = 1;
+  static constexpr int EB = sizeof(ActT);
+  struct Params : Base::Params {
+    CUtensorMap tm_g;   // gates  ActT {D*4H, T, rows}, box {128/EB, 1, 128}
+    CUtensorMap tm_c;   // c      fp32 {D*H,  T, rows}, box {32, 1, 128}
+    CUtensorMap tm_h;   // h      ActT {D*H,  T, rows}, box {min(128, BLOCK_N/4*EB)/EB, 1, 128}
+    int t[2];           // time index per direction
+    int H;
+  };
+  template <int BLOCK_N> static __host__ __device__ constexpr int g_boxes() { return BLOCK_N * EB / 128; }
+  template <int BLOCK_N> static __host__ __device__ constexpr int c_boxes() { return BLOCK_N / 128; }
+  template <int BLOCK_N> static __host__ __device__ constexpr int h_row_bytes() { return BLOCK_N / 4 * EB; }
+  template <int BLOCK_N> static __host__ __device__ constexpr int h_boxes() { return h_row_bytes<BLOCK_N>() >= 128 ? h_row_bytes<BLOCK_N>() / 128 : 1; }
+  template <int BLOCK_N> static __host__ __device__ constexpr int h_bytes() { return kBlockM * h_row_bytes<BLOCK_N>(); }
+  template <int BLOCK_N>
+  static __host__ __device__ constexpr int staging_bytes() {
+    return (g_boxes<BLOCK_N>() + c_boxes<BLOCK_N>()) * kBlockM * 128 + h_bytes<BLOCK_N>();
+  }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run_staged(const Params& p, const AccSource& acc, const typename Base::template Regs<BLOCK_N>& r,
+                                                    int row, int m, int n0, int zb, int col0, int col1, const GemmShape& shp,
+                                                    uint32_t stage) {
+    const bool row_ok = m < shp.M;
+    const uint32_t sg = stage, sc = sg + g_boxes<BLOCK_N>() * kBlockM * 128, sh = sc + c_boxes<BLOCK_N>() * kBlockM * 128;
+    auto box_addr = [&](uint32_t base, int byte_in_row) {   // 16-byte chunk of this row in a [boxes][128 rows][128 B] tile
+      return base + static_cast<uint32_t>((byte_in_row >> 7) * (kBlockM * 128) + row * 128 +
+                                          ((((byte_in_row & 127) >> 4) ^ (row & 7)) << 4));
+    };
+#pragma unroll
+    for (int k = 0; k < Base::template Regs<BLOCK_N>::NCH; ++k) {
+      const int c = col0 + 32 * k;
+      __syncwarp();
+      float a[32];
+      acc.template load<32>(c, a);
+      float x[32], cprev[8];
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Act8<ActT>::unpack(r.x[k][j], x + 8 * j);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = 0.f;
+      }
+      if (row_ok && p.c_prev) Act8<float>::unpack(r.c[k], cprev);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cprev[i] = 0.f;
+      }
+      float cn[8], hn[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float ig = sigmoid_f(a[4 * i] + x[4 * i]), fg = sigmoid_f(a[4 * i + 1] + x[4 * i + 1]);
+        const float gg = tanh_f(a[4 * i + 2] + x[4 * i + 2]), og = sigmoid_f(a[4 * i + 3] + x[4 * i + 3]);
+        a[4 * i] = ig; a[4 * i + 1] = fg; a[4 * i + 2] = gg; a[4 * i + 3] = og;
+        cn[i] = fg * cprev[i] + ig * gg;
+        hn[i] = og * tanh_f(cn[i]);
+      }
+      // gates: 32 columns = 32*EB bytes at byte c*EB of the row
+#pragma unroll
+      for (int j = 0; j < 32 * EB / 16; ++j) {
+        uint4 u;
+        if constexpr (EB == 2) {
+          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(a[8 * j + 2 * i], a[8 * j + 2 * i + 1]);
+        } else {
+          u = make_uint4(__float_as_uint(round_tf32(a[4 * j])), __float_as_uint(round_tf32(a[4 * j + 1])),
+                         __float_as_uint(round_tf32(a[4 * j + 2])), __float_as_uint(round_tf32(a[4 * j + 3])));
+        }
+        ptx::st_shared_v4(box_addr(sg, c * EB + 16 * j), u);
+      }
+      // c: 8 units fp32 = 32 bytes at byte c (= 4 * (c / 4)) of the row
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        ptx::st_shared_v4(box_addr(sc, c + 16 * j),
+                          make_uint4(__float_as_uint(cn[4 * j]), __float_as_uint(cn[4 * j + 1]), __float_as_uint(cn[4 * j + 2]),
+                                     __float_as_uint(cn[4 * j + 3])));
+      // h: 8 units = 8*EB bytes at byte (c / 4) * EB of the row
+#pragma unroll
+      for (int j = 0; j < 8 * EB / 16; ++j) {
+        uint4 u;
+        if constexpr (EB == 2) {
+          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(hn[2 * i], hn[2 * i + 1]);
+        } else {
+          u = make_uint4(__float_as_uint(round_tf32(hn[4 * j])), __float_as_uint(round_tf32(hn[4 * j + 1])),
+                         __float_as_uint(round_tf32(hn[4 * j + 2])), __float_as_uint(round_tf32(hn[4 * j + 3])));
+        }
+        const int byte = (c / 4) * EB + 16 * j;
+        if constexpr (h_row_bytes<BLOCK_N>() >= 128) ptx::st_shared_v4(box_addr(sh, byte), u);
+        else ptx::st_shared_v4(sh + row * h_row_bytes<BLOCK_N>() + byte, u);   // narrow tile: unswizzled rows
+      }
+    }
+  }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void flush(const Params& p, uint32_t stage, int tile_m, int tile_n, int zb,
+                                               const GemmShape& shp) {
+    const uint32_t sg = stage, sc = sg + g_boxes<BLOCK_N>() * kBlockM * 128, sh = sc + c_boxes<BLOCK_N>() * kBlockM * 128;
+    const int t = p.t[zb], m0 = tile_m * kBlockM, n0 = tile_n * BLOCK_N;
+    constexpr int GE = 128 / EB;   // elements per 128-byte box row
+#pragma unroll
+    for (int b = 0; b < h_boxes<BLOCK_N>(); ++b)   // h first: the next step's GEMM waits for it
+      ptx::tma_store_3d(&p.tm_h, sh + b * (kBlockM * 128), zb * p.H + n0 / 4 + b * GE, t, m0);
+#pragma unroll
+    for (int b = 0; b < g_boxes<BLOCK_N>(); ++b)
+      ptx::tma_store_3d(&p.tm_g, sg + b * (kBlockM * 128), zb * 4 * p.H + n0 + b * GE, t, m0);
+#pragma unroll
+    for (int b = 0; b < c_boxes<BLOCK_N>(); ++b)
+      ptx::tma_store_3d(&p.tm_c, sc + b * (kBlockM * 128), zb * p.H + n0 / 4 + b * 32, t, m0);
   }
 };
 

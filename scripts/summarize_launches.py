@@ -41,3 +41,11 @@ total = sum(a[1] for a in agg.values())
 print(f"launches {len(rows)}  total {total / 1e3:.3f} ms (serialised, cold cache: compare shares)")
 for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{us / total * 100:6.2f}%  {us / 1e3:9.3f} ms  {n:6d} x {us / n:9.2f} us  {k}")
+
+# optional: list every launch whose short name contains argv[3] (grid, duration) in launch order
+if len(sys.argv) > 3:
+    key = sys.argv[3]
+    print(f"--- individual launches matching '{key}'")
+    for i, name, us, grid, block in rows:
+        if key in short(name):
+            print(f"  #{i:5d} {us:9.2f} us  grid {grid:>14s}  {short(name)[:110]}")
