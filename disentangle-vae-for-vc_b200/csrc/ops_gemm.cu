@@ -69,9 +69,13 @@ template <int BN, bool A_MN, bool B_MN, int EB, class Epi>
 static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const OperandWalk& wa, const OperandWalk& wb,
                                   const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream) {
   static_assert(BN <= 256, "");
-  constexpr int ST = Stages<BN>::value + (BN == 128 ? 3 : (BN == 64 ? 4 : 0));   // 1 CTA / SM: use the whole 227 KB
+  constexpr int STAGING = persistent_staging_bytes<Epi, BN>();
+  constexpr int ST_FULL = Stages<BN>::value + (BN == 128 ? 3 : (BN == 64 ? 4 : 0));   // 1 CTA / SM: use the whole 227 KB
+  constexpr int ST_FIT = (227 * 1024 - 1280 - STAGING) / ((128 + BN) * 128);        // what is left next to a staging tile
+  constexpr int ST = ST_FIT < ST_FULL ? ST_FIT : ST_FULL;
+  static_assert(ST >= 2, "persistent GEMM: ring too shallow");
   auto kern = tc_gemm_persistent_kernel<BN, ST, A_MN, B_MN, EB, Epi>;
-  constexpr int smem = gemm_smem_bytes<BN, ST>();
+  constexpr int smem = gemm_smem_bytes<BN, ST>() + STAGING;
   static_assert(smem <= 227 * 1024, "persistent GEMM shared memory");
   static bool configured = false;
   if (!configured) {
@@ -130,6 +134,16 @@ static int pick_mt(long M, int n_tiles_total) {
   return 1;   // measured: the 256-row tile is not faster (profiles/): the persistent 128-row kernel is the default
 }
 
+// Staged (TMA) output stores for the persistent kernel: eligible when the only output is the activation tensor.
+// DVAE_GEMM_TMA_STORE: 0 never, 1 whenever eligible, default 2: when the main loop is short (<= 16 k-blocks per tile), i.e.
+// when the direct row-per-lane stores would take as long as the MMAs.
+static bool use_tma_store(const void* out, const float* out_f32, const void* mask, long ldo, int elem_bytes, int num_kb) {
+  static const int mode = env_int("DVAE_GEMM_TMA_STORE", 2);
+  if (mode == 0 || out == nullptr || out_f32 != nullptr || mask != nullptr || (ldo * elem_bytes) % 16 != 0) return false;
+  static const int max_kb = env_int("DVAE_GEMM_TMA_STORE_MAX_KB", 16);
+  return mode == 1 || num_kb <= max_kb;
+}
+
 // ------------------------------------------------------------------------------------ Linear
 template <typename AT>
 static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, AT* out, float* out_f32, long ldo, int M,
@@ -155,6 +169,16 @@ static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, A
     }
   }
   if (want_persistent(grid)) {
+    if (use_tma_store(out, out_f32, nullptr, ldo, EB, shp.num_kb)) {
+      typename EpiStoreTma<AT>::Params et;
+      if (int e = encode_map3(&et.tm_out, out, EB, N, M, 1, (uint64_t)ldo * EB, (uint64_t)M * ldo * EB, BK, 128, 1)) return e;
+      et.bias = bias; et.relu = relu;
+      switch (BN) {
+        case 64: return launch_gemm_persistent<64, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+        case 128: return launch_gemm_persistent<128, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+        default: return launch_gemm_persistent<256, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+      }
+    }
     switch (BN) {
       case 64: return launch_gemm_persistent<64, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
       case 128: return launch_gemm_persistent<128, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -193,6 +217,16 @@ static int linear_dgrad_t(const AT* dy, long lddy, const AT* w, AT* dx, float* d
     }
   }
   if (want_persistent(grid)) {
+    if (use_tma_store(dx, dx_f32, relu_mask, ldx, EB, shp.num_kb)) {
+      typename EpiStoreTma<AT>::Params et;
+      if (int e = encode_map3(&et.tm_out, dx, EB, K, M, 1, (uint64_t)ldx * EB, (uint64_t)M * ldx * EB, BK, 128, 1)) return e;
+      et.bias = nullptr; et.relu = 0;
+      switch (BN) {
+        case 64: return launch_gemm_persistent<64, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+        case 128: return launch_gemm_persistent<128, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+        default: return launch_gemm_persistent<256, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+      }
+    }
     switch (BN) {
       case 64: return launch_gemm_persistent<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
       case 128: return launch_gemm_persistent<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -212,6 +246,22 @@ static int pick_splits(int tiles, int num_kb) {
   int cap = num_kb / 4 > 0 ? num_kb / 4 : 1;
   int s = want < cap ? want : cap;
   return s < 1 ? 1 : s;
+}
+
+// Split-K factor for a persistent launch: the work items (tiles x splits) are dealt round-robin to one CTA per SM, so what
+// matters is how full the last wave is (40 tiles x 8 splits = 2.16 waves runs as 3), then fewer splits (less fp32
+// reduction traffic).  At least 8 k-blocks per split.
+static int pick_splits_persistent(int tiles, int num_kb) {
+  const int sms = num_sms();
+  int best = 1;
+  double best_score = -1.0;
+  for (int s = 1; s <= 24 && num_kb / s >= 8; ++s) {
+    const double waves = static_cast<double>(tiles) * s / sms;
+    const double eff = waves / static_cast<double>(ceil_div(static_cast<long>(tiles) * s, sms));
+    const double score = eff - 0.004 * s;
+    if (score > best_score) { best_score = score; best = s; }
+  }
+  return best;
 }
 
 template <typename AT>
@@ -297,6 +347,24 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
       default: return launch_gemm<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
     }
   }
+  if (want_persistent(grid) && use_tma_store(y, y_f32, nullptr, Cn, EB, shp.num_kb)) {
+    typename EpiStoreTma<AT>::Params et;
+    if (int e = encode_map3(&et.tm_out, y, EB, Cn, (uint64_t)R * T, 1, (uint64_t)Cn * EB, (uint64_t)R * T * Cn * EB, BK, 128, 1))
+      return e;
+    et.bias = bias; et.relu = 0;
+    if (!dgrad) {
+      switch (BN) {
+        case 64: return launch_gemm_persistent<64, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+        case 128: return launch_gemm_persistent<128, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+        default: return launch_gemm_persistent<256, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+      }
+    }
+    switch (BN) {
+      case 64: return launch_gemm_persistent<64, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+      case 128: return launch_gemm_persistent<128, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+      default: return launch_gemm_persistent<256, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+    }
+  }
   if (want_persistent(grid)) {
     if (!dgrad) {
       switch (BN) {
@@ -334,7 +402,12 @@ static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, in
   CUtensorMap ta, tb;
   if (int e = encode_map3(&ta, dy, EB, Cout, T, R, (uint64_t)Cout * EB, (uint64_t)T * Cout * EB, BK, BK, 1, true)) return e;
   if (int e = encode_map3(&tb, x, EB, Cin, T, R, (uint64_t)Cin * EB, (uint64_t)T * Cin * EB, BK, BK, 1, true)) return e;
-  const int BN = Cin <= 64 ? 64 : 128;
+  // 128 x 256 tiles when the filter is wide enough and the launch is persistent: the 128 x 128 tile reads 8 KB of operands
+  // per 64 tensor-core clocks (exactly the shared-memory bandwidth) and moves 1.33x the L2->SM bytes per FLOP.
+  static const int wide_env = env_int("DVAE_WGRAD_WIDE", 1);
+  int BN = Cin <= 64 ? 64 : 128;
+  const bool wide = wide_env != 0 && !g_background && Cin % 256 == 0;
+  if (wide) BN = 256;
   OperandWalk wa = zero_walk(), wb = zero_walk();
   // k-block kb -> (sequence r = kb / (T/BK)  [the "tap" slot of the walk], time block j = kb % (T/BK))
   wa.per_j[1] = BK; wa.per_tap[2] = 1; wa.per_box[0] = BK; wa.per_tile[0] = 128;
@@ -342,9 +415,15 @@ static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, in
   const int kpt = T / BK;
   const int num_kb = R * kpt;
   const int tiles = ceil_div(Cout, 128) * ceil_div(Cin, BN) * 5;
-  GemmShape shp{Cout, Cin, num_kb, kpt, pick_splits(tiles, num_kb)};
+  int splits = pick_splits(tiles, num_kb);
+  {
+    dim3 probe(ceil_div(Cout, 128), ceil_div(Cin, BN), 5 * splits);
+    if (want_persistent(probe) || wide) splits = pick_splits_persistent(tiles, num_kb);
+  }
+  GemmShape shp{Cout, Cin, num_kb, kpt, splits};
   EpiAtomic::Params ep{dwk, (long)5 * Cin, (long)Cin};
   dim3 grid(ceil_div(Cout, 128), ceil_div(Cin, BN), 5 * shp.splits);
+  if (wide) return launch_gemm_persistent<256, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
   if (want_persistent(grid)) {
     if (BN == 64) return launch_gemm_persistent<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
     return launch_gemm_persistent<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);

@@ -180,38 +180,66 @@ __global__ void recon_out_bwd_kernel(const float* __restrict__ g_rec, const floa
 }
 
 // ------------------------------------------------------------------------------------ BatchNorm1d
-// stats buffer (double) [halves][2][C]: sum, sum of squares.  Block = 64 rows x C channels.
-constexpr int kBnRowsPerBlock = 64;
+// All four streaming kernels share one mapping: a block owns a slab of 64 channels (8 threads x 8 channels = one 128-byte
+// line per row in bf16) for `rb` consecutive rows of one statistics half; its 32 row lanes walk down the rows four at a
+// time, so every thread keeps 4 (or 8, with two input tensors) independent 16-byte loads in flight -- the kernels are
+// pure HBM streams and latency x bandwidth decides how many bytes have to be outstanding.  The reductions finish with
+// 2 x 64 fp64 atomics per block (a 512-row block: 8x fewer than one atomic per channel per 64-row block).
+// stats buffer (double) [halves][2][C]: sum, sum of squares.
+constexpr int kBnRowsPerBlock = 64;    // granularity the callers guarantee for rows_half
+constexpr int kBnSlab = 64;            // channels per block
+constexpr int kBnLanes = 32;           // row lanes per block (256 threads)
+constexpr int kBnUnroll = 4;
+
+// block-level reduction of per-thread partial sums s[8], q[8] over the 32 row lanes, then fp64 atomics
+__device__ __forceinline__ void bn_block_reduce(const float* s, const float* q, float* red, double* sums_half, int c_slab,
+                                                int C) {
+  const int rl = threadIdx.x >> 3, cg = threadIdx.x & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[(rl * 2 + 0) * kBnSlab + cg * 8 + i] = s[i];
+    red[(rl * 2 + 1) * kBnSlab + cg * 8 + i] = q[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kBnSlab) {
+    const int which = threadIdx.x / kBnSlab, c = threadIdx.x - which * kBnSlab;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int l = 0; l < kBnLanes; ++l) acc += red[(l * 2 + which) * kBnSlab + c];
+    if (c_slab + c < C) atomicAdd(sums_half + static_cast<long>(which) * C + c_slab + c, static_cast<double>(acc));
+  }
+}
+
 template <typename AT>
-__global__ void bn_stats_kernel(const AT* __restrict__ y, double* __restrict__ sums, int rows_half, int C) {
-  extern __shared__ float red[];  // [lanes][2][C]
-  const int tpr = C >> 3;                     // threads per row (8 channels each)
-  const int lanes = blockDim.x / tpr;         // row lanes
-  const int rl = threadIdx.x / tpr, cg = threadIdx.x - rl * tpr;
-  const long row0 = static_cast<long>(blockIdx.x) * kBnRowsPerBlock;
+__global__ void __launch_bounds__(256) bn_stats_kernel(const AT* __restrict__ y, double* __restrict__ sums, int rows_half, int C,
+                                                       int rb) {
+  __shared__ float red[kBnLanes * 2 * kBnSlab];
+  const int rl = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  const int c_slab = blockIdx.x * kBnSlab, c0 = c_slab + cg * 8;
+  const long row0 = static_cast<long>(blockIdx.y) * rb;
   const int half = static_cast<int>(row0 / rows_half);
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  if (rl < lanes) {
-    for (int r = rl; r < kBnRowsPerBlock; r += lanes) {
-      float v[8];
-      Act8<AT>::load(y + (row0 + r) * C + cg * 8, v);
+  if (c0 < C) {
+    const AT* base = y + row0 * C + c0;
+    for (int r = rl; r < rb; r += kBnLanes * kBnUnroll) {
+      typename Act8<AT>::raw_t raw[kBnUnroll];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
-    }
+      for (int u = 0; u < kBnUnroll; ++u)
+        if (r + u * kBnLanes < rb) raw[u] = Act8<AT>::load_raw(base + static_cast<long>(r + u * kBnLanes) * C);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      red[(rl * 2 + 0) * C + cg * 8 + i] = s[i];
-      red[(rl * 2 + 1) * C + cg * 8 + i] = q[i];
+      for (int u = 0; u < kBnUnroll; ++u) {
+        if (r + u * kBnLanes < rb) {
+          float v[8];
+          Act8<AT>::unpack(raw[u], v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] = fmaf(v[i], v[i], q[i]); }
+        }
+      }
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += red[l * 2 * C + i];
-    atomicAdd(sums + static_cast<long>(half) * 2 * C + i, static_cast<double>(acc));
-  }
+  bn_block_reduce(s, q, red, sums + static_cast<long>(half) * 2 * C, c_slab, C);
 }
 // stat (fp32) [halves][4][C]: mean, rstd, scale = rstd*gamma, shift = beta - mean*scale.  Running statistics are
 // updated half by half, in call order (x1 then x2), exactly like two consecutive nn.BatchNorm1d calls.
@@ -257,87 +285,102 @@ __global__ void bn_eval_stat_kernel(const float* __restrict__ gamma, const float
 
 __device__ __forceinline__ float apply_act(float z, int act) {
   if (act == kAct_Relu) return fmaxf(z, 0.f);
-  if (act == kAct_Tanh) return tanhf(z);
+  if (act == kAct_Tanh) return tanh_f(z);
   return z;
 }
 __device__ __forceinline__ float act_grad_from_z(float z, int act) {
   if (act == kAct_Relu) return z > 0.f ? 1.f : 0.f;
-  if (act == kAct_Tanh) { const float t = tanhf(z); return 1.f - t * t; }
+  if (act == kAct_Tanh) { const float t = tanh_f(z); return 1.f - t * t; }
   return 1.f;
 }
 
-// out = act(y * scale[h] + shift[h]).  Block = 64 rows x C channels; a thread keeps the affine constants of its
-// 8 channels in registers and walks down its row lane, so the kernel is pure streaming (16-byte loads / stores).
+// out = act(y * scale[h] + shift[h]); a thread keeps the affine constants of its 8 channels in registers.
 template <typename AT>
-__global__ void bn_apply_kernel(const AT* __restrict__ y, AT* __restrict__ out, const float* __restrict__ stat, long rows,
-                                int rows_half, int C, int act) {
-  const int tpr = C >> 3;
-  const int lanes = blockDim.x / tpr;
-  const int rl = threadIdx.x / tpr, cg = threadIdx.x - rl * tpr;
-  if (rl >= lanes) return;
-  const long row0 = static_cast<long>(blockIdx.x) * kBnRowsPerBlock;
+__global__ void __launch_bounds__(256) bn_apply_kernel(const AT* __restrict__ y, AT* __restrict__ out,
+                                                       const float* __restrict__ stat, long rows, int rows_half, int C, int act,
+                                                       int rb) {
+  const int rl = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  const int c0 = blockIdx.x * kBnSlab + cg * 8;
+  if (c0 >= C) return;
+  const long row0 = static_cast<long>(blockIdx.y) * rb;
   const int h = static_cast<int>(row0 / rows_half);
   float sc[8], sh[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    sc[k] = stat[(h * 4 + 2) * C + cg * 8 + k];
-    sh[k] = stat[(h * 4 + 3) * C + cg * 8 + k];
+    sc[k] = stat[(h * 4 + 2) * C + c0 + k];
+    sh[k] = stat[(h * 4 + 3) * C + c0 + k];
   }
-  const long rend = min(rows, row0 + kBnRowsPerBlock);
-  for (long r = row0 + rl; r < rend; r += lanes) {
-    float v[8];
-    Act8<AT>::load(y + r * C + cg * 8, v);
+  const int nr = static_cast<int>(min(static_cast<long>(rb), rows - row0));
+  const AT* src = y + row0 * C + c0;
+  AT* dst = out + row0 * C + c0;
+  for (int r = rl; r < nr; r += kBnLanes * kBnUnroll) {
+    typename Act8<AT>::raw_t raw[kBnUnroll];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = apply_act(fmaf(v[k], sc[k], sh[k]), act);
-    Act8<AT>::store(out + r * C + cg * 8, v);
+    for (int u = 0; u < kBnUnroll; ++u)
+      if (r + u * kBnLanes < nr) raw[u] = Act8<AT>::load_raw(src + static_cast<long>(r + u * kBnLanes) * C);
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      if (r + u * kBnLanes < nr) {
+        float v[8];
+        Act8<AT>::unpack(raw[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = apply_act(fmaf(v[k], sc[k], sh[k]), act);
+        Act8<AT>::store(dst + static_cast<long>(r + u * kBnLanes) * C, v);
+      }
+    }
   }
 }
 
 // backward pass 1: per (half, channel) sums of dz and dz*xhat, dz = dout * act'(z)
 template <typename AT>
-__global__ void bn_bwd_reduce_kernel(const AT* __restrict__ dout, const AT* __restrict__ y, const float* __restrict__ stat,
-                                     double* __restrict__ sums, int rows_half, int C, int act) {
-  extern __shared__ float red[];
-  const int tpr = C >> 3;
-  const int lanes = blockDim.x / tpr;
-  const int rl = threadIdx.x / tpr, cg = threadIdx.x - rl * tpr;
-  const long row0 = static_cast<long>(blockIdx.x) * kBnRowsPerBlock;
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const AT* __restrict__ dout, const AT* __restrict__ y,
+                                                            const float* __restrict__ stat, double* __restrict__ sums,
+                                                            int rows_half, int C, int act, int rb) {
+  __shared__ float red[kBnLanes * 2 * kBnSlab];
+  const int rl = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  const int c_slab = blockIdx.x * kBnSlab, c0 = c_slab + cg * 8;
+  const long row0 = static_cast<long>(blockIdx.y) * rb;
   const int h = static_cast<int>(row0 / rows_half);
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  if (rl < lanes) {
+  if (c0 < C) {
     float mean[8], rstd[8], sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      mean[i] = stat[(h * 4 + 0) * C + cg * 8 + i];
-      rstd[i] = stat[(h * 4 + 1) * C + cg * 8 + i];
-      sc[i] = stat[(h * 4 + 2) * C + cg * 8 + i];
-      sh[i] = stat[(h * 4 + 3) * C + cg * 8 + i];
+      mean[i] = stat[(h * 4 + 0) * C + c0 + i];
+      rstd[i] = stat[(h * 4 + 1) * C + c0 + i];
+      sc[i] = stat[(h * 4 + 2) * C + c0 + i];
+      sh[i] = stat[(h * 4 + 3) * C + c0 + i];
     }
-    for (int r = rl; r < kBnRowsPerBlock; r += lanes) {
-      float v[8], d[8];
-      Act8<AT>::load(y + (row0 + r) * C + cg * 8, v);
-      Act8<AT>::load(dout + (row0 + r) * C + cg * 8, d);
+    const AT* ys = y + row0 * C + c0;
+    const AT* dsrc = dout + row0 * C + c0;
+    for (int r = rl; r < rb; r += kBnLanes * kBnUnroll) {
+      typename Act8<AT>::raw_t ry[kBnUnroll], rd[kBnUnroll];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float dz = d[i] * act_grad_from_z(fmaf(v[i], sc[i], sh[i]), act);
-        s[i] += dz;
-        q[i] += dz * (v[i] - mean[i]) * rstd[i];
+      for (int u = 0; u < kBnUnroll; ++u) {
+        if (r + u * kBnLanes < rb) {
+          ry[u] = Act8<AT>::load_raw(ys + static_cast<long>(r + u * kBnLanes) * C);
+          rd[u] = Act8<AT>::load_raw(dsrc + static_cast<long>(r + u * kBnLanes) * C);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        if (r + u * kBnLanes < rb) {
+          float v[8], d[8];
+          Act8<AT>::unpack(ry[u], v);
+          Act8<AT>::unpack(rd[u], d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float dz = d[i] * act_grad_from_z(fmaf(v[i], sc[i], sh[i]), act);
+            s[i] += dz;
+            q[i] = fmaf(dz, (v[i] - mean[i]) * rstd[i], q[i]);
+          }
+        }
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      red[(rl * 2 + 0) * C + cg * 8 + i] = s[i];
-      red[(rl * 2 + 1) * C + cg * 8 + i] = q[i];
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-    float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += red[l * 2 * C + i];
-    atomicAdd(sums + static_cast<long>(h) * 2 * C + i, static_cast<double>(acc));
-  }
+  bn_block_reduce(s, q, red, sums + static_cast<long>(h) * 2 * C, c_slab, C);
 }
 // dgamma = sum_h sum dz*xhat, dbeta = sum_h sum dz; coef [halves][2][C] = (sum dz)/n, (sum dz*xhat)/n
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, float* __restrict__ coef, float* __restrict__ dgamma,
@@ -356,16 +399,15 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, float* _
 }
 // backward pass 2: dy = scale * (dz - mean(dz) - xhat * mean(dz*xhat)); same streaming structure as bn_apply_kernel
 template <typename AT>
-__global__ void bn_bwd_apply_kernel(const AT* __restrict__ dout, const AT* __restrict__ y, const float* __restrict__ stat,
-                                    const float* __restrict__ coef, AT* __restrict__ dy, long rows, int rows_half, int C,
-                                    int act) {
-  const int tpr = C >> 3;
-  const int lanes = blockDim.x / tpr;
-  const int rl = threadIdx.x / tpr, cg = threadIdx.x - rl * tpr;
-  if (rl >= lanes) return;
-  const long row0 = static_cast<long>(blockIdx.x) * kBnRowsPerBlock;
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const AT* __restrict__ dout, const AT* __restrict__ y,
+                                                           const float* __restrict__ stat, const float* __restrict__ coef,
+                                                           AT* __restrict__ dy, long rows, int rows_half, int C, int act,
+                                                           int rb) {
+  const int rl = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  const int c0 = blockIdx.x * kBnSlab + cg * 8;
+  if (c0 >= C) return;
+  const long row0 = static_cast<long>(blockIdx.y) * rb;
   const int h = static_cast<int>(row0 / rows_half);
-  const int c0 = cg * 8;
   float mean[8], rstd[8], sc[8], sh[8], k0[8], k1[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -376,18 +418,34 @@ __global__ void bn_bwd_apply_kernel(const AT* __restrict__ dout, const AT* __res
     k0[k] = coef[(h * 2 + 0) * C + c0 + k];
     k1[k] = coef[(h * 2 + 1) * C + c0 + k];
   }
-  const long rend = min(rows, row0 + kBnRowsPerBlock);
-  for (long r = row0 + rl; r < rend; r += lanes) {
-    float v[8], d[8];
-    Act8<AT>::load(y + r * C + c0, v);
-    Act8<AT>::load(dout + r * C + c0, d);
+  const int nr = static_cast<int>(min(static_cast<long>(rb), rows - row0));
+  const AT* ys = y + row0 * C + c0;
+  const AT* dsrc = dout + row0 * C + c0;
+  AT* dst = dy + row0 * C + c0;
+  for (int r = rl; r < nr; r += kBnLanes * kBnUnroll) {
+    typename Act8<AT>::raw_t ry[kBnUnroll], rd[kBnUnroll];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float dz = d[k] * act_grad_from_z(fmaf(v[k], sc[k], sh[k]), act);
-      const float xh = (v[k] - mean[k]) * rstd[k];
-      d[k] = sc[k] * (dz - k0[k] - xh * k1[k]);
+    for (int u = 0; u < kBnUnroll; ++u) {
+      if (r + u * kBnLanes < nr) {
+        ry[u] = Act8<AT>::load_raw(ys + static_cast<long>(r + u * kBnLanes) * C);
+        rd[u] = Act8<AT>::load_raw(dsrc + static_cast<long>(r + u * kBnLanes) * C);
+      }
     }
-    Act8<AT>::store(dy + r * C + c0, d);
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      if (r + u * kBnLanes < nr) {
+        float v[8], d[8];
+        Act8<AT>::unpack(ry[u], v);
+        Act8<AT>::unpack(rd[u], d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float dz = d[k] * act_grad_from_z(fmaf(v[k], sc[k], sh[k]), act);
+          const float xh = (v[k] - mean[k]) * rstd[k];
+          d[k] = sc[k] * (dz - k0[k] - xh * k1[k]);
+        }
+        Act8<AT>::store(dst + static_cast<long>(r + u * kBnLanes) * C, d);
+      }
+    }
   }
 }
 
@@ -522,6 +580,13 @@ int dvae_recon_out_bwd(int dtype, const float* g_rec, const float* g_hat, void* 
   return 0;
 }
 
+// rows per block: the largest power-of-two multiple of 64 up to `want` that divides rows_half (blocks never straddle halves)
+static int bn_rows_per_block(int rows_half, int want) {
+  int rb = kBnRowsPerBlock;
+  while (rb * 2 <= want && rows_half % (rb * 2) == 0) rb *= 2;
+  return rb;
+}
+
 // Train-mode BatchNorm forward over y [halves*rows_half, C]: statistics per half, then act(y*scale+shift).
 // ws: double [halves*2*C] scratch; stat: fp32 [halves*4*C] (kept for backward).
 int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
@@ -532,15 +597,12 @@ int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, c
   DVAE_REQUIRE(rows_half % kBnRowsPerBlock == 0, "rows per half must be a multiple of 64");
   const long rows = static_cast<long>(rows_half) * halves;
   DVAE_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * halves * 2 * C, st));
-  const int tpr = C / 8;
-  const int threads = 256;
-  const int lanes = threads / tpr;
-  DVAE_REQUIRE(lanes >= 1, "C too large for one block");
-  const int smem = lanes * 2 * C * 4;
-  DISPATCH_AT(dtype, bn_stats_kernel<AT><<<rows / kBnRowsPerBlock, threads, smem, st>>>((const AT*)y, ws, rows_half, C));
+  const int rb_red = bn_rows_per_block(rows_half, 512), rb_app = bn_rows_per_block(rows_half, 256);
+  const dim3 g_red(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_red)), g_app(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_app));
+  DISPATCH_AT(dtype, bn_stats_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)y, ws, rows_half, C, rb_red));
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, gamma, beta, stat, run_mean, run_var, num_batches, halves, C,
                                                         static_cast<double>(rows_half), eps, momentum);
-  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<rows / kBnRowsPerBlock, threads, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half, C, act));
+  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<g_app, 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half, C, act, rb_app));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -549,10 +611,10 @@ int dvae_bn_eval_fwd(int dtype, const void* y, void* out, const float* gamma, co
   auto st = static_cast<cudaStream_t>(stream);
   DVAE_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
   bn_eval_stat_kernel<<<ceil_div(C, 128), 128, 0, st>>>(gamma, beta, run_mean, run_var, stat, C, eps);
-  const int tpr = C / 8;
   const int rows_half = rows > 0x7fffffffL ? 0x7fffffff : static_cast<int>(rows);
-  DVAE_REQUIRE(tpr <= 256, "C too large for one block");
-  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<ceil_div(rows, kBnRowsPerBlock), 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half > 0 ? rows_half : 1, C, act));
+  const dim3 g_app(ceil_div(C, kBnSlab), static_cast<unsigned>(ceil_div(rows, 256)));
+  if (rows > 0)
+    DISPATCH_AT(dtype, bn_apply_kernel<AT><<<g_app, 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half > 0 ? rows_half : 1, C, act, 256));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -564,11 +626,11 @@ int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* s
   DVAE_REQUIRE(rows_half % kBnRowsPerBlock == 0, "rows per half must be a multiple of 64");
   const long rows = static_cast<long>(rows_half) * halves;
   DVAE_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * halves * 2 * C, st));
-  const int tpr = C / 8, threads = 256, lanes = threads / tpr;
-  const int smem = lanes * 2 * C * 4;
-  DISPATCH_AT(dtype, bn_bwd_reduce_kernel<AT><<<rows / kBnRowsPerBlock, threads, smem, st>>>((const AT*)dout, (const AT*)y, stat, ws, rows_half, C, act));
+  const int rb_red = bn_rows_per_block(rows_half, 512), rb_app = bn_rows_per_block(rows_half, 256);
+  const dim3 g_red(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_red)), g_app(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_app));
+  DISPATCH_AT(dtype, bn_bwd_reduce_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)dout, (const AT*)y, stat, ws, rows_half, C, act, rb_red));
   bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, coef, dgamma, dbeta, halves, C, static_cast<double>(rows_half));
-  DISPATCH_AT(dtype, bn_bwd_apply_kernel<AT><<<rows / kBnRowsPerBlock, threads, 0, st>>>((const AT*)dout, (const AT*)y, stat, coef, (AT*)dy, rows, rows_half, C, act));
+  DISPATCH_AT(dtype, bn_bwd_apply_kernel<AT><<<g_app, 256, 0, st>>>((const AT*)dout, (const AT*)y, stat, coef, (AT*)dy, rows, rows_half, C, act, rb_app));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -85,6 +85,12 @@ struct epi_is_staged { static constexpr bool value = false; };
 template <class Epi>
 struct epi_is_staged<Epi, decltype((void)Epi::kStaged)> { static constexpr bool value = Epi::kStaged; };
 
+template <class Epi, int BLOCK_N>
+__host__ __device__ constexpr int persistent_staging_bytes() {
+  if constexpr (epi_is_staged<Epi>::value) return Epi::template staging_bytes<BLOCK_N>();
+  else return 0;
+}
+
 // Optional per-CTA phase stamps (globaltimer ns): [cta][0]=entry [1]=setup done [2]=producer done [3]=accumulator ready
 // [4]=epilogue done.  Off (nullptr) unless dvae_debug_timing() installs a buffer; one predictable branch per stamp.
 __device__ unsigned long long* g_phase_stamps = nullptr;
@@ -343,8 +349,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                          const OperandWalk wa, const OperandWalk wb, const GemmShape shp, const typename Epi::Params ep,
-                          const int tiles_m, const int tiles_n, const int num_tiles) {
+                          const OperandWalk wa, const OperandWalk wb, const GemmShape shp,
+                          const __grid_constant__ typename Epi::Params ep, const int tiles_m, const int tiles_n,
+                          const int num_tiles) {
   constexpr int BLOCK_K = kSwizzleRow / ELEM_BYTES;
   constexpr int UMMA_K = 32 / ELEM_BYTES;
   constexpr int STAGE_A = kBlockM * kSwizzleRow;
@@ -359,18 +366,20 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   constexpr uint32_t IDESC = instr_desc<ELEM_BYTES, BLOCK_N, A_MN, B_MN>();
   constexpr int TMEM_COLS = 2 * BLOCK_N;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "two accumulators must fit TMEM");
+  constexpr int RING = STAGES * (STAGE_A + STAGE_B);
+  constexpr int STAGING = persistent_staging_bytes<Epi, BLOCK_N>();   // staged epilogues: one output tile, after the ring
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   const uint32_t smem_base = raw_addr + pad;
-  const uint32_t bar_base = smem_base + STAGES * (STAGE_A + STAGE_B);
+  const uint32_t bar_base = smem_base + RING + STAGING;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + STAGES * (STAGE_A + STAGE_B) + 8 * (2 * STAGES + 4));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + RING + STAGING + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -508,10 +517,34 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       acc.split_stride = 0;
       ptx::mbar_wait(tmem_full_bar(as), (local >> 1) & 1);
       ptx::tc_fence_after();
-      Epi::template run<BLOCK_N>(ep, acc, regs, m, n0, zb, col0, col1, shp);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));   // this warp no longer reads accumulator `as`
+      if constexpr (epi_is_staged<Epi>::value) {
+        // Output tile -> swizzled staging -> TMA store.  The accumulator is released as soon as it is in shared memory;
+        // the store of tile i drains while the main loop of tile i+1 runs, and is only waited for when the staging
+        // buffer is needed again.
+        const uint32_t stage = smem_base + RING;
+        if (local > 0) {
+          if (threadIdx.x == 64) ptx::bulk_wait_read<0>();
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
+        Epi::template run_staged<BLOCK_N>(ep, acc, regs, q * 32 + lane, m, n0, zb, col0, col1, shp, stage);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+          Epi::template flush<BLOCK_N>(ep, stage, tm, tn, zb, shp);
+          ptx::bulk_commit();
+        }
+      } else {
+        Epi::template run<BLOCK_N>(ep, acc, regs, m, n0, zb, col0, col1, shp);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));   // this warp no longer reads accumulator `as`
+      }
+    }
+    if constexpr (epi_is_staged<Epi>::value) {
+      if (threadIdx.x == 64) ptx::bulk_wait_read<0>();
     }
   }
   __syncthreads();
@@ -655,6 +688,85 @@ struct EpiStore {
           }
         }
       }
+    }
+  }
+};
+
+// ---- out = act(acc + bias) -> activation dtype through staging + TMA store.  The direct version (EpiStore) writes one
+// row per lane: 16 st.global.v4 per thread for a 128 x 256 bf16 tile, 32 LSU transactions per warp instruction, ~2 us per
+// tile -- as long as the whole main loop when K <= 512 (LSTM input projections, 80-channel convolutions).
+template <typename OutT>
+struct EpiStoreTma {
+  static constexpr bool kFixup = true;    // needs the complete sum: no split-K
+  static constexpr bool kStaged = true;
+  static constexpr int kCtasPerSm = 1;
+  static constexpr int EB = sizeof(OutT);
+  struct Params {
+    CUtensorMap tm_out;   // OutT {N, M, batches}, box {128 / EB, 128, 1}
+    const float* bias;    // [N] or null
+    int relu;
+  };
+  template <int BLOCK_N>
+  static __host__ __device__ constexpr int staging_bytes() { return BLOCK_N * EB * kBlockM; }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void prefetch(const Params&, int, int, int, int, int, const GemmShape&) {}
+  template <int BLOCK_N> struct Regs {};
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void preload(const Params&, Regs<BLOCK_N>&, int, int, int, int, int, const GemmShape&) {}
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run_staged(const Params& p, const AccSource& acc, const Regs<BLOCK_N>&, int row, int m,
+                                                    int n0, int zb, int col0, int col1, const GemmShape& shp,
+                                                    uint32_t stage) {
+#pragma unroll 1
+    for (int c = col0; c < col1; c += 32) {
+      if (n0 + c >= shp.N) break;
+      __syncwarp();
+      float v[32];
+      acc.template load<32>(c, v);
+      const int nb = n0 + c;
+      if (p.bias != nullptr) {
+        if (nb + 32 <= shp.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + i);
+            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (nb + i < shp.N) v[i] += __ldg(p.bias + nb + i);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 32 * EB / 16; ++j) {
+        uint4 u;
+        if constexpr (EB == 2) {
+          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+        } else {
+          u = make_uint4(__float_as_uint(round_tf32(v[4 * j])), __float_as_uint(round_tf32(v[4 * j + 1])),
+                         __float_as_uint(round_tf32(v[4 * j + 2])), __float_as_uint(round_tf32(v[4 * j + 3])));
+        }
+        const int byte = c * EB + 16 * j;
+        ptx::st_shared_v4(stage + static_cast<uint32_t>((byte >> 7) * (kBlockM * 128) + row * 128 +
+                                                        ((((byte & 127) >> 4) ^ (row & 7)) << 4)),
+                          u);
+      }
+    }
+  }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void flush(const Params& p, uint32_t stage, int tile_m, int tile_n, int zb,
+                                               const GemmShape& shp) {
+    constexpr int GE = 128 / EB;
+#pragma unroll 1
+    for (int b = 0; b < BLOCK_N / GE; ++b) {
+      if (tile_n * BLOCK_N + b * GE >= shp.N) break;
+      ptx::tma_store_3d(&p.tm_out, stage + b * (kBlockM * 128), tile_n * BLOCK_N + b * GE, tile_m * kBlockM, zb);
     }
   }
 };

@@ -14,6 +14,7 @@ Data layout in HBM (R2 = rows in flight, T = 64 frames):
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -131,7 +132,7 @@ class Engine:
     def __init__(self, dt: int, latent_dim: int, speaker_size: int, bn_eps: float = 1e-5, bn_momentum: float = 0.1):
         self.buckets = None   # set to a parallel.GradBuckets for data-parallel training
         self.side_stream = None     # created lazily; weight-gradient GEMMs that are off the critical path run here
-        self.use_side_stream = True
+        self.use_side_stream = os.environ.get("DVAE_SIDE_STREAM", "1") != "0"   # A/B switch for profiling
         self._keepalive: List[tuple] = []
         self.dt = dt
         self.L = latent_dim
