@@ -98,6 +98,31 @@ __device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f
 __device__ __forceinline__ float tanh_f(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
 
 
+// Gate non-linearities of the LSTM cells, selected by the storage type.  fp32-on-the-tf32-grid storage keeps the exp-based
+// forms (2 MUFU ops each).  bf16 storage uses the hardware tanh (1 MUFU op; absolute error ~5e-4, below the 2e-3 rounding
+// step of a bf16 gate value near 1): the cell epilogues are MUFU-bound -- 10 special-function ops per hidden unit and row
+// with the exp forms, 5 with these.  DVAE_GATE_APPROX=0 at compile time restores the exp forms everywhere.
+#ifndef DVAE_GATE_APPROX
+#define DVAE_GATE_APPROX 1
+#endif
+__device__ __forceinline__ float tanh_hw(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename ActT>
+struct GateMath {
+  static __device__ __forceinline__ float sig(float x) { return sigmoid_f(x); }
+  static __device__ __forceinline__ float tnh(float x) { return tanh_f(x); }
+};
+#if DVAE_GATE_APPROX
+template <>
+struct GateMath<__nv_bfloat16> {
+  static __device__ __forceinline__ float sig(float x) { return fmaf(tanh_hw(0.5f * x), 0.5f, 0.5f); }
+  static __device__ __forceinline__ float tnh(float x) { return tanh_hw(x); }
+};
+#endif
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -579,7 +579,7 @@ __global__ void lstm_cell_bwd_kernel(const AT* __restrict__ dh_out, float* __res
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float ig = g4[4 * k], fg = g4[4 * k + 1], gg = g4[4 * k + 2], og = g4[4 * k + 3];
-      const float tc = tanh_f(cc[k]);
+      const float tc = GateMath<AT>::tnh(cc[k]);
       const float dht = dh[k] + (dh_rec ? rec[k] : 0.f);
       const float dct = (dc_zero ? 0.f : dcv[k]) + dht * og * (1.f - tc * tc);
       dao[k] = dht * tc * og * (1.f - og);

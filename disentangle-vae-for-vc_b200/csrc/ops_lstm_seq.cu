@@ -189,12 +189,12 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, AT* __restrict__ xg
       float cn[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float ig = sigmoid_f(a[4 * i] + x[4 * i]), fg = sigmoid_f(a[4 * i + 1] + x[4 * i + 1]);
-        const float gg = tanh_f(a[4 * i + 2] + x[4 * i + 2]), og = sigmoid_f(a[4 * i + 3] + x[4 * i + 3]);
+        const float ig = GateMath<AT>::sig(a[4 * i] + x[4 * i]), fg = GateMath<AT>::sig(a[4 * i + 1] + x[4 * i + 1]);
+        const float gg = GateMath<AT>::tnh(a[4 * i + 2] + x[4 * i + 2]), og = GateMath<AT>::sig(a[4 * i + 3] + x[4 * i + 3]);
         a[4 * i] = ig; a[4 * i + 1] = fg; a[4 * i + 2] = gg; a[4 * i + 3] = og;
         cn[i] = fg * c[8 * k + i] + ig * gg;
         c[8 * k + i] = cn[i];
-        hn[8 * k + i] = og * tanh_f(cn[i]);
+        hn[8 * k + i] = og * GateMath<AT>::tnh(cn[i]);
       }
       if (row_ok) {
         AT* gp = xrow + static_cast<long>(t) * D * 4 * H + 32 * k;
@@ -375,7 +375,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const AT* __restric
       for (int i = 0; i < 8; ++i) {
         const int u = 8 * k + i;
         const float ig = g4[4 * i], fg = g4[4 * i + 1], gg = g4[4 * i + 2], og = g4[4 * i + 3];
-        const float tc = tanh_f(ca[u]);
+        const float tc = GateMath<AT>::tnh(ca[u]);
         const float dht = dh[i] + rec[u];
         const float dct = dc[u] + dht * og * (1.f - tc * tc);
         dao[u] = dht * tc * og * (1.f - og);
@@ -643,12 +643,12 @@ lstm_seq_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_co
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float* xx = x + 32 * k + 4 * i;
-          const float ig = sigmoid_f(a[4 * i] + xx[0]), fg = sigmoid_f(a[4 * i + 1] + xx[1]);
-          const float gg = tanh_f(a[4 * i + 2] + xx[2]), og = sigmoid_f(a[4 * i + 3] + xx[3]);
+          const float ig = GateMath<AT>::sig(a[4 * i] + xx[0]), fg = GateMath<AT>::sig(a[4 * i + 1] + xx[1]);
+          const float gg = GateMath<AT>::tnh(a[4 * i + 2] + xx[2]), og = GateMath<AT>::sig(a[4 * i + 3] + xx[3]);
           a[4 * i] = ig; a[4 * i + 1] = fg; a[4 * i + 2] = gg; a[4 * i + 3] = og;
           cn[i] = fg * c[8 * k + i] + ig * gg;
           c[8 * k + i] = cn[i];
-          hn[8 * k + i] = og * tanh_f(cn[i]);
+          hn[8 * k + i] = og * GateMath<AT>::tnh(cn[i]);
         }
         sts_slice<AT, 32>(xb, lane, 64 * q + 32 * k, a);      // activated gates, in place of the x-projection
         sts_slice<float, 8>(cb, lane, 16 * q + 8 * k, cn);
@@ -840,7 +840,7 @@ lstm_seq_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_co
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const float ig = g4[4 * u], fg = g4[4 * u + 1], gg = g4[4 * u + 2], og = g4[4 * u + 3];
-        const float tc = tanh_f(ca[u]);
+        const float tc = GateMath<AT>::tnh(ca[u]);
         const float dht = dh[u] + rec[u];
         const float dct = dc[u] + dht * og * (1.f - tc * tc);
         dao[u] = dht * tc * og * (1.f - og);

@@ -885,11 +885,11 @@ struct EpiLstmFwd {
         float cn[8], hn[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float ig = sigmoid_f(a[4 * i] + x[4 * i]), fg = sigmoid_f(a[4 * i + 1] + x[4 * i + 1]);
-          const float gg = tanh_f(a[4 * i + 2] + x[4 * i + 2]), og = sigmoid_f(a[4 * i + 3] + x[4 * i + 3]);
+          const float ig = GateMath<ActT>::sig(a[4 * i] + x[4 * i]), fg = GateMath<ActT>::sig(a[4 * i + 1] + x[4 * i + 1]);
+          const float gg = GateMath<ActT>::tnh(a[4 * i + 2] + x[4 * i + 2]), og = GateMath<ActT>::sig(a[4 * i + 3] + x[4 * i + 3]);
           a[4 * i] = ig; a[4 * i + 1] = fg; a[4 * i + 2] = gg; a[4 * i + 3] = og;
           cn[i] = fg * cprev[i] + ig * gg;
-          hn[i] = og * tanh_f(cn[i]);
+          hn[i] = og * GateMath<ActT>::tnh(cn[i]);
         }
         Act8<float>::store(co + c / 4, cn);
         Act8<ActT>::store(ho + c / 4, hn);
@@ -958,11 +958,11 @@ struct EpiLstmFwdTma : EpiLstmFwd<ActT> {
       float cn[8], hn[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float ig = sigmoid_f(a[4 * i] + x[4 * i]), fg = sigmoid_f(a[4 * i + 1] + x[4 * i + 1]);
-        const float gg = tanh_f(a[4 * i + 2] + x[4 * i + 2]), og = sigmoid_f(a[4 * i + 3] + x[4 * i + 3]);
+        const float ig = GateMath<ActT>::sig(a[4 * i] + x[4 * i]), fg = GateMath<ActT>::sig(a[4 * i + 1] + x[4 * i + 1]);
+        const float gg = GateMath<ActT>::tnh(a[4 * i + 2] + x[4 * i + 2]), og = GateMath<ActT>::sig(a[4 * i + 3] + x[4 * i + 3]);
         a[4 * i] = ig; a[4 * i + 1] = fg; a[4 * i + 2] = gg; a[4 * i + 3] = og;
         cn[i] = fg * cprev[i] + ig * gg;
-        hn[i] = og * tanh_f(cn[i]);
+        hn[i] = og * GateMath<ActT>::tnh(cn[i]);
       }
       // gates: 32 columns = 32*EB bytes at byte c*EB of the row
 #pragma unroll
@@ -1102,7 +1102,7 @@ struct EpiLstmBwd {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float ig = g4[k][4 * i], fg = g4[k][4 * i + 1], gg = g4[k][4 * i + 2], og = g4[k][4 * i + 3];
-            const float tc = tanh_f(cc[k][i]);
+            const float tc = GateMath<ActT>::tnh(cc[k][i]);
             const float dht = dh[k][i] + acc[i];
             const float dct = dc[k][i] + dht * og * (1.f - tc * tc);
             dao[i] = dht * tc * og * (1.f - og);
