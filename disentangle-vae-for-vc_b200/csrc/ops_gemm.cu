@@ -35,7 +35,7 @@ struct Stages2 {
 
 template <int BN, bool A_MN, bool B_MN, int EB, class Epi, int MT = 1, int ST = (MT == 2 ? Stages2<BN>::value : Stages<BN>::value)>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const OperandWalk& wa, const OperandWalk& wb,
-                       const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream) {
+                       const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream, int cluster = 1) {
   if (Epi::kFixup && shp.splits > 1 && (shp.splitk_ws == nullptr || shp.tickets == nullptr)) {
     set_last_error("split-K with a full-sum epilogue needs a fix-up workspace and tickets");
     return 1;
@@ -54,11 +54,26 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const Opera
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {   // CTAs of a cluster = consecutive M tiles; they share (multicast) the B operand
+    if (MT != 1 || grid.x % cluster != 0 || (Epi::kFixup && shp.splits > 1)) {
+      set_last_error("cluster launch needs single-accumulator tiles, grid.x divisible by the cluster size and no fix-up split-K");
+      return 1;
+    }
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   DVAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, wa, wb, shp, ep));
   return 0;
 }
@@ -474,6 +489,18 @@ static int lstm_bwd_splits(int rows, int H, int D, int elem_bytes) {
   return s < 1 ? 1 : s;
 }
 
+// Cluster size of the recurrence step kernels (CTAs of a cluster = consecutive row tiles sharing the weight tile by TMA
+// multicast): DVAE_LSTM_CLUSTER = 1 | 2 | 4, reduced until it divides the number of row tiles and the B tile's parts.
+// Default 1: measured on B200 (profiles/r01_lstm_cluster_multicast.txt) multicast makes the step SLOWER (main loop
+// 8.45 -> 9.7 us at H = 1024): the main loop is bound by bytes in flight per SM (4 stages x 48 KB against ~1.7 us of loaded
+// L2 latency), not by L2 bandwidth, and multicast only couples the two pipelines.  Kept as a tested option.
+static int lstm_cluster(int row_tiles, int b_parts) {
+  static const int want = env_int("DVAE_LSTM_CLUSTER", 1);
+  int c = (want == 2 || want == 4) ? want : 1;
+  while (c > 1 && (row_tiles % c != 0 || b_parts % c != 0)) c >>= 1;
+  return c;
+}
+
 template <typename AT>
 static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows, int T, int H, int D, cudaStream_t st) {
   constexpr int EB = sizeof(AT);
@@ -484,7 +511,9 @@ static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows
   CUtensorMap ta, tb;
   if (int e = encode_map3(&ta, h_all, EB, (uint64_t)D * H, T, rows, (uint64_t)D * H * EB, (uint64_t)T * D * H * EB, BK, 1, 128))
     return e;
-  if (int e = encode_map3(&tb, whh_p, EB, H, 4 * H, D, (uint64_t)H * EB, (uint64_t)4 * H * H * EB, BK, BN, 1)) return e;
+  // clusters of consecutive row tiles share (multicast) the W_hh tile: each CTA fetches BN / cluster of its rows
+  const int cluster = lstm_cluster(ceil_div(rows, 128), BN >= 128 ? BN / 64 : 1);
+  if (int e = encode_map3(&tb, whh_p, EB, H, 4 * H, D, (uint64_t)H * EB, (uint64_t)4 * H * H * EB, BK, BN / cluster, 1)) return e;
   const long ldx = (long)T * D * 4 * H, ldc = (long)T * D * H;
   // staged (TMA) stores of gates / c / h for the wide tiles; DVAE_LSTM_FWD_TMA=0 keeps the direct row-per-lane stores
   static const int tma_env = env_int("DVAE_LSTM_FWD_TMA", 1);
@@ -526,14 +555,14 @@ static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows
       fill(ep);
       ep.tm_g = tg; ep.tm_c = tc; ep.tm_h = th;
       ep.t[0] = tf; ep.t[1] = tr; ep.H = H;
-      e = (BN == 256) ? launch_gemm<256, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
-                      : launch_gemm<128, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      e = (BN == 256) ? launch_gemm<256, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st, cluster)
+                      : launch_gemm<128, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st, cluster);
     } else {
       typename EpiLstmFwd<AT>::Params ep;
       fill(ep);
-      e = (BN == 256)   ? launch_gemm<256, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
-          : (BN == 128) ? launch_gemm<128, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
-                        : launch_gemm<64, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      e = (BN == 256)   ? launch_gemm<256, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st, cluster)
+          : (BN == 128) ? launch_gemm<128, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st, cluster)
+                        : launch_gemm<64, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st, cluster);
     }
     if (e) return e;
   }
@@ -649,8 +678,9 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
           GemmShape shp{rows, H, 4 * H / BK, 4 * H / BK, rsplits, nullptr, nullptr};
           EpiReduceTma::Params ep{trec};
           dim3 grid(ceil_div(rows, 128), H / RBN, D * rsplits);
-          int e = (RBN == 256) ? launch_gemm<256, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st)
-                               : launch_gemm<128, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st);
+          const int cluster = lstm_cluster(ceil_div(rows, 128), RBN * EB / 128);
+          int e = (RBN == 256) ? launch_gemm<256, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st, cluster)
+                               : launch_gemm<128, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st, cluster);
           if (e) return e;
         } else {
           wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN; wb.per_z[2] = 1;

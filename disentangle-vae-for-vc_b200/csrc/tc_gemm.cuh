@@ -164,13 +164,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_end = min(shp.num_kb, kb_begin + kb_chunk);
   const int num_local = max(0, kb_end - kb_begin);
 
+  // Cluster of cs CTAs along x (consecutive M tiles, same N tile, same batch / split): the B tile is identical for all
+  // of them, so each CTA fetches 1/cs of it and multicasts that share to every CTA of the cluster.  The step kernels of
+  // the LSTM recurrence are bound by L2->SM operand traffic (~11.6 TB/s measured); this removes (cs-1)/cs of the B bytes.
+  // An operand slot may only be refilled once ALL CTAs of the cluster have consumed it: the MMA warps commit to the
+  // empty barrier of every CTA (count cs).
+  const uint32_t cs = ptx::cluster_nctarank(), cr = ptx::cluster_ctarank();
+  const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
   if (threadIdx.x == 0) phase_stamp(0);
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), cs);
     }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_barrier_init();
@@ -180,7 +187,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (cs > 1) ptx::cluster_sync();   // peers must see initialised barriers before their multicasts / commits arrive
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // PDL: the set-up above overlapped the previous kernel; from here on we read / write its data
@@ -213,14 +221,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tma_load_3d(sa + mt * TILE_A + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
           }
         }
+        if (cs == 1) {
 #pragma unroll
-        for (int i = 0; i < B_BOXES; ++i) {
+          for (int i = 0; i < B_BOXES; ++i) {
+            int c[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+              c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + i * wb.per_box[d] + tile_n * wb.per_tile[d] +
+                     zb * wb.per_z[d];
+            ptx::tma_load_3d(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
+          }
+        } else if constexpr (B_MN) {   // my share = B_BOXES / cs of the MN-major boxes
+          const int per = B_BOXES / static_cast<int>(cs);
+          for (int i = static_cast<int>(cr) * per; i < (static_cast<int>(cr) + 1) * per; ++i) {
+            int c[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+              c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + i * wb.per_box[d] + tile_n * wb.per_tile[d] +
+                     zb * wb.per_z[d];
+            ptx::tma_load_3d_multicast(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2], cmask);
+          }
+        } else {                       // my share = BLOCK_N / cs rows of the K-major tile (the host encoded that box height)
           int c[3];
 #pragma unroll
           for (int d = 0; d < 3; ++d)
-            c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + i * wb.per_box[d] + tile_n * wb.per_tile[d] +
-                   zb * wb.per_z[d];
-          ptx::tma_load_3d(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
+            c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + tile_n * wb.per_tile[d] +
+                   static_cast<int>(cr) * (wb.per_tile[d] / static_cast<int>(cs)) + zb * wb.per_z[d];
+          ptx::tma_load_3d_multicast(sb + cr * (STAGE_B / cs), &tmB, full_bar(s), c[0], c[1], c[2], cmask);
         }
       }
       phase_stamp(2);
@@ -250,7 +277,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::umma<ELEM_BYTES>(tmem_base + mt * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
                                   (it > 0 || k > 0) ? 1u : 0u);
         }
-        ptx::umma_commit(empty_bar(s));  // frees the smem slot once these MMAs retire
+        if (cs > 1) ptx::umma_commit_multicast(empty_bar(s), cmask);   // the slot is shared cluster-wide
+        else ptx::umma_commit(empty_bar(s));                             // frees the smem slot once these MMAs retire
       }
       __syncwarp();
     }
@@ -332,7 +360,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 64) phase_stamp(4);
     ptx::tc_fence_before();
   }
-  __syncthreads();
+  if (cs > 1) ptx::cluster_sync();   // my commits arrive on the peers' barriers: nobody leaves before everybody is done
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
