@@ -35,7 +35,7 @@ struct Stages2 {
 
 template <int BN, bool A_MN, bool B_MN, int EB, class Epi, int MT = 1, int ST = (MT == 2 ? Stages2<BN>::value : Stages<BN>::value)>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const OperandWalk& wa, const OperandWalk& wb,
-                       const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream, int cluster = 1) {
+                       const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream) {
   if (Epi::kFixup && shp.splits > 1 && (shp.splitk_ws == nullptr || shp.tickets == nullptr)) {
     set_last_error("split-K with a full-sum epilogue needs a fix-up workspace and tickets");
     return 1;
@@ -54,22 +54,51 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const Opera
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  DVAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, wa, wb, shp, ep));
+  return 0;
+}
+
+// CTA-pair launch (tcgen05 cta_group::2): clusters of two consecutive M tiles; every CTA stages half of the B tile, so the
+// ring is as deep as 227 KB allow.  The B tensor map of a K-major operand must have been encoded with BN / 2 rows per box.
+template <int BN, bool A_MN, bool B_MN, int EB, class Epi>
+static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const OperandWalk& wa, const OperandWalk& wb,
+                            const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream) {
+  constexpr int STAGE = 128 * 128 + BN * 128 / 2;
+  constexpr int ST_FIT = (227 * 1024 - 1280) / STAGE;
+  constexpr int ST = ST_FIT > 10 ? 10 : ST_FIT;
+  constexpr int smem = ST * STAGE + 1024 + 256;
+  if ((Epi::kFixup && shp.splits > 1) || grid.x % 2 != 0) {
+    set_last_error("CTA-pair GEMM needs an even number of M tiles and no fix-up split-K");
+    return 1;
+  }
+  auto kern = tc_gemm_kernel<BN, ST, A_MN, B_MN, EB, Epi, 1, 2>;
+  static bool configured = false;
+  if (!configured) {
+    DVAE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
+  static const int use_pdl = env_int("DVAE_PDL", 1);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 2;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
   if (use_pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  if (cluster > 1) {   // CTAs of a cluster = consecutive M tiles; they share (multicast) the B operand
-    if (MT != 1 || grid.x % cluster != 0 || (Epi::kFixup && shp.splits > 1)) {
-      set_last_error("cluster launch needs single-accumulator tiles, grid.x divisible by the cluster size and no fix-up split-K");
-      return 1;
-    }
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = cluster;
-    attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = 1;
     ++na;
   }
   cfg.attrs = attr;
@@ -489,16 +518,14 @@ static int lstm_bwd_splits(int rows, int H, int D, int elem_bytes) {
   return s < 1 ? 1 : s;
 }
 
-// Cluster size of the recurrence step kernels (CTAs of a cluster = consecutive row tiles sharing the weight tile by TMA
-// multicast): DVAE_LSTM_CLUSTER = 1 | 2 | 4, reduced until it divides the number of row tiles and the B tile's parts.
-// Default 1: measured on B200 (profiles/r01_lstm_cluster_multicast.txt) multicast makes the step SLOWER (main loop
-// 8.45 -> 9.7 us at H = 1024): the main loop is bound by bytes in flight per SM (4 stages x 48 KB against ~1.7 us of loaded
-// L2 latency), not by L2 bandwidth, and multicast only couples the two pipelines.  Kept as a tested option.
-static int lstm_cluster(int row_tiles, int b_parts) {
-  static const int want = env_int("DVAE_LSTM_CLUSTER", 1);
-  int c = (want == 2 || want == 4) ? want : 1;
-  while (c > 1 && (row_tiles % c != 0 || b_parts % c != 0)) c >>= 1;
-  return c;
+// CTA-pair MMA (cta_group::2) for the recurrence step kernels: DVAE_LSTM_PAIR=1, when the row tiles pair up.  Default
+// off: measured on B200 (profiles/r01_lstm_cluster_multicast.txt) the pair shortens the backward step's main loop
+// (8.96 -> 7.68 us at H = 1024) but lengthens the forward's (8.45 -> 10.75 us), and a cluster launch per time step adds
+// ~1.5 us of set-up (cluster scheduling + two cluster barriers), so a step is 0.1 - 2.5 us slower end to end.
+// (An earlier experiment shared the weight tile by plain TMA multicast across 1-SM MMAs instead; also slower.)
+static bool lstm_pair(int row_tiles) {
+  static const int want = env_int("DVAE_LSTM_PAIR", 0);
+  return want != 0 && row_tiles % 2 == 0;
 }
 
 template <typename AT>
@@ -511,13 +538,13 @@ static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows
   CUtensorMap ta, tb;
   if (int e = encode_map3(&ta, h_all, EB, (uint64_t)D * H, T, rows, (uint64_t)D * H * EB, (uint64_t)T * D * H * EB, BK, 1, 128))
     return e;
-  // clusters of consecutive row tiles share (multicast) the W_hh tile: each CTA fetches BN / cluster of its rows
-  const int cluster = lstm_cluster(ceil_div(rows, 128), BN >= 128 ? BN / 64 : 1);
-  if (int e = encode_map3(&tb, whh_p, EB, H, 4 * H, D, (uint64_t)H * EB, (uint64_t)4 * H * H * EB, BK, BN / cluster, 1)) return e;
+  // CTA pairs (cta_group::2): each CTA of a pair of consecutive row tiles stages half of the W_hh tile
+  const bool pair = lstm_pair(ceil_div(rows, 128)) && BN >= 128;
+  if (int e = encode_map3(&tb, whh_p, EB, H, 4 * H, D, (uint64_t)H * EB, (uint64_t)4 * H * H * EB, BK, pair ? BN / 2 : BN, 1)) return e;
   const long ldx = (long)T * D * 4 * H, ldc = (long)T * D * H;
   // staged (TMA) stores of gates / c / h for the wide tiles; DVAE_LSTM_FWD_TMA=0 keeps the direct row-per-lane stores
   static const int tma_env = env_int("DVAE_LSTM_FWD_TMA", 1);
-  const bool staged = tma_env != 0 && BN >= 128;
+  const bool staged = (tma_env != 0 && BN >= 128) || pair;
   CUtensorMap tg, tc, th;
   if (staged) {
     if (int e = encode_map3(&tg, xg, EB, (uint64_t)D * 4 * H, T, rows, (uint64_t)D * 4 * H * EB, (uint64_t)T * D * 4 * H * EB, BK, 1, 128))
@@ -555,14 +582,18 @@ static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows
       fill(ep);
       ep.tm_g = tg; ep.tm_c = tc; ep.tm_h = th;
       ep.t[0] = tf; ep.t[1] = tr; ep.H = H;
-      e = (BN == 256) ? launch_gemm<256, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st, cluster)
-                      : launch_gemm<128, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st, cluster);
+      if (pair)
+        e = (BN == 256) ? launch_gemm_pair<256, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                        : launch_gemm_pair<128, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      else
+        e = (BN == 256) ? launch_gemm<256, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                        : launch_gemm<128, false, false, EB, EpiLstmFwdTma<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
     } else {
       typename EpiLstmFwd<AT>::Params ep;
       fill(ep);
-      e = (BN == 256)   ? launch_gemm<256, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st, cluster)
-          : (BN == 128) ? launch_gemm<128, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st, cluster)
-                        : launch_gemm<64, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st, cluster);
+      e = (BN == 256)   ? launch_gemm<256, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+          : (BN == 128) ? launch_gemm<128, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
+                        : launch_gemm<64, false, false, EB, EpiLstmFwd<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
     }
     if (e) return e;
   }
@@ -678,9 +709,13 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
           GemmShape shp{rows, H, 4 * H / BK, 4 * H / BK, rsplits, nullptr, nullptr};
           EpiReduceTma::Params ep{trec};
           dim3 grid(ceil_div(rows, 128), H / RBN, D * rsplits);
-          const int cluster = lstm_cluster(ceil_div(rows, 128), RBN * EB / 128);
-          int e = (RBN == 256) ? launch_gemm<256, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st, cluster)
-                               : launch_gemm<128, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st, cluster);
+          int e;
+          if (lstm_pair(ceil_div(rows, 128)))
+            e = (RBN == 256) ? launch_gemm_pair<256, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st)
+                             : launch_gemm_pair<128, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st);
+          else
+            e = (RBN == 256) ? launch_gemm<256, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st)
+                             : launch_gemm<128, false, true, EB, EpiReduceTma>(ta, tb, wa, wb, shp, ep, grid, st);
           if (e) return e;
         } else {
           wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN; wb.per_z[2] = 1;

@@ -149,14 +149,16 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// TMA load delivered to the same shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier (same
-// offset) receives the complete_tx for the bytes written into that CTA
-__device__ __forceinline__ void tma_load_3d_multicast(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
-                                                      int c2, uint16_t cta_mask) {
+// CTA-pair (cta_group::2) TMA load: the bytes land in THIS CTA's shared memory, the complete_tx is delivered to the
+// mbarrier at the same offset in the pair's leader (even-ranked) CTA -- bit 24 of a shared-window address selects the CTA
+// of the pair, clearing it addresses the leader.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                 int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, "
-      "%5}], [%2], %6;" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 
@@ -198,12 +200,40 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// same, arriving on the barrier at this offset in every CTA of cta_mask (operand slots filled by multicast loads are
-// released cluster-wide)
-__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(cta_mask)
+// ---- CTA pair (cta_group::2): one MMA spans two SMs (M = 256: 128 accumulator rows in each CTA's TMEM); each CTA keeps
+// its own A rows and HALF of the B tile in shared memory.  Issued by the leader CTA only.
+template <int ELEM_BYTES>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if constexpr (ELEM_BYTES == 2) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// arrives (once all previously issued pair MMAs have completed) on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(static_cast<uint16_t>(3))
                : "memory");
+}
+// both CTAs of the pair execute these with the same warp and the same shared-memory slot offset
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
 // TMEM -> registers: this warp's 32 lanes (rows), N consecutive 32-bit columns each.

@@ -120,26 +120,36 @@ constexpr int gemm_smem_bytes() {
 // M_TILES = 2: the CTA owns 256 output rows as two 128-row accumulators that share every B stage.  ncu shows the
 // 128 x 256 tile already pulls ~11.6 TB/s from L2 (profiles/r01_ncu_gemm_v1.txt), i.e. the big GEMMs are bound by L2->SM
 // bandwidth, not by the tensor pipe; the 256 x 256 tile moves 1/3 fewer operand bytes per FLOP.
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi, int M_TILES = 1>
-__global__ void __launch_bounds__(kGemmThreads, (Epi::kCtasPerSm == 2 && STAGES * (M_TILES * kBlockM + BLOCK_N) * kSwizzleRow <= 100 * 1024) ? 2 : 1)
+//
+// CTA_GROUP = 2: CTA pairs (clusters of two consecutive M tiles) run the 256 x BLOCK_N MMA of tcgen05 cta_group::2.  Each
+// CTA stages its own 128 A rows and only HALF of the B tile (the tensor core reads both halves across the pair), so a
+// stage is 16 + BLOCK_N/2 * 128 bytes and 227 KB hold 7 stages instead of 4.  That is what the recurrence step GEMMs
+// need: their main loop is bound by the operand bytes one SM can keep in flight against ~1.7 us of loaded L2 latency,
+// and the pair MMA needs 1/3 fewer bytes per FLOP per SM.  Both CTAs run a TMA producer (complete_tx goes to the leader's
+// full barrier), only the leader (even rank) issues MMAs; its commits arrive on the empty / accumulator barriers of both.
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi, int M_TILES = 1, int CTA_GROUP = 1>
+__global__ void __launch_bounds__(kGemmThreads, (CTA_GROUP == 1 && Epi::kCtasPerSm == 2 && STAGES * (M_TILES * kBlockM + BLOCK_N) * kSwizzleRow <= 100 * 1024) ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const OperandWalk wa, const OperandWalk wb, const GemmShape shp,
                const __grid_constant__ typename Epi::Params ep) {
+  static_assert(CTA_GROUP == 1 || (CTA_GROUP == 2 && M_TILES == 1), "CTA pairs use the single-accumulator tile");
+  constexpr bool PAIR = CTA_GROUP == 2;
   constexpr int BLOCK_K = kSwizzleRow / ELEM_BYTES;  // 64 bf16 / 32 tf32
   constexpr int UMMA_K = 32 / ELEM_BYTES;            // 16 / 8
   constexpr int TILE_A = kBlockM * kSwizzleRow;      // one 128-row A tile
   constexpr int STAGE_A = M_TILES * TILE_A;
   constexpr int TMEM_COLS = M_TILES * BLOCK_N;
   static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
-  constexpr int STAGE_B = BLOCK_N * kSwizzleRow;
+  constexpr int STAGE_B = BLOCK_N * kSwizzleRow / CTA_GROUP;   // a pair CTA holds half of the B tile
   constexpr int A_BOXES = A_MN ? (kBlockM * ELEM_BYTES / kSwizzleRow) : 1;
-  constexpr int B_BOXES = B_MN ? (BLOCK_N * ELEM_BYTES / kSwizzleRow) : 1;
+  constexpr int B_BOXES = B_MN ? (BLOCK_N * ELEM_BYTES / kSwizzleRow / CTA_GROUP) : 1;   // boxes this CTA loads
+  static_assert(B_BOXES >= 1, "B tile too narrow to split over a CTA pair");
   constexpr int MN_BOX_BYTES = BLOCK_K * kSwizzleRow;  // one MN-major box: BLOCK_K rows of 128 B
   constexpr int A_BOX_BYTES = A_MN ? MN_BOX_BYTES : TILE_A;
   constexpr int B_BOX_BYTES = B_MN ? MN_BOX_BYTES : STAGE_B;
   constexpr uint32_t ADV_A = (A_MN ? UMMA_K * kSwizzleRow : 32) >> 4;  // descriptor advance per MMA (16 B units)
   constexpr uint32_t ADV_B = (B_MN ? UMMA_K * kSwizzleRow : 32) >> 4;
-  constexpr uint32_t IDESC = instr_desc<ELEM_BYTES, BLOCK_N, A_MN, B_MN>();
+  constexpr uint32_t IDESC = instr_desc<ELEM_BYTES, BLOCK_N, A_MN, B_MN, kBlockM * CTA_GROUP>();
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "TMEM allocation must be a power of two");
 
   extern __shared__ uint8_t smem_raw[];
@@ -163,31 +173,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_begin = split * kb_chunk;
   const int kb_end = min(shp.num_kb, kb_begin + kb_chunk);
   const int num_local = max(0, kb_end - kb_begin);
+  const int cr = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;   // rank in the pair; 0 = leader
 
-  // Cluster of cs CTAs along x (consecutive M tiles, same N tile, same batch / split): the B tile is identical for all
-  // of them, so each CTA fetches 1/cs of it and multicasts that share to every CTA of the cluster.  The step kernels of
-  // the LSTM recurrence are bound by L2->SM operand traffic (~11.6 TB/s measured); this removes (cs-1)/cs of the B bytes.
-  // An operand slot may only be refilled once ALL CTAs of the cluster have consumed it: the MMA warps commit to the
-  // empty barrier of every CTA (count cs).
-  const uint32_t cs = ptx::cluster_nctarank(), cr = ptx::cluster_ctarank();
-  const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
   if (threadIdx.x == 0) phase_stamp(0);
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar(s), 1);
-      ptx::mbar_init(empty_bar(s), cs);
+      ptx::mbar_init(empty_bar(s), 1);
     }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) {
+      ptx::tmem_alloc_pair(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  if (cs > 1) ptx::cluster_sync();   // peers must see initialised barriers before their multicasts / commits arrive
+  if constexpr (PAIR) ptx::cluster_sync();   // the peer must see initialised barriers before its loads / commits arrive
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -197,14 +206,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) phase_stamp(1);
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (in a pair: both CTAs, own A rows + own B half)
     if (lane == 0) {
       for (int it = 0; it < num_local; ++it) {
         const int kb = kb_begin + it;
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-        ptx::mbar_expect_tx(full_bar(s), STAGE_A + STAGE_B);
+        if (!PAIR || cr == 0) ptx::mbar_expect_tx(full_bar(s), CTA_GROUP * (STAGE_A + STAGE_B));   // bytes of both CTAs
         const int tap = kb / shp.kb_per_tap;
         const int j = kb - tap * shp.kb_per_tap;
         const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
@@ -218,72 +227,66 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int d = 0; d < 3; ++d)
               c[d] = wa.base[d] + j * wa.per_j[d] + tap * wa.per_tap[d] + i * wa.per_box[d] +
                      (tile_m * M_TILES + mt) * wa.per_tile[d] + zb * wa.per_z[d];
-            ptx::tma_load_3d(sa + mt * TILE_A + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
+            if constexpr (PAIR) ptx::tma_load_3d_pair(sa + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
+            else ptx::tma_load_3d(sa + mt * TILE_A + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
           }
         }
-        if (cs == 1) {
 #pragma unroll
-          for (int i = 0; i < B_BOXES; ++i) {
-            int c[3];
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-              c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + i * wb.per_box[d] + tile_n * wb.per_tile[d] +
-                     zb * wb.per_z[d];
-            ptx::tma_load_3d(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
-          }
-        } else if constexpr (B_MN) {   // my share = B_BOXES / cs of the MN-major boxes
-          const int per = B_BOXES / static_cast<int>(cs);
-          for (int i = static_cast<int>(cr) * per; i < (static_cast<int>(cr) + 1) * per; ++i) {
-            int c[3];
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-              c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + i * wb.per_box[d] + tile_n * wb.per_tile[d] +
-                     zb * wb.per_z[d];
-            ptx::tma_load_3d_multicast(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2], cmask);
-          }
-        } else {                       // my share = BLOCK_N / cs rows of the K-major tile (the host encoded that box height)
+        for (int i = 0; i < B_BOXES; ++i) {
           int c[3];
 #pragma unroll
-          for (int d = 0; d < 3; ++d)
-            c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + tile_n * wb.per_tile[d] +
-                   static_cast<int>(cr) * (wb.per_tile[d] / static_cast<int>(cs)) + zb * wb.per_z[d];
-          ptx::tma_load_3d_multicast(sb + cr * (STAGE_B / cs), &tmB, full_bar(s), c[0], c[1], c[2], cmask);
+          for (int d = 0; d < 3; ++d) {
+            c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + (cr * B_BOXES + i) * wb.per_box[d] +
+                   tile_n * wb.per_tile[d] + zb * wb.per_z[d];
+            if (PAIR && !B_MN) c[d] += cr * (wb.per_tile[d] / 2);   // K-major: second half of the tile's rows
+          }
+          if constexpr (PAIR) ptx::tma_load_3d_pair(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
+          else ptx::tma_load_3d(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
         }
       }
       phase_stamp(2);
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    for (int it = 0; it < num_local; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      ptx::mbar_wait(full_bar(s), ph);
-      ptx::tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
-        const uint32_t sb = sa + STAGE_A;
-        // K-major: 8-row x 128 B swizzle atoms, 1024 B apart.  MN-major: atoms of (128 B along MN) x (8 k-rows),
-        // next atom along MN one TMA box further (LBO), next k-group SBO further.  32-bit MN-major operands
-        // only exist in the 32-byte-atom swizzle (4 k-rows per atom): layout type 1, SBO 512.
-        constexpr uint32_t MN_LAYOUT = (ELEM_BYTES == 4) ? 1u : 2u;
-        constexpr uint32_t MN_SBO = (ELEM_BYTES == 4) ? 512u : 1024u;
-        const uint64_t bdesc = B_MN ? smem_desc(sb, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sb, 16, 1024, 2);
+    // ------------------------------------------------------------ MMA issuer (in a pair: the leader only)
+    if (!PAIR || cr == 0) {
+      for (int it = 0; it < num_local; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        ptx::mbar_wait(full_bar(s), ph);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
+          const uint32_t sb = sa + STAGE_A;
+          // K-major: 8-row x 128 B swizzle atoms, 1024 B apart.  MN-major: atoms of (128 B along MN) x (8 k-rows),
+          // next atom along MN one TMA box further (LBO), next k-group SBO further.  32-bit MN-major operands
+          // only exist in the 32-byte-atom swizzle (4 k-rows per atom): layout type 1, SBO 512.
+          constexpr uint32_t MN_LAYOUT = (ELEM_BYTES == 4) ? 1u : 2u;
+          constexpr uint32_t MN_SBO = (ELEM_BYTES == 4) ? 512u : 1024u;
+          const uint64_t bdesc = B_MN ? smem_desc(sb, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sb, 16, 1024, 2);
 #pragma unroll
-        for (int mt = 0; mt < M_TILES; ++mt) {
-          const uint32_t sam = sa + mt * TILE_A;
-          const uint64_t adesc = A_MN ? smem_desc(sam, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sam, 16, 1024, 2);
+          for (int mt = 0; mt < M_TILES; ++mt) {
+            const uint32_t sam = sa + mt * TILE_A;
+            const uint64_t adesc = A_MN ? smem_desc(sam, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sam, 16, 1024, 2);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            ptx::umma<ELEM_BYTES>(tmem_base + mt * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
-                                  (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              if constexpr (PAIR)
+                ptx::umma_pair<ELEM_BYTES>(tmem_base, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+              else
+                ptx::umma<ELEM_BYTES>(tmem_base + mt * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
+                                      (it > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          if constexpr (PAIR) ptx::umma_commit_pair(empty_bar(s));   // frees the slot in both CTAs
+          else ptx::umma_commit(empty_bar(s));                        // frees the smem slot once these MMAs retire
         }
-        if (cs > 1) ptx::umma_commit_multicast(empty_bar(s), cmask);   // the slot is shared cluster-wide
-        else ptx::umma_commit(empty_bar(s));                             // frees the smem slot once these MMAs retire
+        __syncwarp();
+      }
+      if (num_local > 0 && lane == 0) {
+        if constexpr (PAIR) ptx::umma_commit_pair(tmem_full_bar);
+        else ptx::umma_commit(tmem_full_bar);
       }
       __syncwarp();
     }
-    if (num_local > 0 && lane == 0) ptx::umma_commit(tmem_full_bar);
-    __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;            // TMEM lane quarter this warp may read
@@ -360,11 +363,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 64) phase_stamp(4);
     ptx::tc_fence_before();
   }
-  if (cs > 1) ptx::cluster_sync();   // my commits arrive on the peers' barriers: nobody leaves before everybody is done
+  if constexpr (PAIR) ptx::cluster_sync();   // the leader's commits / MMAs touch the peer: nobody leaves before both are done
   else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
