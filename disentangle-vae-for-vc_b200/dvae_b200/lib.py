@@ -69,6 +69,8 @@ _SIGNATURES = {
     "dvae_group_finalize": [_i, _p, _p, _p, _p, _p, _p, _l, _l, _i, _p],
     "dvae_group_pog_bwd": [_p] * 7 + [_l, _i, _p],
     "dvae_group_reparam": [_p] * 5 + [_l, _i, _p],
+    # optimizer
+    "dvae_adam_step": [_p] * 7 + [_i, _i, _f, _f, _f, _f, _l, _p],
 }
 _OPTIONAL = {}
 

@@ -21,6 +21,7 @@ import torch.nn as nn
 from torch import optim
 
 from dvae_b200 import lib, ops
+from dvae_b200 import optim as fused_optim
 from dvae_b200.engine import Engine, PreparedWeights
 from model.variational_base_vae import VariationalBaseModelVAE
 
@@ -289,7 +290,7 @@ class ConvolutionalMulVAE(VariationalBaseModelVAE):
         self.style_cof = style_cof
         self.model = DisentangledVAE(latent_dim=self.latent_dim, beta=0.1, batch_size=batch_size,
                                      speaker_size=speaker_size).to(device)
-        self.optimizer = optim.Adam(self.model.parameters(), lr=self.lr)
+        self.optimizer = fused_optim.Adam(self.model.parameters(), lr=self.lr)   # torch.optim.Adam semantics, one launch
         self.train_losses = []
         self.test_losses = []
 

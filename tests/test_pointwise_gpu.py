@@ -213,3 +213,34 @@ def test_group_ops_large_and_backward(D):
     acc_g, _ = ops.group_accumulate(ops.MODE_RAW, d1, d2, gid_d, 300)
     dmu, dlv = ops.group_pog_bwd(mu_d, lv_d, gid_d, acc, acc_g)
     assert torch.allclose(dmu, mt.grad, atol=1e-4, rtol=1e-4) and torch.allclose(dlv, lt.grad, atol=1e-4, rtol=1e-4)
+
+
+def test_fused_adam_matches_torch_adam():
+    """dvae_b200.optim.Adam = torch.optim.Adam (reference model/disentangled_vae.py:304) step for step, including odd sizes,
+    unaligned views and state_dict interchange."""
+    from dvae_b200.optim import Adam
+    torch.manual_seed(3)
+    shapes = [(512, 80, 5), (80,), (4096, 1024), (3,), (1, 1), (2049, 7)]
+    flat = torch.randn(10_000, device="cuda")
+    ref_p = [torch.randn(s, device="cuda") for s in shapes] + [flat[1:1 + 333].clone()]
+    our_p = [p.clone().requires_grad_(True) for p in ref_p]
+    ref_p = [p.requires_grad_(True) for p in ref_p]
+    ref, our = torch.optim.Adam(ref_p, lr=1e-3), Adam(our_p, lr=1e-3)
+    for step in range(5):
+        for a, b in zip(ref_p, our_p):
+            g = torch.randn_like(a) * (10.0 ** (step - 2))
+            a.grad, b.grad = g.clone(), g.clone()
+        ref.step()
+        our.step()
+        for a, b in zip(ref_p, our_p):
+            assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (step, a.shape, (a - b).abs().max().item())
+    sd = our.state_dict()
+    ref2 = torch.optim.Adam([p.detach().clone().requires_grad_(True) for p in our_p], lr=1e-3)
+    ref2.load_state_dict(sd)                      # same state layout: step / exp_avg / exp_avg_sq
+    assert float(ref2.state[ref2.param_groups[0]["params"][0]]["step"]) == 5.0
+    for a, b in zip(ref.state_dict()["state"].values(), sd["state"].values()):
+        # one-ulp differences of the lerp / addcmul forms, relative to the tensor's scale (values near zero cancel)
+        assert torch.allclose(a["exp_avg"], b["exp_avg"], rtol=1e-5, atol=1e-6 * a["exp_avg"].abs().max().item())
+        assert torch.allclose(a["exp_avg_sq"], b["exp_avg_sq"], rtol=1e-5, atol=1e-6 * a["exp_avg_sq"].abs().max().item())
+    with pytest.raises(NotImplementedError):
+        Adam(our_p, weight_decay=0.1)
