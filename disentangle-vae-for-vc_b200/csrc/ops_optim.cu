@@ -21,7 +21,7 @@ constexpr int kAdamThreads = 256;
 __global__ void __launch_bounds__(kAdamThreads)
 adam_multi_kernel(float* const* __restrict__ ps, const float* const* __restrict__ gs, float* const* __restrict__ ms,
                   float* const* __restrict__ vs, const long* __restrict__ sizes, const int* __restrict__ blk_tensor,
-                  const long* __restrict__ blk_off, int chunk, float beta1, float beta2, float eps, float step_size,
+                  const long* __restrict__ blk_off, int chunk, float w1, float beta2, float w2, float eps, float step_size,
                   float inv_bc2_sqrt) {
   const int t = blk_tensor[blockIdx.x];
   const long off = blk_off[blockIdx.x];
@@ -30,7 +30,6 @@ adam_multi_kernel(float* const* __restrict__ ps, const float* const* __restrict_
   const float* __restrict__ g = gs[t] + off;
   float* __restrict__ m = ms[t] + off;
   float* __restrict__ v = vs[t] + off;
-  const float w1 = 1.f - beta1, w2 = 1.f - beta2;
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
     mm = mm + w1 * (gg - mm);
     vv = vv * beta2 + w2 * gg * gg;
@@ -80,19 +79,21 @@ extern "C" {
 // One Adam step for every tensor in the tables (all arrays are DEVICE memory; `step` is the 1-based step count the bias
 // corrections use).  blk_tensor / blk_off: for each block, which tensor and which element offset its chunk starts at.
 int dvae_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                   const long* sizes, const int* blk_tensor, const long* blk_off, int num_blocks, int chunk, float lr,
-                   float beta1, float beta2, float eps, long step, void* stream) {
+                   const long* sizes, const int* blk_tensor, const long* blk_off, int num_blocks, int chunk, double lr,
+                   double beta1, double beta2, double eps, long step, void* stream) {
   using namespace dvae;
   DVAE_REQUIRE(chunk > 0 && chunk % 4 == 0, "chunk must be a positive multiple of 4");
   DVAE_REQUIRE(step >= 1, "step counts from 1");
   if (num_blocks <= 0) return 0;
-  // bias corrections in double like torch's Python scalars, then rounded once
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
-  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  // Hyper-parameters are doubles, like torch's Python scalars: 1 - beta and the bias corrections are formed in double and
+  // rounded to fp32 once (1.f - 0.999f differs from float(1 - 0.999) by 1.3e-5 relative -- visible in exp_avg_sq).
+  const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+  const float step_size = static_cast<float>(lr / bc1);
   const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
   adam_multi_kernel<<<num_blocks, kAdamThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      params, grads, exp_avg, exp_avg_sq, sizes, blk_tensor, blk_off, chunk, beta1, beta2, eps, step_size, inv_bc2_sqrt);
+      params, grads, exp_avg, exp_avg_sq, sizes, blk_tensor, blk_off, chunk, static_cast<float>(1.0 - beta1),
+      static_cast<float>(beta2), static_cast<float>(1.0 - beta2), static_cast<float>(eps), step_size, inv_bc2_sqrt);
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -25,7 +25,7 @@ if not os.path.exists(LIB_PATH):
 _lib = C.CDLL(LIB_PATH)
 _lib.dvae_last_error.restype = C.c_char_p
 
-_p, _i, _l, _f = C.c_void_p, C.c_int, C.c_long, C.c_float
+_p, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_double
 
 # name -> argtypes (all return int)
 _SIGNATURES = {
@@ -70,7 +70,7 @@ _SIGNATURES = {
     "dvae_group_pog_bwd": [_p] * 7 + [_l, _i, _p],
     "dvae_group_reparam": [_p] * 5 + [_l, _i, _p],
     # optimizer
-    "dvae_adam_step": [_p] * 7 + [_i, _i, _f, _f, _f, _f, _l, _p],
+    "dvae_adam_step": [_p] * 7 + [_i, _i, _d, _d, _d, _d, _l, _p],
 }
 _OPTIONAL = {}
 

@@ -117,8 +117,8 @@ int dvae_group_reparam(const float* mu, const float* logvar, const int* gid, con
  *      for all tensors; every pointer is DEVICE memory: arrays of tensor base pointers / sizes, and for each block the
  *      tensor index and element offset of its chunk.  `step` counts from 1 (bias corrections). */
 int dvae_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
-                   const long* sizes, const int* blk_tensor, const long* blk_off, int num_blocks, int chunk, float lr,
-                   float beta1, float beta2, float eps, long step, void* stream);
+                   const long* sizes, const int* blk_tensor, const long* blk_off, int num_blocks, int chunk, double lr,
+                   double beta1, double beta2, double eps, long step, void* stream);
 
 #ifdef __cplusplus
 }

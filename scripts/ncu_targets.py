@@ -21,5 +21,11 @@ whh = (torch.randn(1, 4 * H, H, device="cuda") / H ** 0.5).to(torch.bfloat16)
 h, c = ops.lstm_fwd(dt, xg, whh, H, 1)               # launches 2..5: LSTM fwd steps (step 0 has no MMA)
 dh = torch.randn(rows, T, H, device="cuda").to(torch.bfloat16)
 ops.lstm_bwd(dt, dh, xg, c, whh, H, 1)               # launches 6..9: LSTM bwd steps
+H2 = 64
+xg2 = torch.randn(rows, 64, 2 * 4 * H2, device="cuda").to(torch.bfloat16)
+whh2 = (torch.randn(2, 4 * H2, H2, device="cuda") / H2 ** 0.5).to(torch.bfloat16)
+h2, c2 = ops.lstm_fwd(dt, xg2, whh2, H2, 2)          # sequence-resident BiLSTM forward (one launch, 64 steps)
+dh2 = torch.randn(rows, 64, 2 * H2, device="cuda").to(torch.bfloat16)
+ops.lstm_bwd(dt, dh2, xg2, c2, whh2, H2, 2)          # sequence-resident backward
 torch.cuda.synchronize()
 print("done")
