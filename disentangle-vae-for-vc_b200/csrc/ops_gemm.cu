@@ -315,7 +315,10 @@ static int linear_wgrad_t(const AT* dy, long lddy, const AT* x, long ldx, float*
   constexpr int EB = sizeof(AT);
   constexpr int BK = 128 / EB;
   CUtensorMap ta, tb;
-  const int BN = K <= 64 ? 64 : 128;
+  // wide (128 x 256) persistent tiles with a wave-aware split-K when the launch may take whole SMs (see conv5_wgrad_t)
+  static const int wide_env = env_int("DVAE_WGRAD_WIDE", 1);
+  const bool wide = wide_env != 0 && !g_background && K % 256 == 0;
+  const int BN = wide ? 256 : (K <= 64 ? 64 : 128);
   if (int e = encode_map3(&ta, dy, EB, N, M, 1, lddy * EB, (uint64_t)M * lddy * EB, BK, BK, 1, true)) return e;
   if (int e = encode_map3(&tb, x, EB, K, M, 1, ldx * EB, (uint64_t)M * ldx * EB, BK, BK, 1, true)) return e;
   OperandWalk wa = zero_walk(), wb = zero_walk();
@@ -323,9 +326,15 @@ static int linear_wgrad_t(const AT* dy, long lddy, const AT* x, long ldx, float*
   wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN;
   const int num_kb = ceil_div(M, BK);
   const int tiles = ceil_div(N, 128) * ceil_div(K, BN);
-  GemmShape shp{N, K, num_kb, num_kb, pick_splits(tiles, num_kb)};
+  int splits = pick_splits(tiles, num_kb);
+  {
+    dim3 probe(ceil_div(N, 128), ceil_div(K, BN), splits);
+    if (want_persistent(probe) || wide) splits = pick_splits_persistent(tiles, num_kb);
+  }
+  GemmShape shp{N, K, num_kb, num_kb, splits};
   EpiAtomic::Params ep{dw, lddw, 0};
   dim3 grid(ceil_div(N, 128), ceil_div(K, BN), shp.splits);
+  if (wide) return launch_gemm_persistent<256, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
   if (want_persistent(grid)) {
     if (BN == 64) return launch_gemm_persistent<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
     return launch_gemm_persistent<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -797,16 +806,19 @@ static int lstm_wgrad_hh_t(const AT* da_all, const AT* h_all, float* dwhh, int r
     return e;
   if (int e = encode_map3(&tb, h_all, EB, (uint64_t)D * H, T, rows, (uint64_t)D * H * EB, (uint64_t)T * D * H * EB, BK, BK, 1, true))
     return e;
-  const int BN = H <= 64 ? 64 : 128;
+  static const int wide_env = env_int("DVAE_WGRAD_WIDE", 1);
+  const bool wide = wide_env != 0 && !g_background && H % 256 == 0;
+  const int BN = wide ? 256 : (H <= 64 ? 64 : 128);
   OperandWalk wa = zero_walk(), wb = zero_walk();
   wa.per_j[1] = BK; wa.per_tap[2] = 1; wa.per_box[0] = BK; wa.per_tile[0] = 128; wa.per_z[0] = 4 * H;
   wb.base[1] = -1; wb.per_z[1] = 2; wb.per_z[0] = H; wb.per_j[1] = BK; wb.per_tap[2] = 1; wb.per_box[0] = BK;
   wb.per_tile[0] = BN;
   const int kpt = T / BK, num_kb = rows * kpt;
   const int tiles = ceil_div(4 * H, 128) * ceil_div(H, BN) * D;
-  GemmShape shp{4 * H, H, num_kb, kpt, pick_splits(tiles, num_kb)};
+  GemmShape shp{4 * H, H, num_kb, kpt, wide ? pick_splits_persistent(tiles, num_kb) : pick_splits(tiles, num_kb)};
   EpiAtomic::Params ep{dwhh, (long)H, (long)4 * H * H};
   dim3 grid(ceil_div(4 * H, 128), ceil_div(H, BN), D * shp.splits);
+  if (wide) return launch_gemm_persistent<256, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
   if (BN == 64) return launch_gemm<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
   return launch_gemm<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
 }
@@ -916,6 +928,11 @@ int dvae_lstm_launches(int H, int T, int backward) {
 
 // 1: subsequent GEMM launches from this host thread are background work (see want_persistent); 0: normal
 int dvae_set_background(int on) {
+  // DVAE_BACKGROUND=1 restores the small-footprint background kernels for side-stream GEMMs.  Default 0: since the LSTM step
+  // kernels own whole SMs (staging needs the full shared memory) there is little room to co-run; the wide persistent
+  // weight-gradient kernels (1050-1090 TFLOP/s vs 630) finish sooner even though they serialise (17.76 vs 18.02 ms/step).
+  static const int allow = env_int("DVAE_BACKGROUND", 0);
+  if (!allow) on = 0;
   g_background = on;
   return 0;
 }
