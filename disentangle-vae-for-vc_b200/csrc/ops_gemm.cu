@@ -21,6 +21,7 @@
 namespace dvae {
 
 static int env_int(const char* name, int dflt);
+static int g_background_flag();
 
 template <int BN>
 struct Stages {
@@ -109,17 +110,18 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const 
 
 // Persistent launch: one CTA per SM looping over all (m, n, batch x split) tiles.  Used when there are at least two
 // tiles per SM; smaller problems (LSTM steps, M = 1024 linears) keep the one-tile-per-CTA kernel.
-template <int BN, bool A_MN, bool B_MN, int EB, class Epi>
+template <int BN, bool A_MN, bool B_MN, int EB, class Epi, int CG = 1>
 static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const OperandWalk& wa, const OperandWalk& wb,
                                   const GemmShape& shp, const typename Epi::Params& ep, dim3 grid, cudaStream_t stream) {
   static_assert(BN <= 256, "");
   constexpr int STAGING = persistent_staging_bytes<Epi, BN>();
-  constexpr int ST_FULL = Stages<BN>::value + (BN == 128 ? 3 : (BN == 64 ? 4 : 0));   // 1 CTA / SM: use the whole 227 KB
-  constexpr int ST_FIT = (227 * 1024 - 1280 - STAGING) / ((128 + BN) * 128);        // what is left next to a staging tile
+  constexpr int STAGE = 128 * 128 + BN * 128 / CG;   // CG = 2 (CTA pairs): every CTA stages half of the B tile
+  constexpr int ST_FULL = CG == 2 ? 10 : Stages<BN>::value + (BN == 128 ? 3 : (BN == 64 ? 4 : 0));   // 1 CTA / SM: use the whole 227 KB
+  constexpr int ST_FIT = (227 * 1024 - 1280 - STAGING) / STAGE;        // what is left next to a staging tile
   constexpr int ST = ST_FIT < ST_FULL ? ST_FIT : ST_FULL;
   static_assert(ST >= 2, "persistent GEMM: ring too shallow");
-  auto kern = tc_gemm_persistent_kernel<BN, ST, A_MN, B_MN, EB, Epi>;
-  constexpr int smem = gemm_smem_bytes<BN, ST>() + STAGING;
+  auto kern = tc_gemm_persistent_kernel<BN, ST, A_MN, B_MN, EB, Epi, CG>;
+  constexpr int smem = ST * STAGE + 1024 + 256 + STAGING;
   static_assert(smem <= 227 * 1024, "persistent GEMM shared memory");
   static bool configured = false;
   if (!configured) {
@@ -133,24 +135,49 @@ static int launch_gemm_persistent(const CUtensorMap& ta, const CUtensorMap& tb, 
     set_last_error("persistent GEMM needs K > 0 and supports split-K only for accumulate epilogues");
     return 1;
   }
+  if (CG == 2 && tiles_m % 2 != 0) {
+    set_last_error("CTA-pair GEMM needs an even number of M tiles");
+    return 1;
+  }
   static const int use_pdl = env_int("DVAE_PDL", 1);
+  long ctas = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (CG == 2) ctas &= ~1L;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(num_tiles < num_sms() ? num_tiles : num_sms()));
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   DVAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, wa, wb, shp, ep, tiles_m, tiles_n, static_cast<int>(num_tiles)));
   return 0;
+}
+
+// CTA pairs (tcgen05 cta_group::2) for the persistent 128 x 256 kernels: DVAE_GEMM_PAIR (default 1) when the M tiles pair up.
+// K-major B operands must then be encoded with BN / 2 rows per TMA box.
+static bool gemm_pair(int tiles_m, int bn) {
+  static const int want = env_int("DVAE_GEMM_PAIR", 1);
+  return want != 0 && !g_background_flag() && bn == 256 && tiles_m % 2 == 0;
 }
 
 // Background mode (dvae_set_background): GEMMs that run on a side stream next to latency-critical kernels keep the
 // one-tile-per-CTA kernel (96 KB CTAs that co-reside with the LSTM step kernels) instead of taking whole SMs.
 static thread_local int g_background = 0;
+static int g_background_flag() { return g_background; }
 
 // DVAE_GEMM_PERSISTENT = 0 disables, 1 forces (tests); default: when the grid has >= 2 tiles per SM
 static bool want_persistent(dim3 grid) {
@@ -212,6 +239,16 @@ static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, A
       default: return launch_gemm<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
     }
   }
+  if (want_persistent(grid) && mt == 1 && gemm_pair(grid.x, BN)) {   // CTA pairs: half of the weight tile per CTA
+    if (int e = encode_map3(&tb, w, EB, K, N, 1, (uint64_t)K * EB, (uint64_t)N * K * EB, BK, BN / 2, 1)) return e;
+    if (use_tma_store(out, out_f32, nullptr, ldo, EB, shp.num_kb)) {
+      typename EpiStoreTma<AT>::Params et;
+      if (int e = encode_map3(&et.tm_out, out, EB, N, M, 1, (uint64_t)ldo * EB, (uint64_t)M * ldo * EB, BK, 128, 1)) return e;
+      et.bias = bias; et.relu = relu;
+      return launch_gemm_persistent<256, false, false, EB, EpiStoreTma<AT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
+    }
+    return launch_gemm_persistent<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+  }
   if (want_persistent(grid)) {
     if (use_tma_store(out, out_f32, nullptr, ldo, EB, shp.num_kb)) {
       typename EpiStoreTma<AT>::Params et;
@@ -259,6 +296,15 @@ static int linear_dgrad_t(const AT* dy, long lddy, const AT* w, AT* dx, float* d
       case 128: return launch_gemm<128, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
       default: return launch_gemm<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
     }
+  }
+  if (want_persistent(grid) && mt == 1 && gemm_pair(grid.x, BN)) {   // B is MN-major: the pair splits its boxes
+    if (use_tma_store(dx, dx_f32, relu_mask, ldx, EB, shp.num_kb)) {
+      typename EpiStoreTma<AT>::Params et;
+      if (int e = encode_map3(&et.tm_out, dx, EB, K, M, 1, (uint64_t)ldx * EB, (uint64_t)M * ldx * EB, BK, 128, 1)) return e;
+      et.bias = nullptr; et.relu = 0;
+      return launch_gemm_persistent<256, false, true, EB, EpiStoreTma<AT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
+    }
+    return launch_gemm_persistent<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   }
   if (want_persistent(grid)) {
     if (use_tma_store(dx, dx_f32, relu_mask, ldx, EB, shp.num_kb)) {
@@ -334,6 +380,7 @@ static int linear_wgrad_t(const AT* dy, long lddy, const AT* x, long ldx, float*
   GemmShape shp{N, K, num_kb, num_kb, splits};
   EpiAtomic::Params ep{dw, lddw, 0};
   dim3 grid(ceil_div(N, 128), ceil_div(K, BN), shp.splits);
+  if (wide && gemm_pair(grid.x, BN)) return launch_gemm_persistent<256, true, true, EB, EpiAtomic, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   if (wide) return launch_gemm_persistent<256, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
   if (want_persistent(grid)) {
     if (BN == 64) return launch_gemm_persistent<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -399,6 +446,21 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
       case 128: return launch_gemm<128, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
       default: return launch_gemm<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
     }
+  }
+  if (want_persistent(grid) && mt == 1 && gemm_pair(grid.x, BN)) {   // CTA pairs (cta_group::2)
+    if (!dgrad) {   // K-major filter tile: re-encode with half the rows per box
+      if (int e = encode_map3(&tb, wk, EB, Cin, 5, Cout, (uint64_t)Cin * EB, (uint64_t)5 * Cin * EB, BK, 1, BN / 2)) return e;
+    }
+    if (use_tma_store(y, y_f32, nullptr, Cn, EB, shp.num_kb)) {
+      typename EpiStoreTma<AT>::Params et;
+      if (int e = encode_map3(&et.tm_out, y, EB, Cn, (uint64_t)R * T, 1, (uint64_t)Cn * EB, (uint64_t)R * T * Cn * EB, BK, 128, 1))
+        return e;
+      et.bias = bias; et.relu = 0;
+      if (!dgrad) return launch_gemm_persistent<256, false, false, EB, EpiStoreTma<AT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
+      return launch_gemm_persistent<256, false, true, EB, EpiStoreTma<AT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
+    }
+    if (!dgrad) return launch_gemm_persistent<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+    return launch_gemm_persistent<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   }
   if (want_persistent(grid) && use_tma_store(y, y_f32, nullptr, Cn, EB, shp.num_kb)) {
     typename EpiStoreTma<AT>::Params et;
@@ -476,6 +538,7 @@ static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, in
   GemmShape shp{Cout, Cin, num_kb, kpt, splits};
   EpiAtomic::Params ep{dwk, (long)5 * Cin, (long)Cin};
   dim3 grid(ceil_div(Cout, 128), ceil_div(Cin, BN), 5 * shp.splits);
+  if (wide && gemm_pair(grid.x, BN)) return launch_gemm_persistent<256, true, true, EB, EpiAtomic, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   if (wide) return launch_gemm_persistent<256, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
   if (want_persistent(grid)) {
     if (BN == 64) return launch_gemm_persistent<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -818,6 +881,7 @@ static int lstm_wgrad_hh_t(const AT* da_all, const AT* h_all, float* dwhh, int r
   GemmShape shp{4 * H, H, num_kb, kpt, wide ? pick_splits_persistent(tiles, num_kb) : pick_splits(tiles, num_kb)};
   EpiAtomic::Params ep{dwhh, (long)H, (long)4 * H * H};
   dim3 grid(ceil_div(4 * H, 128), ceil_div(H, BN), D * shp.splits);
+  if (wide && gemm_pair(grid.x, BN)) return launch_gemm_persistent<256, true, true, EB, EpiAtomic, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   if (wide) return launch_gemm_persistent<256, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
   if (BN == 64) return launch_gemm<64, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
   return launch_gemm<128, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);

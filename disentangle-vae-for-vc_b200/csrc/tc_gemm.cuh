@@ -379,24 +379,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ncu on the one-tile-per-CTA kernel: tensor pipe active 52 %, of which the un-overlapped epilogue + tile start cost
 // ~30 % (profiles/r01_phase_timing_v2.txt).  Split-K is supported for accumulate-type epilogues only (no fix-up).
 // =====================================================================================
-template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi>
+// CTA_GROUP = 2: clusters of two CTAs walk the tile list together (pair tile = two consecutive M tiles of the same N tile,
+// batch and split) and run the 256 x BLOCK_N MMA of tcgen05 cta_group::2: each SM stages its own A rows and half of the B
+// tile, i.e. 2/3 of the operand bytes per FLOP -- the large contractions are bound by L2->SM traffic (~97 GB/s per SM,
+// profiles/r01_ncu_targets_v2.txt), not by the tensor pipe.  The leader issues the MMAs; its commits release the operand
+// slot and publish the accumulator in both CTAs; the epilogue warps of both CTAs hand the accumulator back by arriving
+// on the leader's barrier.
+template <int BLOCK_N, int STAGES, bool A_MN, bool B_MN, int ELEM_BYTES, class Epi, int CTA_GROUP = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const OperandWalk wa, const OperandWalk wb, const GemmShape shp,
                           const __grid_constant__ typename Epi::Params ep, const int tiles_m, const int tiles_n,
                           const int num_tiles) {
+  constexpr bool PAIR = CTA_GROUP == 2;
   constexpr int BLOCK_K = kSwizzleRow / ELEM_BYTES;
   constexpr int UMMA_K = 32 / ELEM_BYTES;
   constexpr int STAGE_A = kBlockM * kSwizzleRow;
-  constexpr int STAGE_B = BLOCK_N * kSwizzleRow;
+  constexpr int STAGE_B = BLOCK_N * kSwizzleRow / CTA_GROUP;
   constexpr int A_BOXES = A_MN ? (kBlockM * ELEM_BYTES / kSwizzleRow) : 1;
-  constexpr int B_BOXES = B_MN ? (BLOCK_N * ELEM_BYTES / kSwizzleRow) : 1;
+  constexpr int B_BOXES = B_MN ? (BLOCK_N * ELEM_BYTES / kSwizzleRow / CTA_GROUP) : 1;
+  static_assert(B_BOXES >= 1, "B tile too narrow to split over a CTA pair");
   constexpr int MN_BOX_BYTES = BLOCK_K * kSwizzleRow;
   constexpr int A_BOX_BYTES = A_MN ? MN_BOX_BYTES : STAGE_A;
   constexpr int B_BOX_BYTES = B_MN ? MN_BOX_BYTES : STAGE_B;
   constexpr uint32_t ADV_A = (A_MN ? UMMA_K * kSwizzleRow : 32) >> 4;
   constexpr uint32_t ADV_B = (B_MN ? UMMA_K * kSwizzleRow : 32) >> 4;
-  constexpr uint32_t IDESC = instr_desc<ELEM_BYTES, BLOCK_N, A_MN, B_MN>();
+  constexpr uint32_t IDESC = instr_desc<ELEM_BYTES, BLOCK_N, A_MN, B_MN, kBlockM * CTA_GROUP>();
   constexpr int TMEM_COLS = 2 * BLOCK_N;
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "two accumulators must fit TMEM");
   constexpr int RING = STAGES * (STAGE_A + STAGE_B);
@@ -417,6 +425,10 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kb_chunk = (shp.num_kb + shp.splits - 1) / shp.splits;
+  const int cr = PAIR ? static_cast<int>(ptx::cluster_ctarank()) : 0;   // rank in the pair; 0 = leader
+  // work items: tiles, or pair tiles (two consecutive M tiles); walkers: CTAs, or clusters
+  const int items = num_tiles / CTA_GROUP;
+  const int walker = blockIdx.x / CTA_GROUP, walkers = gridDim.x / CTA_GROUP;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -427,25 +439,32 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tmem_full_bar(a), 1);
-      ptx::mbar_init(tmem_empty_bar(a), kEpilogueThreads / 32);   // one arrival per epilogue warp
+      ptx::mbar_init(tmem_empty_bar(a), CTA_GROUP * kEpilogueThreads / 32);   // one arrival per epilogue warp (of both CTAs)
     }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (PAIR) {
+      ptx::tmem_alloc_pair(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
 
-  // tile -> (tile_m, tile_n, batch zb, split): m fastest, so CTAs running side by side share the B (weight) tile in L2
-  auto decode = [&](int tile, int& tm, int& tn, int& zb, int& split) {
-    tm = tile % tiles_m;
-    const int rest = tile / tiles_m;
+  // item -> (tile_m, tile_n, batch zb, split): m fastest, so CTAs running side by side share the B (weight) tile in L2
+  const int items_m = tiles_m / CTA_GROUP;
+  auto decode = [&](int item, int& tm, int& tn, int& zb, int& split) {
+    tm = (item % items_m) * CTA_GROUP + cr;
+    const int rest = item / items_m;
     tn = rest % tiles_n;
     const int zz = rest / tiles_n;
     zb = zz / shp.splits;
@@ -453,10 +472,10 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   };
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (pair: both CTAs, own A rows + own half of B)
     if (lane == 0) {
       int it = 0;   // running k-block counter of this CTA: the ring never drains between tiles
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = walker; tile < items; tile += walkers) {
         int tm, tn, zb, split;
         decode(tile, tm, tn, zb, split);
         const int kb_begin = split * kb_chunk;
@@ -465,7 +484,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(empty_bar(s), ph ^ 1u);
-          ptx::mbar_expect_tx(full_bar(s), STAGE_A + STAGE_B);
+          if (!PAIR || cr == 0) ptx::mbar_expect_tx(full_bar(s), CTA_GROUP * (STAGE_A + STAGE_B));
           const int tap = kb / shp.kb_per_tap;
           const int j = kb - tap * shp.kb_per_tap;
           const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
@@ -477,53 +496,68 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             for (int d = 0; d < 3; ++d)
               c[d] = wa.base[d] + j * wa.per_j[d] + tap * wa.per_tap[d] + i * wa.per_box[d] + tm * wa.per_tile[d] +
                      zb * wa.per_z[d];
-            ptx::tma_load_3d(sa + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
+            if constexpr (PAIR) ptx::tma_load_3d_pair(sa + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
+            else ptx::tma_load_3d(sa + i * A_BOX_BYTES, &tmA, full_bar(s), c[0], c[1], c[2]);
           }
 #pragma unroll
           for (int i = 0; i < B_BOXES; ++i) {
             int c[3];
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
-              c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + i * wb.per_box[d] + tn * wb.per_tile[d] +
-                     zb * wb.per_z[d];
-            ptx::tma_load_3d(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
+            for (int d = 0; d < 3; ++d) {
+              c[d] = wb.base[d] + j * wb.per_j[d] + tap * wb.per_tap[d] + (cr * B_BOXES + i) * wb.per_box[d] +
+                     tn * wb.per_tile[d] + zb * wb.per_z[d];
+              if (PAIR && !B_MN) c[d] += cr * (wb.per_tile[d] / 2);
+            }
+            if constexpr (PAIR) ptx::tma_load_3d_pair(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
+            else ptx::tma_load_3d(sb + i * B_BOX_BYTES, &tmB, full_bar(s), c[0], c[1], c[2]);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------ MMA issuer (pair: the leader only)
     constexpr uint32_t MN_LAYOUT = (ELEM_BYTES == 4) ? 1u : 2u;
     constexpr uint32_t MN_SBO = (ELEM_BYTES == 4) ? 512u : 1024u;
-    int it = 0, local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-      int tm, tn, zb, split;
-      decode(tile, tm, tn, zb, split);
-      const int kb_begin = split * kb_chunk;
-      const int num_local = max(0, min(shp.num_kb, kb_begin + kb_chunk) - kb_begin);
-      const int as = local & 1;
-      ptx::mbar_wait(tmem_empty_bar(as), ((local >> 1) & 1) ^ 1u);   // epilogue has drained this accumulator
-      ptx::tc_fence_after();
-      for (int k0 = 0; k0 < num_local; ++k0, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(full_bar(s), ph);
+    if (!PAIR || cr == 0) {
+      int it = 0, local = 0;
+      for (int tile = walker; tile < items; tile += walkers, ++local) {
+        int tm, tn, zb, split;
+        decode(tile, tm, tn, zb, split);
+        const int kb_begin = split * kb_chunk;
+        const int num_local = max(0, min(shp.num_kb, kb_begin + kb_chunk) - kb_begin);
+        const int as = local & 1;
+        ptx::mbar_wait(tmem_empty_bar(as), ((local >> 1) & 1) ^ 1u);   // the epilogues have drained this accumulator
         ptx::tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
-          const uint32_t sb = sa + STAGE_A;
-          const uint64_t adesc = A_MN ? smem_desc(sa, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sa, 16, 1024, 2);
-          const uint64_t bdesc = B_MN ? smem_desc(sb, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sb, 16, 1024, 2);
+        for (int k0 = 0; k0 < num_local; ++k0, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(full_bar(s), ph);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_base + s * (STAGE_A + STAGE_B);
+            const uint32_t sb = sa + STAGE_A;
+            const uint64_t adesc = A_MN ? smem_desc(sa, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sa, 16, 1024, 2);
+            const uint64_t bdesc = B_MN ? smem_desc(sb, MN_BOX_BYTES, MN_SBO, MN_LAYOUT) : smem_desc(sb, 16, 1024, 2);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            ptx::umma<ELEM_BYTES>(tmem_base + as * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
-                                  (k0 > 0 || k > 0) ? 1u : 0u);
-          ptx::umma_commit(empty_bar(s));
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              if constexpr (PAIR)
+                ptx::umma_pair<ELEM_BYTES>(tmem_base + as * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
+                                           (k0 > 0 || k > 0) ? 1u : 0u);
+              else
+                ptx::umma<ELEM_BYTES>(tmem_base + as * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
+                                      (k0 > 0 || k > 0) ? 1u : 0u);
+            }
+            if constexpr (PAIR) ptx::umma_commit_pair(empty_bar(s));
+            else ptx::umma_commit(empty_bar(s));
+          }
+          __syncwarp();
+        }
+        if (lane == 0) {
+          if constexpr (PAIR) ptx::umma_commit_pair(tmem_full_bar(as));
+          else ptx::umma_commit(tmem_full_bar(as));
         }
         __syncwarp();
       }
-      if (lane == 0) ptx::umma_commit(tmem_full_bar(as));
-      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
@@ -531,7 +565,12 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const int half = (warp - 2) >> 2;
     const int col0 = half * (BLOCK_N / 2), col1 = col0 + BLOCK_N / 2;
     int local = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    // the accumulator goes back to the MMA issuer: in a pair that is the leader's barrier, for the warps of both CTAs
+    auto release_acc = [&](int as) {
+      if constexpr (PAIR) ptx::mbar_arrive_leader(tmem_empty_bar(as));
+      else ptx::mbar_arrive(tmem_empty_bar(as));
+    };
+    for (int tile = walker; tile < items; tile += walkers, ++local) {
       int tm, tn, zb, split;
       decode(tile, tm, tn, zb, split);
       const int as = local & 1;
@@ -562,7 +601,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         Epi::template run_staged<BLOCK_N>(ep, acc, regs, q * 32 + lane, m, n0, zb, col0, col1, shp, stage);
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));
+        if (lane == 0) release_acc(as);
         ptx::fence_proxy_async_smem();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 64) {
@@ -573,17 +612,19 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         Epi::template run<BLOCK_N>(ep, acc, regs, m, n0, zb, col0, col1, shp);
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));   // this warp no longer reads accumulator `as`
+        if (lane == 0) release_acc(as);   // this warp no longer reads accumulator `as`
       }
     }
     if constexpr (epi_is_staged<Epi>::value) {
       if (threadIdx.x == 64) ptx::bulk_wait_read<0>();
     }
   }
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
