@@ -93,7 +93,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -145,8 +145,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     os.environ["DVAE_B200_PRECISION"] = args.precision
     from dvae_b200 import lib, ops
@@ -266,11 +264,11 @@ def run_ours(args):
         pass
     peak_tf = peaks.get("bf16_tflops", 1590.0) * (1.0 if args.precision == "bf16" else 0.5)
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "tc_gemm_kernel<BLOCK_N=256, conv5 fwd 512->512>", "achieved": achieved,
+    roofline = {"bound": "tensor", "kernel": "tc_gemm_persistent_kernel<BLOCK_N=256, cta_group::2 pairs> conv5 fwd 512->512", "achieved": achieved,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
                 # (profiles/r01_ncu_gemm_v1.txt): 102.8 MB + 35.3 MB; algorithmic = 67.1 (x) + 2.6 (w) + 67.1 (y) MB
-                "traffic": 138.07e6 if (args.precision == "bf16" and R == 512) else None,
+                "traffic": 125.0e6 if (args.precision == "bf16" and R == 512) else None,   # dram rd+wr, profiles/r01_ncu_targets_v2.txt
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PF")
                 + ("" if args.precision == "bf16" else " x 0.5 for kind::tf32"),
                 "flops_per_launch": conv_flops, "ms_per_launch": conv_ms}
@@ -303,12 +301,36 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "clocks": clocks.summary(),
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+# stdout carries exactly ONE line, the JSON result: libraries that chat on fd 1 (NCCL prints its version banner there at
+# init) are sent to stderr for the whole run and the result is written to the saved descriptor.
+_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_STDOUT_FD, data)
+
+
 if __name__ == "__main__":
+    _quiet_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)
