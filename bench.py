@@ -219,12 +219,26 @@ def run_ours(args):
     model.noise_hook = None
     x1_h, x2_h = x1.cpu().pin_memory(), x2.cpu().pin_memory()
 
+    # the host side is the package's own input pipeline (dvae_b200.data): the copy of step k+1's batch overlaps step k, and
+    # the loss of step k is read back (4 bytes, pinned) while step k+1 runs -- every step still moves its own inputs H2D
+    # and its own loss D2H inside the timed region
+    from dvae_b200.data import AsyncScalars, DevicePrefetcher
+
+    def host_batches():
+        while True:
+            yield x1_h, x2_h, None
+    feed = iter(DevicePrefetcher(host_batches(), dev, depth=2))
+    readback = AsyncScalars(1, dev)
+    last_loss = [None]
+
     def e2e_step():
-        a = x1_h.to(dev, non_blocking=True).float()
-        b = x2_h.to(dev, non_blocking=True).float()
+        a, b, _ = next(feed)
         losses = fwd_bwd(a, b)
-        return losses[0].item()
+        got = readback.push(losses[0])
+        if got is not None:
+            last_loss[0] = got[0]
     e2e_ms = timed(e2e_step, args.steps, warm) / args.steps
+    last_loss[0] = readback.flush()[0]
     e2e_value = world * frames_per_step / (e2e_ms * 1e-3)
     noise_bytes = (2 * R * 28 + R * 4) * 4
     h2d = x1_h.numel() * 4 * 2 + noise_bytes
@@ -292,7 +306,8 @@ def run_ours(args):
                    "parallelism": f"dp{world} (whole speaker groups per rank, bucketed NCCL all-reduce)" if world > 1 else "single GPU",
                    "l2": "inputs+activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
                    "weights": "random init (reference initialisers), no checkpoint"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+                "pipeline": "dvae_b200.data: H2D of step k+1 (pinned, side stream) overlaps step k; loss of step k read back during step k+1"},
         "gpu_launches": launches,
         "roofline": roofline,
         "step_tensor_frac": {"algorithmic_tflop_per_step": step_flops / 1e12, "achieved_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,

@@ -73,17 +73,31 @@ class VariationalBaseModelVAE():
         return tuple(torch.stack([l.detach() for l in losses]).tolist())
 
     def train(self, train_loader, epoch, logging_func=print):
-        """One epoch (:74-101).  Returns the reference's 7-tuple of summed loss terms."""
+        """One epoch (:74-101).  Returns the reference's 7-tuple of summed loss terms.
+
+        Same arithmetic and the same return value as the reference loop; the host side is pipelined: batch k+1 is
+        copied to the device while batch k computes (`DevicePrefetcher`) and the eight loss scalars of a step are read
+        back one step late, without stalling the launch queue (`AsyncScalars`)."""
+        from dvae_b200.data import AsyncScalars, DevicePrefetcher
         self.model.train()
         tot = [0.0] * 8
         dev = next(self.model.parameters()).device
-        for batch_idx, (data1, data2, speaker_ids) in enumerate(tqdm(train_loader)):
-            data1 = data1.to(dev, non_blocking=True).float()
-            data2 = data2.to(dev, non_blocking=True).float()
-            speaker_ids = speaker_ids.view(-1)
-            vals = self.step(data1, data2, speaker_ids, train=True)
-            tot = [a + b for a, b in zip(tot, vals)]
-            last_style_kl = vals[7]
+        scalars = AsyncScalars(8, dev)
+        last_style_kl = 0.0
+
+        def account(vals):
+            nonlocal tot, last_style_kl
+            if vals is not None:
+                tot = [a + b for a, b in zip(tot, vals)]
+                last_style_kl = vals[7]
+        for batch_idx, (data1, data2, speaker_ids) in enumerate(tqdm(DevicePrefetcher(train_loader, dev))):
+            self.optimizer.zero_grad()
+            out = self.model(data1, data2)
+            losses = self.loss_functionGVAE2(data1, data2, *out, train=True)
+            losses[0].backward()
+            self.optimizer.step()
+            account(scalars.push(torch.stack([l.detach() for l in losses])))
+        account(scalars.flush())
         if hasattr(train_loader.dataset, "shuffle_data"):
             train_loader.dataset.shuffle_data()
         logging_func('====> Epoch: {} Average loss: {:.4f}'.format(epoch, tot[0] / len(train_loader.dataset)))

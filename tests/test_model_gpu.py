@@ -195,3 +195,51 @@ def test_trainer_loop_checkpoint_and_resume(tmp_path):
     w2 = _build("bf16", 4, O.synth_state_dict(1))
     assert w2.load_last_model(ck) == 2
     assert torch.equal(w2.model.dec_linear2.linear_layer.weight, w.model.dec_linear2.linear_layer.weight)
+
+
+def test_pipelined_epoch_equals_step_loop():
+    """`train()` (prefetched H2D copies + one-step-late loss read-back, dvae_b200.data) returns what the reference-style
+    loop of blocking `step()` calls returns (model/variational_base_vae.py:74-101) on the same batches, weights and noise."""
+    from oracle import dvae_oracle as O
+    ds = _PairDataset(12)
+    loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False, pin_memory=True)
+    noise = [torch.randn(4, 28, device="cuda"), torch.randn(4, 28, device="cuda"), torch.randn(4, 4, device="cuda")]
+    results = []
+    for mode in ("pipelined", "blocking"):
+        w = _build("bf16", 4, O.synth_state_dict(0))
+        k = [0]
+
+        def hook(shape):
+            k[0] += 1
+            return noise[(k[0] - 1) % 3]
+        w.model.noise_hook = hook
+        if mode == "pipelined":
+            out = w.train(loader, 1, logging_func=lambda *_: None)
+        else:
+            w.model.train()
+            tot, last = [0.0] * 8, 0.0
+            for d1, d2, spk in loader:
+                vals = w.step(d1.cuda().float(), d2.cuda().float(), spk.view(-1), train=True)
+                tot = [a + b for a, b in zip(tot, vals)]
+                last = vals[7]
+            out = (tot[1], tot[2], tot[3], tot[4], tot[5], tot[6], last)
+        results.append((out, w.model.dec_linear2.linear_layer.weight.detach().clone()))
+    # not bit-equal run to run: the split-K weight-gradient reductions add in arrival order, and Adam amplifies the last
+    # bits of near-zero gradients (three steps of at most lr = 1e-4 each)
+    for a, b in zip(results[0][0], results[1][0]):
+        assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (a, b)
+    assert (results[0][1] - results[1][1]).abs().max().item() <= 6.1e-4
+    assert (results[0][1] - results[1][1]).abs().mean().item() <= 5e-5
+
+
+def test_device_prefetcher_order_and_values():
+    from dvae_b200.data import AsyncScalars, DevicePrefetcher
+    batches = [(torch.full((2, 80, 64), float(i)), torch.full((2, 80, 64), float(-i)), torch.tensor([i, i])) for i in range(5)]
+    seen = []
+    for a, b, spk in DevicePrefetcher(batches, torch.device("cuda"), depth=2):
+        assert a.is_cuda and a.dtype == torch.float32
+        seen.append((a[0, 0, 0].item(), b[0, 0, 0].item(), int(spk[0])))
+    assert seen == [(float(i), float(-i), i) for i in range(5)]
+    s = AsyncScalars(3, torch.device("cuda"))
+    outs = [s.push(torch.tensor([i, 2.0 * i, 3.0 * i], device="cuda")) for i in range(4)] + [s.flush()]
+    assert outs[0] is None and outs[1:] == [[float(i), 2.0 * i, 3.0 * i] for i in range(4)]
