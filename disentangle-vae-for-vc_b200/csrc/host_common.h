@@ -47,6 +47,10 @@ inline int ceil_div(long a, long b) { return static_cast<int>((a + b - 1) / b); 
 
 int num_sms();
 
+// BatchNorm statistics pass (ops_pointwise.cu): per-half column sums / sums of squares of y [halves*rows_half, C] into
+// ws [halves][2][C] doubles (accumulating; the caller zeroes ws)
+int bn_stats_launch(int dtype, const void* y, double* ws, int rows_half, int halves, int C, cudaStream_t st);
+
 // Sequence-resident LSTM recurrence (ops_lstm_seq.cu): one launch for all T steps when W_hh fits in shared memory.
 bool lstm_seq_supported(int H, int T);
 void lstm_seq_set_stamps(long long* buf);

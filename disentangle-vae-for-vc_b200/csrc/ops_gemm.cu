@@ -215,6 +215,11 @@ static bool use_tma_store(const void* out, const float* out_f32, const void* mas
   return mode == 1 || num_kb <= max_kb;
 }
 
+static bool tma_store_possible(const void* out, const float* out_f32, const void* mask, long ldo, int elem_bytes) {
+  static const int mode = env_int("DVAE_GEMM_TMA_STORE", 2);
+  return mode != 0 && out != nullptr && out_f32 == nullptr && mask == nullptr && (ldo * elem_bytes) % 16 == 0;
+}
+
 // ------------------------------------------------------------------------------------ Linear
 template <typename AT>
 static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, AT* out, float* out_f32, long ldo, int M,
@@ -244,7 +249,7 @@ static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, A
     if (use_tma_store(out, out_f32, nullptr, ldo, EB, shp.num_kb)) {
       typename EpiStoreTma<AT>::Params et;
       if (int e = encode_map3(&et.tm_out, out, EB, N, M, 1, (uint64_t)ldo * EB, (uint64_t)M * ldo * EB, BK, 128, 1)) return e;
-      et.bias = bias; et.relu = relu;
+      et.bias = bias; et.relu = relu; et.stat_sums = nullptr; et.rows_half = 0;
       return launch_gemm_persistent<256, false, false, EB, EpiStoreTma<AT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
     }
     return launch_gemm_persistent<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -253,7 +258,7 @@ static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, A
     if (use_tma_store(out, out_f32, nullptr, ldo, EB, shp.num_kb)) {
       typename EpiStoreTma<AT>::Params et;
       if (int e = encode_map3(&et.tm_out, out, EB, N, M, 1, (uint64_t)ldo * EB, (uint64_t)M * ldo * EB, BK, 128, 1)) return e;
-      et.bias = bias; et.relu = relu;
+      et.bias = bias; et.relu = relu; et.stat_sums = nullptr; et.rows_half = 0;
       switch (BN) {
         case 64: return launch_gemm_persistent<64, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
         case 128: return launch_gemm_persistent<128, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
@@ -301,7 +306,7 @@ static int linear_dgrad_t(const AT* dy, long lddy, const AT* w, AT* dx, float* d
     if (use_tma_store(dx, dx_f32, relu_mask, ldx, EB, shp.num_kb)) {
       typename EpiStoreTma<AT>::Params et;
       if (int e = encode_map3(&et.tm_out, dx, EB, K, M, 1, (uint64_t)ldx * EB, (uint64_t)M * ldx * EB, BK, 128, 1)) return e;
-      et.bias = nullptr; et.relu = 0;
+      et.bias = nullptr; et.relu = 0; et.stat_sums = nullptr; et.rows_half = 0;
       return launch_gemm_persistent<256, false, true, EB, EpiStoreTma<AT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
     }
     return launch_gemm_persistent<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -310,7 +315,7 @@ static int linear_dgrad_t(const AT* dy, long lddy, const AT* w, AT* dx, float* d
     if (use_tma_store(dx, dx_f32, relu_mask, ldx, EB, shp.num_kb)) {
       typename EpiStoreTma<AT>::Params et;
       if (int e = encode_map3(&et.tm_out, dx, EB, K, M, 1, (uint64_t)ldx * EB, (uint64_t)M * ldx * EB, BK, 128, 1)) return e;
-      et.bias = nullptr; et.relu = 0;
+      et.bias = nullptr; et.relu = 0; et.stat_sums = nullptr; et.rows_half = 0;
       switch (BN) {
         case 64: return launch_gemm_persistent<64, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
         case 128: return launch_gemm_persistent<128, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
@@ -405,7 +410,9 @@ static bool conv_tile_geometry(int T, int* box_t, int* box_r, int* tiles_per_seq
 
 template <typename AT>
 static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, float* y_f32, int R, int T, int Cin, int Cout,
-                       bool dgrad, cudaStream_t st) {
+                       bool dgrad, cudaStream_t st, double* bn_sums = nullptr, int rows_half = 0, bool* stats_fused = nullptr) {
+  // bn_sums != nullptr: also accumulate the train-mode BatchNorm statistics of y (per column sum / sum of squares of the
+  // stored values, per statistics half) -- fused into the staged store epilogue when that path is taken (*stats_fused).
   // fwd :  y[r,t,co]  = sum_{k,ci} x[r,t+k-2,ci] wk[co][k][ci]                     (B K-major)
   // dgrad: dx[r,t,ci] = sum_{k',co} dy[r,t+k'-2,co] wk[co][4-k'][ci]               (B MN-major)
   // In dgrad mode the caller passes x:=dy, y:=dx, and (Cin, Cout) are still the forward layer's.
@@ -431,6 +438,9 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
   const int kpt = ceil_div(Ca, BK);
   GemmShape shp{R * T, Cn, 5 * kpt, kpt, 1};
   typename EpiStore<AT>::Params ep{y, y_f32, bias, nullptr, (long)Cn, 0, 0};
+  static const int fuse_env = env_int("DVAE_BN_FUSE_STATS", 1);
+  const bool want_stats = fuse_env != 0 && bn_sums != nullptr && !dgrad && rows_half > 0 && rows_half % 128 == 0;
+  if (stats_fused) *stats_fused = false;
   const int mt = pick_mt((long)R * T, ceil_div(Cn, BN));
   dim3 grid(ceil_div((long)R * T, 128 * mt), ceil_div(Cn, BN), 1);
   if (mt == 2) {
@@ -451,22 +461,27 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
     if (!dgrad) {   // K-major filter tile: re-encode with half the rows per box
       if (int e = encode_map3(&tb, wk, EB, Cin, 5, Cout, (uint64_t)Cin * EB, (uint64_t)5 * Cin * EB, BK, 1, BN / 2)) return e;
     }
-    if (use_tma_store(y, y_f32, nullptr, Cn, EB, shp.num_kb)) {
+    if (use_tma_store(y, y_f32, nullptr, Cn, EB, shp.num_kb) || (want_stats && tma_store_possible(y, y_f32, nullptr, Cn, EB))) {
       typename EpiStoreTma<AT>::Params et;
       if (int e = encode_map3(&et.tm_out, y, EB, Cn, (uint64_t)R * T, 1, (uint64_t)Cn * EB, (uint64_t)R * T * Cn * EB, BK, 128, 1))
         return e;
       et.bias = bias; et.relu = 0;
+      et.stat_sums = want_stats ? bn_sums : nullptr; et.rows_half = rows_half;
+      if (want_stats && stats_fused) *stats_fused = true;
       if (!dgrad) return launch_gemm_persistent<256, false, false, EB, EpiStoreTma<AT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
       return launch_gemm_persistent<256, false, true, EB, EpiStoreTma<AT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
     }
     if (!dgrad) return launch_gemm_persistent<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
     return launch_gemm_persistent<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   }
-  if (want_persistent(grid) && use_tma_store(y, y_f32, nullptr, Cn, EB, shp.num_kb)) {
+  if (want_persistent(grid) &&
+      (use_tma_store(y, y_f32, nullptr, Cn, EB, shp.num_kb) || (want_stats && tma_store_possible(y, y_f32, nullptr, Cn, EB)))) {
     typename EpiStoreTma<AT>::Params et;
     if (int e = encode_map3(&et.tm_out, y, EB, Cn, (uint64_t)R * T, 1, (uint64_t)Cn * EB, (uint64_t)R * T * Cn * EB, BK, 128, 1))
       return e;
     et.bias = bias; et.relu = 0;
+    et.stat_sums = want_stats ? bn_sums : nullptr; et.rows_half = rows_half;
+    if (want_stats && stats_fused) *stats_fused = true;
     if (!dgrad) {
       switch (BN) {
         case 64: return launch_gemm_persistent<64, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
@@ -930,6 +945,29 @@ int dvae_conv5_fwd(int dtype, const void* x, const void* wk, const float* bias, 
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype, conv5_fwd_t<bf16>((const bf16*)x, (const bf16*)wk, bias, (bf16*)y, y_f32, R, T, Cin, Cout, false, st),
                  conv5_fwd_t<tf32_t>((const tf32_t*)x, (const tf32_t*)wk, bias, (tf32_t*)y, y_f32, R, T, Cin, Cout, false, st));
+}
+
+// Convolution + the statistics pass of the train-mode BatchNorm that follows it (ConvNorm -> BatchNorm1d,
+// model/disentangled_vae.py:154-160): bn_ws [halves*2*Cout + 1] doubles receives per-half column sums / sums of squares of
+// y (zeroed here).  Fused into the GEMM's staged store epilogue when possible, otherwise a separate reduction kernel.
+int dvae_conv5_fwd_bnstats(int dtype, const void* x, const void* wk, const float* bias, void* y, int R, int T, int Cin, int Cout,
+                           double* bn_ws, int rows_half, int halves, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DVAE_REQUIRE(bn_ws != nullptr && halves >= 1 && (long)rows_half * halves == (long)R * T, "rows_half * halves must equal R * T");
+  DVAE_CHECK_CUDA(cudaMemsetAsync(bn_ws, 0, sizeof(double) * ((long)halves * 2 * Cout + 1), st));
+  bool fused = false;
+  int e;
+  if (dtype == kBF16)
+    e = conv5_fwd_t<bf16>((const bf16*)x, (const bf16*)wk, bias, (bf16*)y, nullptr, R, T, Cin, Cout, false, st, bn_ws, rows_half, &fused);
+  else if (dtype == kTF32)
+    e = conv5_fwd_t<tf32_t>((const tf32_t*)x, (const tf32_t*)wk, bias, (tf32_t*)y, nullptr, R, T, Cin, Cout, false, st, bn_ws, rows_half, &fused);
+  else {
+    set_last_error("unknown dtype tag");
+    return 1;
+  }
+  if (e) return e;
+  if (!fused) return bn_stats_launch(dtype, y, bn_ws, rows_half, halves, Cout, st);
+  return 0;
 }
 
 int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,

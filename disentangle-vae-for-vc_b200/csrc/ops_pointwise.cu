@@ -493,6 +493,26 @@ using namespace dvae;
     else { set_last_error("unknown dtype tag"); return 1; }  \
   } while (0)
 
+// rows per block: the largest power-of-two multiple of 64 up to `want` that divides rows_half (blocks never straddle halves)
+static int bn_rows_per_block(int rows_half, int want) {
+  int rb = kBnRowsPerBlock;
+  while (rb * 2 <= want && rows_half % (rb * 2) == 0) rb *= 2;
+  return rb;
+}
+
+namespace dvae {
+int bn_stats_launch(int dtype, const void* y, double* ws, int rows_half, int halves, int C, cudaStream_t st) {
+  DVAE_REQUIRE(C % 8 == 0 && C <= 2048, "C must be a multiple of 8 (<= 2048)");
+  DVAE_REQUIRE(rows_half % kBnRowsPerBlock == 0, "rows per half must be a multiple of 64");
+  const long rows = static_cast<long>(rows_half) * halves;
+  const int rb_red = bn_rows_per_block(rows_half, 512);
+  const dim3 g_red(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_red));
+  DISPATCH_AT(dtype, bn_stats_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)y, ws, rows_half, C, rb_red));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace dvae
+
 extern "C" {
 
 int dvae_prep_cast(int dtype, const float* src, void* dst, long n, void* stream) {
@@ -580,13 +600,6 @@ int dvae_recon_out_bwd(int dtype, const float* g_rec, const float* g_hat, void* 
   return 0;
 }
 
-// rows per block: the largest power-of-two multiple of 64 up to `want` that divides rows_half (blocks never straddle halves)
-static int bn_rows_per_block(int rows_half, int want) {
-  int rb = kBnRowsPerBlock;
-  while (rb * 2 <= want && rows_half % (rb * 2) == 0) rb *= 2;
-  return rb;
-}
-
 // Train-mode BatchNorm forward over y [halves*rows_half, C]: statistics per half, then act(y*scale+shift).
 // ws: double [halves*2*C] scratch; stat: fp32 [halves*4*C] (kept for backward).
 int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
@@ -600,6 +613,23 @@ int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, c
   const int rb_red = bn_rows_per_block(rows_half, 512), rb_app = bn_rows_per_block(rows_half, 256);
   const dim3 g_red(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_red)), g_app(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_app));
   DISPATCH_AT(dtype, bn_stats_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)y, ws, rows_half, C, rb_red));
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, gamma, beta, stat, run_mean, run_var, num_batches, halves, C,
+                                                        static_cast<double>(rows_half), eps, momentum);
+  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<g_app, 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half, C, act, rb_app));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// Second half of dvae_bn_train_fwd for a caller that already holds the statistics sums in ws (dvae_conv5_fwd_bnstats):
+// finalise (mean / rstd / scale / shift, running statistics) and apply the affine transform + activation.
+int dvae_bn_finalize_apply(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
+                           float* run_var, long long* num_batches, const double* ws, float* stat, int rows_half, int halves,
+                           int C, int act, float eps, float momentum, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DVAE_REQUIRE(C % 8 == 0 && C <= 2048, "C must be a multiple of 8 (<= 2048)");
+  DVAE_REQUIRE(rows_half % kBnRowsPerBlock == 0, "rows per half must be a multiple of 64");
+  const long rows = static_cast<long>(rows_half) * halves;
+  const int rb_app = bn_rows_per_block(rows_half, 256);
+  const dim3 g_app(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_app));
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, gamma, beta, stat, run_mean, run_var, num_batches, halves, C,
                                                         static_cast<double>(rows_half), eps, momentum);
   DISPATCH_AT(dtype, bn_apply_kernel<AT><<<g_app, 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half, C, act, rb_app));

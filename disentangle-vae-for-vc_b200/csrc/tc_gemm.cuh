@@ -28,6 +28,7 @@ namespace dvae {
 
 constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpilogueThreads = 256;
+constexpr int kEpilogueThreadsC = 256;   // (same, usable in constant expressions of the epilogue structs)
 
 struct OperandWalk {
   int base[3];
@@ -608,6 +609,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           Epi::template flush<BLOCK_N>(ep, stage, tm, tn, zb, shp);
           ptx::bulk_commit();
         }
+        Epi::template after_stage<BLOCK_N>(ep, stage, static_cast<int>(threadIdx.x) - 64, tm, tn, zb, shp);   // reads the staged tile
       } else {
         Epi::template run<BLOCK_N>(ep, acc, regs, m, n0, zb, col0, col1, shp);
         ptx::tc_fence_before();
@@ -643,6 +645,8 @@ struct EpiReduceTma {
   };
   template <int BLOCK_N>
   static __host__ __device__ constexpr int staging_bytes() { return BLOCK_N * 4 * kBlockM; }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void after_stage(const Params&, uint32_t, int, int, int, int, const GemmShape&) {}
   template <int BLOCK_N>
   static __device__ __forceinline__ void prefetch(const Params& p, int, int, int, int, int, const GemmShape&) {
     if ((threadIdx.x & 255) == 64) ptx::prefetch_tmap(&p.tm_out);
@@ -779,9 +783,51 @@ struct EpiStoreTma {
     CUtensorMap tm_out;   // OutT {N, M, batches}, box {128 / EB, 128, 1}
     const float* bias;    // [N] or null
     int relu;
+    // optional BatchNorm statistics of the stored tile (train-mode nn.BatchNorm1d right after the convolution): per
+    // column sum and sum of squares of the values AS STORED, added to stat_sums[half][2][N] (double), half = m / rows_half
+    double* stat_sums;
+    int rows_half;
   };
   template <int BLOCK_N>
   static __host__ __device__ constexpr int staging_bytes() { return BLOCK_N * EB * kBlockM; }
+  // After the tile is staged (and its TMA store issued) every epilogue thread sums one column of the staged tile: the
+  // statistics pass of the BatchNorm that follows costs no extra read of the activation tensor.  Column c of row r lives
+  // in box c*EB/128 at chunk ((c*EB%128)/16) ^ (r&7): the 32 lanes of a warp read 32 consecutive columns of one row.
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void after_stage(const Params& p, uint32_t stage, int et, int tile_m, int tile_n, int,
+                                                     const GemmShape& shp) {
+    if (p.stat_sums == nullptr) return;
+    constexpr int CPT = BLOCK_N / kEpilogueThreadsC;          // columns per thread (1 for BLOCK_N = 256)
+    const int m0 = tile_m * kBlockM;
+    const int nrows = min(kBlockM, shp.M - m0);
+    const int half = m0 / p.rows_half;
+#pragma unroll
+    for (int cc = 0; cc < (CPT > 0 ? CPT : 1); ++cc) {
+      const int c = (CPT > 0) ? et * CPT + cc : et;
+      if (c >= BLOCK_N) return;
+      const int n = tile_n * BLOCK_N + c;
+      if (n >= shp.N) continue;
+      const int byte = c * EB;
+      const uint32_t base = stage + static_cast<uint32_t>((byte >> 7) * (kBlockM * 128) + (byte & 15));
+      const int chunk = (byte & 127) >> 4;
+      float s = 0.f, q = 0.f;
+      for (int r = 0; r < nrows; ++r) {
+        const uint32_t a = base + static_cast<uint32_t>(r * 128 + ((chunk ^ (r & 7)) << 4));
+        float v;
+        if constexpr (EB == 2) {
+          unsigned short u;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(a));
+          v = __uint_as_float(static_cast<uint32_t>(u) << 16);
+        } else {
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+        }
+        s += v;
+        q = fmaf(v, v, q);
+      }
+      atomicAdd(p.stat_sums + (static_cast<long>(half) * 2 + 0) * shp.N + n, static_cast<double>(s));
+      atomicAdd(p.stat_sums + (static_cast<long>(half) * 2 + 1) * shp.N + n, static_cast<double>(q));
+    }
+  }
   template <int BLOCK_N>
   static __device__ __forceinline__ void prefetch(const Params&, int, int, int, int, int, const GemmShape&) {}
   template <int BLOCK_N> struct Regs {};
@@ -1000,6 +1046,8 @@ struct EpiLstmFwdTma : EpiLstmFwd<ActT> {
   static __host__ __device__ constexpr int staging_bytes() {
     return (g_boxes<BLOCK_N>() + c_boxes<BLOCK_N>()) * kBlockM * 128 + h_bytes<BLOCK_N>();
   }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void after_stage(const Params&, uint32_t, int, int, int, int, const GemmShape&) {}
   template <int BLOCK_N>
   static __device__ __forceinline__ void run_staged(const Params& p, const AccSource& acc, const typename Base::template Regs<BLOCK_N>& r,
                                                     int row, int m, int n0, int zb, int col0, int col1, const GemmShape& shp,

@@ -145,16 +145,19 @@ class Engine:
         dt = self.dt
         for conv, bn, act in convs:
             x_in = h
-            y = ops.conv5_fwd(dt, x_in, W.conv[conv], P[conv + ".bias"])
-            C = y.shape[-1]
             if training:
-                h, stat = ops.bn_train_fwd(dt, y.view(-1, C), P[bn + ".weight"], P[bn + ".bias"], B[bn + ".running_mean"],
-                                           B[bn + ".running_var"], B[bn + ".num_batches_tracked"], halves, act, self.eps,
-                                           self.momentum)
+                # the convolution's epilogue also produces the BatchNorm statistics of its output (no extra pass over y)
+                y, ws = ops.conv5_fwd_bnstats(dt, x_in, W.conv[conv], P[conv + ".bias"], halves)
+                C = y.shape[-1]
+                h, stat = ops.bn_finalize_apply(dt, y.view(-1, C), ws, P[bn + ".weight"], P[bn + ".bias"],
+                                                B[bn + ".running_mean"], B[bn + ".running_var"],
+                                                B[bn + ".num_batches_tracked"], halves, act, self.eps, self.momentum)
                 h = h.view_as(y)
                 if saved is not None:
                     saved.append(dict(conv=conv, bn=bn, act=act, x_in=x_in, y=y, stat=stat))
             else:
+                y = ops.conv5_fwd(dt, x_in, W.conv[conv], P[conv + ".bias"])
+                C = y.shape[-1]
                 h = ops.bn_eval_fwd(dt, y.view(-1, C), P[bn + ".weight"], P[bn + ".bias"], B[bn + ".running_mean"],
                                     B[bn + ".running_var"], act, self.eps).view_as(y)
         return h

@@ -33,6 +33,7 @@ _SIGNATURES = {
     "dvae_linear_dgrad": [_i, _p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _p],
     "dvae_linear_wgrad": [_i, _p, _l, _p, _l, _p, _l, _i, _i, _i, _p],
     "dvae_conv5_fwd": [_i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dvae_conv5_fwd_bnstats": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p],
     "dvae_conv5_dgrad": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_conv5_wgrad": [_i, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_lstm_fwd": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
@@ -56,6 +57,7 @@ _SIGNATURES = {
     "dvae_recon_out_bwd": [_i, _p, _p, _p, _p, _i, _i, _i, _p],
     # batch norm / reductions
     "dvae_bn_train_fwd": [_i] + [_p] * 9 + [_i, _i, _i, _i, _f, _f, _p],
+    "dvae_bn_finalize_apply": [_i] + [_p] * 9 + [_i, _i, _i, _i, _f, _f, _p],
     "dvae_bn_eval_fwd": [_i] + [_p] * 7 + [_l, _i, _i, _f, _p],
     "dvae_bn_train_bwd": [_i] + [_p] * 8 + [_i, _i, _i, _i, _p],
     "dvae_colsum": [_i, _p, _p, _l, _i, _l, _p],
@@ -106,7 +108,7 @@ def stream():
 
 # kernels launched per C-ABI call (bench.py reports the total as `gpu_launches`)
 LAUNCHES = 0
-_LAUNCHES_PER_CALL = {"dvae_bn_train_fwd": 3, "dvae_bn_train_bwd": 3, "dvae_bn_eval_fwd": 2, "dvae_segment_ids_sorted": 3,
+_LAUNCHES_PER_CALL = {"dvae_bn_finalize_apply": 2, "dvae_bn_train_fwd": 3, "dvae_bn_train_bwd": 3, "dvae_bn_eval_fwd": 2, "dvae_segment_ids_sorted": 3,
                       "dvae_group_finalize": 2}
 _LSTM_SHAPE_ARGS = {"dvae_lstm_fwd": (7, 6), "dvae_lstm_bwd": (11, 10)}   # indices of (H, T): the library says how many launches
 

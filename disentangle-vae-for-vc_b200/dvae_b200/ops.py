@@ -80,6 +80,21 @@ def conv5_fwd(dt: int, x: Tensor, wk: Tensor, bias: Optional[Tensor], want_f32: 
     return (y, y32) if want_f32 else y
 
 
+def conv5_fwd_bnstats(dt: int, x: Tensor, wk: Tensor, bias: Optional[Tensor], halves: int):
+    """conv5_fwd + the statistics pass of the train-mode BatchNorm behind it.  Returns (y, ws): ws holds the per-half
+    column sums / sums of squares of y (double [halves*2*Cout + 1]) for `bn_finalize_apply`."""
+    ad = act_dtype(dt)
+    _chk(x, ad), _chk(wk, ad)
+    R, T, Cin = x.shape
+    Cout = wk.shape[0]
+    assert tuple(wk.shape) == (Cout, 5, Cin) and (R * T) % halves == 0
+    y = torch.empty((R, T, Cout), device=x.device, dtype=ad)
+    ws = torch.empty((halves * 2 * Cout + 1,), device=x.device, dtype=torch.float64)
+    call("dvae_conv5_fwd_bnstats", dt, ptr(x), ptr(wk), ptr(bias), ptr(y), R, T, Cin, Cout, ptr(ws), R * T // halves, halves,
+         stream())
+    return y, ws
+
+
 def conv5_dgrad(dt: int, dy: Tensor, wk: Tensor, want_f32: bool = False):
     ad = act_dtype(dt)
     _chk(dy, ad), _chk(wk, ad)
@@ -253,6 +268,21 @@ def bn_train_fwd(dt: int, y: Tensor, gamma: Tensor, beta: Tensor, run_mean: Opti
     ws = torch.empty((halves * 2 * C,), device=y.device, dtype=torch.float64)
     stat = torch.empty((halves, 4, C), device=y.device, dtype=torch.float32)
     call("dvae_bn_train_fwd", dt, ptr(y), ptr(out), ptr(gamma), ptr(beta), ptr(run_mean), ptr(run_var), ptr(num_batches),
+         ptr(ws), ptr(stat), rows // halves, halves, C, act, eps, momentum, stream())
+    return out, stat
+
+
+def bn_finalize_apply(dt: int, y: Tensor, ws: Tensor, gamma: Tensor, beta: Tensor, run_mean: Optional[Tensor],
+                      run_var: Optional[Tensor], num_batches: Optional[Tensor], halves: int, act: int, eps: float, momentum: float):
+    """bn_train_fwd without its statistics pass: `ws` comes from conv5_fwd_bnstats.  Returns (out, stat)."""
+    ad = act_dtype(dt)
+    _chk(y, ad), _chk(ws, torch.float64)
+    C = y.shape[-1]
+    rows = y.numel() // C
+    assert rows % halves == 0 and ws.numel() >= halves * 2 * C
+    out = torch.empty_like(y)
+    stat = torch.empty((halves, 4, C), device=y.device, dtype=torch.float32)
+    call("dvae_bn_finalize_apply", dt, ptr(y), ptr(out), ptr(gamma), ptr(beta), ptr(run_mean), ptr(run_var), ptr(num_batches),
          ptr(ws), ptr(stat), rows // halves, halves, C, act, eps, momentum, stream())
     return out, stat
 

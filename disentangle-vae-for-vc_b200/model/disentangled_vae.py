@@ -178,8 +178,10 @@ class DisentangledVAE(nn.Module):
         else:
             # pinned staging (torch's caching host allocator) + non_blocking copy: a copy from pageable memory would make
             # the host wait for the previous step to drain before it can start enqueueing this one
-            e = torch.empty(tuple(shape), pin_memory=True).normal_()
-            return e.to(device=dev, non_blocking=True)
+            if dev.type == "cuda":
+                e = torch.empty(tuple(shape), pin_memory=True).normal_()
+                return e.to(device=dev, non_blocking=True)
+            e = torch.empty(tuple(shape)).normal_()
         return e.to(device=dev, dtype=torch.float32).contiguous()
 
     @staticmethod

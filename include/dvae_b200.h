@@ -39,6 +39,10 @@ int dvae_linear_wgrad(int dtype, const void* dy, long lddy, const void* x, long 
  *      x [R,T,Cin] act, wk [Cout,5,Cin] act (dvae_prep_conv_weight), y [R,T,Cout] */
 int dvae_conv5_fwd(int dtype, const void* x, const void* wk, const float* bias, void* y, float* y_f32, int R, int T, int Cin,
                    int Cout, void* stream);
+/* conv + the statistics pass of the train-mode BatchNorm1d behind it (:154-160, :178-189, :54-78): bn_ws [halves*2*Cout + 1]
+ * doubles = per-half column sums / sums of squares of y; consumed by dvae_bn_finalize_apply */
+int dvae_conv5_fwd_bnstats(int dtype, const void* x, const void* wk, const float* bias, void* y, int R, int T, int Cin, int Cout,
+                           double* bn_ws, int rows_half, int halves, void* stream);
 int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,
                      void* stream);
 int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R, int T, int Cin, int Cout, void* stream);
@@ -74,6 +78,9 @@ int dvae_recon_out_bwd(int dtype, const float* g_rec, const float* g_hat, void* 
 int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
                       float* run_var, long long* num_batches, double* ws, float* stat, int rows_half, int halves, int C,
                       int act, float eps, float momentum, void* stream);
+int dvae_bn_finalize_apply(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
+                           float* run_var, long long* num_batches, const double* ws, float* stat, int rows_half, int halves,
+                           int C, int act, float eps, float momentum, void* stream);
 int dvae_bn_eval_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, const float* run_mean,
                      const float* run_var, float* stat, long rows, int C, int act, float eps, void* stream);
 int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* stat, double* ws, float* coef, void* dy,
