@@ -292,17 +292,23 @@ class Engine:
             sink.done(gname), sink.done(bname)
             wk = W.conv[s["conv"]]
             Co, _, Ci = wk.shape
-            dwk = torch.zeros(wk.shape, device=wk.device, dtype=torch.float32)
-            ops.conv5_wgrad(dt, dy, s["x_in"], dwk)
-            ops.conv_wgrad_unpack(dwk, out=sink.buf(s["conv"] + ".weight", (Co, Ci, 5)))
-            sink.done(s["conv"] + ".weight")
-            # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero (BN removes the mean)
-            sink.buf(s["conv"] + ".bias", (C,))
-            sink.done(s["conv"] + ".bias")
+            # dX first: it is the critical path (it feeds the layer below).  The weight gradient then runs on the side stream,
+            # ordered after the dgrad, so the tensor-core-bound wgrad GEMM of layer i overlaps the HBM-bound BatchNorm
+            # backward of layer i-1 instead of delaying it.
             if i > 0 or need_dx:
                 dout = ops.conv5_dgrad(dt, dy, wk)
             else:
                 dout = None
+            self._keepalive.append((dy, s["x_in"]))
+            with self._side_stream_ctx():
+                dwk = torch.zeros(wk.shape, device=wk.device, dtype=torch.float32)
+                ops.conv5_wgrad(dt, dy, s["x_in"], dwk)
+                ops.conv_wgrad_unpack(dwk, out=sink.buf(s["conv"] + ".weight", (Co, Ci, 5)))
+                self._keepalive.append((dwk,))
+            sink.done(s["conv"] + ".weight")
+            # the conv bias feeds a train-mode BatchNorm: its gradient is identically zero (BN removes the mean)
+            sink.buf(s["conv"] + ".bias", (C,))
+            sink.done(s["conv"] + ".bias")
         return dout
 
     def _lstm_bwd(self, W, prefix: str, dh: Tensor, saved_layers: list, sink: GradSink, need_dx: bool):
