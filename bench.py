@@ -282,7 +282,7 @@ def run_ours(args):
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
                 # (profiles/r01_ncu_gemm_v1.txt): 102.8 MB + 35.3 MB; algorithmic = 67.1 (x) + 2.6 (w) + 67.1 (y) MB
-                "traffic": 125.0e6 if (args.precision == "bf16" and R == 512) else None,   # dram rd+wr, profiles/r01_ncu_targets_v2.txt
+                "traffic": 128.1e6 if (args.precision == "bf16" and R == 512) else None,   # dram rd+wr, profiles/r01_ncu_targets_v3.txt
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PF")
                 + ("" if args.precision == "bf16" else " x 0.5 for kind::tf32"),
                 "flops_per_launch": conv_flops, "ms_per_launch": conv_ms}
