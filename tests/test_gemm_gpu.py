@@ -2,6 +2,8 @@
 PyTorch fp32 on the same (bf16- or tf32-representable) inputs.  Tolerances: the operands are exactly
 representable in the storage dtype, accumulation is fp32 on both sides, so only summation order and the
 rounding of the stored result differ."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -176,3 +178,37 @@ def test_lstm(name, rows, H, D, T):
     ops.lstm_wgrad_hh(dt, da, h_all, dwhh, H, D)
     relw = (dwhh - wr.grad).norm().item() / wr.grad.norm().item()
     assert relw <= (3e-2 if name == "bf16" else 3e-3), f"lstm dW_hh rel err {relw}"
+
+
+@pytest.mark.parametrize("env", [
+    {"DVAE_LSTM_SEQ": "0"},                                        # H = 64 through the step-per-launch path
+    {"DVAE_LSTM_SEQ_IO": "direct"},                                # sequence-resident kernels without the TMA staging
+    {"DVAE_LSTM_FWD_TMA": "0", "DVAE_LSTM_BWD_REDUCE": "0"},       # direct cell epilogue, store-epilogue backward
+    {"DVAE_LSTM_PAIR": "1"},                                       # CTA-pair (cta_group::2) step kernels
+    {"DVAE_LSTM_BWD_FUSED": "1"},                                  # cell backward fused into the step GEMM's epilogue
+], ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
+def test_lstm_optional_paths(env):
+    """The kernel variants that are not the default (selected by environment variables read once per process) stay correct:
+    re-run the LSTM parity test in a child process per variant."""
+    import subprocess
+    import sys
+    child_env = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", "test_lstm and not optional",
+                        "-p", "no:cacheprovider"], env=child_env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("env", [
+    {"DVAE_GEMM_PERSISTENT": "1"},                                 # persistent CTA-pair kernels on the small test shapes
+    {"DVAE_GEMM_PERSISTENT": "1", "DVAE_GEMM_PAIR": "0"},          # persistent 1-SM kernels
+    {"DVAE_GEMM_PERSISTENT": "1", "DVAE_GEMM_TMA_STORE": "1"},     # staged TMA-store epilogue wherever eligible
+    {"DVAE_GEMM_PERSISTENT": "0", "DVAE_WGRAD_WIDE": "0"},         # one tile per CTA only
+], ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
+def test_gemm_optional_paths(env):
+    """Same for the dense-contraction variants (linear / conv forward, dgrad, wgrad)."""
+    import subprocess
+    import sys
+    child_env = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", "not lstm and not optional",
+                        "-p", "no:cacheprovider"], env=child_env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
