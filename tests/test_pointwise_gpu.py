@@ -244,3 +244,29 @@ def test_fused_adam_matches_torch_adam():
         assert torch.allclose(a["exp_avg_sq"], b["exp_avg_sq"], rtol=1e-5, atol=1e-6 * a["exp_avg_sq"].abs().max().item())
     with pytest.raises(NotImplementedError):
         Adam(our_p, weight_decay=0.1)
+
+
+def test_fused_adam_survives_state_reload():
+    """load_state_dict replaces the moment tensors: the pointer tables are rebuilt and the next step continues from the
+    loaded state exactly like torch.optim.Adam does."""
+    from dvae_b200.optim import Adam
+    torch.manual_seed(5)
+    p0 = [torch.randn(300, 70, device="cuda"), torch.randn(17, device="cuda")]
+    grads = [[torch.randn_like(p) for p in p0] for _ in range(4)]
+
+    def run(cls, reload_at):
+        ps = [p.clone().requires_grad_(True) for p in p0]
+        opt = cls(ps, lr=3e-3)
+        for i, gs in enumerate(grads):
+            if i == reload_at:
+                sd = opt.state_dict()
+                opt = cls(ps, lr=3e-3)
+                opt.load_state_dict(sd)
+            for p, g in zip(ps, gs):
+                p.grad = g.clone()
+            opt.step()
+        return ps
+    ref = run(torch.optim.Adam, 2)
+    ours = run(Adam, 2)
+    for a, b in zip(ref, ours):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7)
