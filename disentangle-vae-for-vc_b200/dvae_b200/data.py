@@ -86,3 +86,40 @@ class AsyncScalars:
             return None
         self.events[slot].synchronize()
         return self.bufs[slot].tolist()
+
+
+class SpeakerGroupBatchSampler(torch.utils.data.Sampler):
+    """Batch sampler for data-parallel training: every step draws a global batch of `world * pairs_per_rank` items and
+    hands each rank the rows of WHOLE speaker groups (`parallel.shard_pairs_by_speaker`), sorted by speaker, so that the
+    speaker-group kernels never need a cross-rank exchange.  All ranks must construct it with the same
+    `speaker_ids`, `seed` and call `set_epoch` with the same epoch: the global permutation is then identical everywhere.
+
+    With equally sized speaker groups (the BASELINE configs: 8 utterances per speaker) every rank gets exactly
+    `pairs_per_rank` rows; otherwise ranks differ by at most one group.  Use as `DataLoader(ds, batch_sampler=...)`.
+    The reference (`train.py:49-58`) uses a plain shuffled DataLoader on one process."""
+
+    def __init__(self, speaker_ids, pairs_per_rank: int, rank: int = 0, world: int = 1, shuffle: bool = True, seed: int = 0,
+                 drop_last: bool = True):
+        import numpy as np
+        self.ids = np.asarray(speaker_ids).reshape(-1)
+        self.pairs_per_rank, self.rank, self.world = int(pairs_per_rank), int(rank), int(world)
+        self.shuffle, self.seed, self.drop_last, self.epoch = shuffle, seed, drop_last, 0
+        if not 0 <= self.rank < self.world:
+            raise ValueError("rank must be in [0, world)")
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = int(epoch)
+
+    def __len__(self) -> int:
+        g = self.pairs_per_rank * self.world
+        return len(self.ids) // g if self.drop_last else -(-len(self.ids) // g)
+
+    def __iter__(self):
+        import numpy as np
+        from .parallel import shard_pairs_by_speaker
+        n, g = len(self.ids), self.pairs_per_rank * self.world
+        order = np.random.default_rng(self.seed + self.epoch).permutation(n) if self.shuffle else np.arange(n)
+        for b in range(len(self)):
+            glob = order[b * g:(b + 1) * g]
+            local = shard_pairs_by_speaker(self.ids[glob], self.rank, self.world)
+            yield glob[local].tolist()

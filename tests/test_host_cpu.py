@@ -138,3 +138,35 @@ def test_bucket_plan_covers_all_parameters(built_lib):
     assert all(len(m) > 0 for m in gb.members) and len(gb.members) == len(BUCKET_PREFIXES)
     v = gb.view("postnet.convolutions.0.0.conv.weight")
     assert tuple(v.shape) == (512, 80, 5) and all(off % 64 == 0 for _, off, _ in gb.slots.values())   # 256-byte slots
+
+
+def test_speaker_group_batch_sampler(built_lib):
+    """Per step the ranks' index lists partition the global batch, every speaker's rows land on one rank, rows come sorted
+    by speaker, and all ranks agree on the permutation (same seed / epoch)."""
+    import numpy as np
+    from dvae_b200.data import SpeakerGroupBatchSampler
+    ids = np.repeat(np.arange(12), 8)                       # 12 speakers x 8 utterances
+    rng = np.random.default_rng(0)
+    ids = ids[rng.permutation(len(ids))]
+    world, ppr = 4, 8                                       # global batch 32
+    samplers = [SpeakerGroupBatchSampler(ids, ppr, r, world, shuffle=True, seed=7) for r in range(world)]
+    for s in samplers:
+        s.set_epoch(3)
+    steps = [list(iter(s)) for s in samplers]
+    assert all(len(st) == len(ids) // (world * ppr) == len(samplers[0]) for st in steps)
+    seen = []
+    for b in range(len(steps[0])):
+        union = sorted(i for r in range(world) for i in steps[r][b])
+        assert len(set(union)) == len(union) == world * ppr
+        seen += union
+        owners = {}
+        for r in range(world):
+            spk = ids[steps[r][b]]
+            assert list(spk) == sorted(spk) or len(set(spk)) == len({k for k, _ in __import__("itertools").groupby(spk)})
+            for sp in set(spk.tolist()):
+                assert owners.setdefault(sp, r) == r       # a speaker's rows of this batch are on one rank
+    assert len(set(seen)) == len(seen)                      # no index is used twice in an epoch
+    again = list(iter(samplers[1]))
+    assert again == steps[1]                                # deterministic for a fixed (seed, epoch)
+    samplers[1].set_epoch(4)
+    assert list(iter(samplers[1])) != steps[1]
