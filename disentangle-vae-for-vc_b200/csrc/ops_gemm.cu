@@ -570,10 +570,6 @@ static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, in
 //   h_all [rows, T, D*H]   layer output, also the A operand of the next step (3-D TMA over {D*H, T, rows})
 //   c_all [rows, T, D*H]   fp32 cell state
 //   whh_p [D][4H][H]       recurrent weights, rows gate-interleaved like xg columns
-template <int H>
-struct LstmFwdBN {
-  static constexpr int value = (4 * H >= 512) ? 128 : 256;  // H=64 -> one 256-wide tile holds all 4 gates of 64 units
-};
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;

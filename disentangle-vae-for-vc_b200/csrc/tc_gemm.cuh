@@ -28,7 +28,6 @@ namespace dvae {
 
 constexpr int kGemmThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpilogueThreads = 256;
-constexpr int kEpilogueThreadsC = 256;   // (same, usable in constant expressions of the epilogue structs)
 
 struct OperandWalk {
   int base[3];
@@ -797,7 +796,7 @@ struct EpiStoreTma {
   static __device__ __forceinline__ void after_stage(const Params& p, uint32_t stage, int et, int tile_m, int tile_n, int,
                                                      const GemmShape& shp) {
     if (p.stat_sums == nullptr) return;
-    constexpr int CPT = BLOCK_N / kEpilogueThreadsC;          // columns per thread (1 for BLOCK_N = 256)
+    constexpr int CPT = BLOCK_N / kEpilogueThreads;          // columns per thread (1 for BLOCK_N = 256)
     const int m0 = tile_m * kBlockM;
     const int nrows = min(kBlockM, shp.M - m0);
     const int half = m0 / p.rows_half;

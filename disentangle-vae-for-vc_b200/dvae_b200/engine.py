@@ -342,32 +342,31 @@ class Engine:
         dt = self.dt
         D, H, lw = s["D"], s["H"], s["lw"]
         In = lw["In"]
-        if True:
-            if D == 1:   # gradients land directly in their final buffers
-                n_ih, n_hh = f"{prefix}.weight_ih_l{l}", f"{prefix}.weight_hh_l{l}"
-                ops.linear_wgrad(dt, da2, x2, sink.buf(n_ih, (4 * H, In)))
-                sink.done(n_ih)
-                ops.lstm_wgrad_hh(dt, da, s["h_all"], sink.buf(n_hh, (4 * H, H)).view(1, 4 * H, H), H, 1)
-                sink.done(n_hh)
-                db = sink.buf(f"{prefix}.bias_ih_l{l}", (4 * H,))
-                ops.colsum(dt, da2, db)
-                sink.done(f"{prefix}.bias_ih_l{l}")
-                ops.copy_f32(db, sink.buf(f"{prefix}.bias_hh_l{l}", (4 * H,)))   # b_ih and b_hh: equal gradients
-                sink.done(f"{prefix}.bias_hh_l{l}")
-            else:        # both directions come out of one GEMM; slice per direction
-                dwih = torch.zeros((D * 4 * H, In), device=da.device, dtype=torch.float32)
-                ops.linear_wgrad(dt, da2, x2, dwih)
-                dwhh = torch.zeros((D, 4 * H, H), device=da.device, dtype=torch.float32)
-                ops.lstm_wgrad_hh(dt, da, s["h_all"], dwhh, H, D)
-                db = torch.zeros((D * 4 * H,), device=da.device, dtype=torch.float32)
-                ops.colsum(dt, da2, db)
-                for d in range(D):
-                    suf = "_reverse" if d == 1 else ""
-                    sl = slice(d * 4 * H, (d + 1) * 4 * H)
-                    sink.put(f"{prefix}.weight_ih_l{l}{suf}", dwih[sl])
-                    sink.put(f"{prefix}.weight_hh_l{l}{suf}", dwhh[d])
-                    sink.put(f"{prefix}.bias_ih_l{l}{suf}", db[sl])
-                    sink.put(f"{prefix}.bias_hh_l{l}{suf}", db[sl].clone())
+        if D == 1:   # gradients land directly in their final buffers
+            n_ih, n_hh = f"{prefix}.weight_ih_l{l}", f"{prefix}.weight_hh_l{l}"
+            ops.linear_wgrad(dt, da2, x2, sink.buf(n_ih, (4 * H, In)))
+            sink.done(n_ih)
+            ops.lstm_wgrad_hh(dt, da, s["h_all"], sink.buf(n_hh, (4 * H, H)).view(1, 4 * H, H), H, 1)
+            sink.done(n_hh)
+            db = sink.buf(f"{prefix}.bias_ih_l{l}", (4 * H,))
+            ops.colsum(dt, da2, db)
+            sink.done(f"{prefix}.bias_ih_l{l}")
+            ops.copy_f32(db, sink.buf(f"{prefix}.bias_hh_l{l}", (4 * H,)))   # b_ih and b_hh: equal gradients
+            sink.done(f"{prefix}.bias_hh_l{l}")
+        else:        # both directions come out of one GEMM; slice per direction
+            dwih = torch.zeros((D * 4 * H, In), device=da.device, dtype=torch.float32)
+            ops.linear_wgrad(dt, da2, x2, dwih)
+            dwhh = torch.zeros((D, 4 * H, H), device=da.device, dtype=torch.float32)
+            ops.lstm_wgrad_hh(dt, da, s["h_all"], dwhh, H, D)
+            db = torch.zeros((D * 4 * H,), device=da.device, dtype=torch.float32)
+            ops.colsum(dt, da2, db)
+            for d in range(D):
+                suf = "_reverse" if d == 1 else ""
+                sl = slice(d * 4 * H, (d + 1) * 4 * H)
+                sink.put(f"{prefix}.weight_ih_l{l}{suf}", dwih[sl])
+                sink.put(f"{prefix}.weight_hh_l{l}{suf}", dwhh[d])
+                sink.put(f"{prefix}.bias_ih_l{l}{suf}", db[sl])
+                sink.put(f"{prefix}.bias_hh_l{l}{suf}", db[sl].clone())
 
     def _linear_bwd(self, name: str, W_act: Tensor, dy: Tensor, x: Tensor, sink: GradSink, relu_mask=None,
                     want_f32=False, need_dx: bool = True):
