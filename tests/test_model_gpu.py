@@ -243,3 +243,49 @@ def test_device_prefetcher_order_and_values():
     s = AsyncScalars(3, torch.device("cuda"))
     outs = [s.push(torch.tensor([i, 2.0 * i, 3.0 * i], device="cuda")) for i in range(4)] + [s.flush()]
     assert outs[0] is None and outs[1:] == [[float(i), 2.0 * i, 3.0 * i] for i in range(4)]
+
+
+@pytest.mark.parametrize("name", DTS)
+def test_full_size_step_equals_replicated_small_step(name):
+    """BASELINE config 2 size (R = 512 rows per call, 1024 rows in flight: persistent CTA-pair GEMMs, split-K reductions,
+    fused BatchNorm statistics, 128-CTA LSTM step kernels) through a size-independent property: a batch that repeats an
+    R = 8 batch 64 times, with `batch_size` scaled accordingly, has the same BatchNorm statistics, the same per-row outputs,
+    the same loss terms and the same parameter gradients as the R = 8 step -- which test_train_step_parity pins on the
+    oracle."""
+    from oracle import dvae_oracle as O
+    Rs, reps = 8, 64
+    sd = O.synth_state_dict(0)
+    x1, x2, eps = O.synth_inputs(Rs)
+    x1, x2, eps = x1.cuda(), x2.cuda(), [e.cuda() for e in eps]
+
+    def run(R, a, b, noise):
+        w = _build(name, R, sd)
+        queue = list(noise)
+        w.model.noise_hook = lambda shape: queue.pop(0)
+        w.model.train()
+        out = w.model(a, b)
+        losses = w.loss_functionGVAE2(a, b, *out)
+        losses[0].backward()
+        return [t.detach() for t in out], [l.item() for l in losses], {k: p.grad.clone() for k, p in w.model.named_parameters()}
+    o_s, l_s, g_s = run(Rs, x1, x2, eps)
+    rep = lambda t: t.repeat(reps, *([1] * (t.dim() - 1)))
+    o_b, l_b, g_b = run(Rs * reps, rep(x1), rep(x2), [rep(e) for e in eps])
+    # bf16: a last-bit change of a BatchNorm statistic moves stored values by one ulp, and the postnet residual
+    # (outputs 2, 3) amplifies upstream differences ~3x (DESIGN.md section 5)
+    tol = {"bf16": (2e-2, 5e-2), "tf32": (2e-3, 6e-3)}[name]
+    for i, (a, b) in enumerate(zip(o_s, o_b)):
+        assert b.shape[0] == Rs * reps
+        for blk in (0, reps // 2, reps - 1):         # first, middle and last replica
+            d = (b[blk * Rs:(blk + 1) * Rs] - a).norm().item() / a.norm().item()
+            assert d <= tol[1 if i in (2, 3) else 0], (i, blk, d)
+    for a, b in zip(l_s, l_b):
+        assert abs(a - b) <= (4e-3 if name == "bf16" else 5e-4) * max(abs(a), 1e-3), (a, b)
+    dot = na = nb = 0.0
+    for k in g_s:
+        a, b = g_s[k].flatten().double(), g_b[k].flatten().double()
+        dot, na, nb = dot + (a * b).sum().item(), na + (a * a).sum().item(), nb + (b * b).sum().item()
+    cos, ratio = dot / (na * nb) ** 0.5, (nb / na) ** 0.5
+    # The two runs take their own ReLU / L1 branch decisions, and rounding-level differences flip a few of them: this is
+    # the "free decisions" regime of DESIGN.md section 5 (0.973 bf16 / 0.997 tf32 against the oracle), not exact equality.
+    assert cos > (0.95 if name == "bf16" else 0.995), cos
+    assert abs(ratio - 1.0) < (5e-2 if name == "bf16" else 1e-2), ratio
