@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DVAE_B200_PRECISION", "bf16"), choices=["bf16", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("DVAE_B200_PRECISION", "fp16"), choices=["fp16", "bf16", "tf32"])
     ap.add_argument("--pairs", type=int, default=256, help="pairs per step per GPU (BASELINE config 2: 256)")
     ap.add_argument("--frames", type=int, default=128, help="frames per segment (split into 64-frame chunks)")
     ap.add_argument("--cpu-rows", type=int, default=32, help="rows per call of the bounded CPU-baseline sample")
@@ -254,7 +254,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant tensor-core kernel, timed live: the 512->512 k=5 implicit-GEMM conv (8 of 11 convs,
     # fwd + dgrad + wgrad all run this kernel family) at the step's own shape [2R, 64, 512]
-    dt = lib.BF16 if args.precision == "bf16" else lib.TF32
+    dt = {"bf16": lib.BF16, "fp16": lib.F16, "tf32": lib.TF32}[args.precision]
     ad = ops.act_dtype(dt)
     xs = [torch.randn(2 * R, 64, 512, device=dev).to(ad) for _ in range(3)]   # rotate buffers: 3 x 64 MB (bf16) > L2 with outputs
     wk = (torch.randn(512, 5, 512, device=dev) * 0.02).to(ad)
@@ -276,18 +276,18 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak_tf = peaks.get("bf16_tflops", 1590.0) * (1.0 if args.precision == "bf16" else 0.5)
+    peak_tf = peaks.get("bf16_tflops", 1590.0) * (0.5 if args.precision == "tf32" else 1.0)
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "tc_gemm_persistent_kernel<BLOCK_N=256, cta_group::2 pairs> conv5 fwd 512->512", "achieved": achieved,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full capture
                 # (profiles/r01_ncu_gemm_v1.txt): 102.8 MB + 35.3 MB; algorithmic = 67.1 (x) + 2.6 (w) + 67.1 (y) MB
-                "traffic": 128.1e6 if (args.precision == "bf16" and R == 512) else None,   # dram rd+wr, profiles/r01_ncu_targets_v3.txt
+                "traffic": 128.1e6 if (args.precision != "tf32" and R == 512) else None,   # dram rd+wr, profiles/r01_ncu_targets_v3.txt
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1.59 PF")
-                + ("" if args.precision == "bf16" else " x 0.5 for kind::tf32"),
+                + (" x 0.5 for kind::tf32" if args.precision == "tf32" else ""),
                 "flops_per_launch": conv_flops, "ms_per_launch": conv_ms}
     step_flops = 168.56e6 * frames_per_step
-    sustained = peaks.get("bf16_tflops_sustained", 1400.0) * (1.0 if args.precision == "bf16" else 0.5)
+    sustained = peaks.get("bf16_tflops_sustained", 1400.0) * (0.5 if args.precision == "tf32" else 1.0)
     step_frac = step_flops / (ms_per_step * 1e-3) / 1e12 / sustained
 
     cpu_baseline = None

@@ -8,6 +8,7 @@ torch.nn sub-modules are parameter containers only.  Unlike the reference, impor
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -92,23 +93,40 @@ class Generator(nn.Module):
         self.decoder = Decoder(dim_neck, dim_emb, dim_pre)
         self.postnet = Postnet()
         self._dt = _precision_tag(precision)
-        self._engine = Engine(self._dt, dim_emb, 1)
+        # fp16 storage carries the gradient stream scaled (see Engine.grad_scale); there is no loss in the reference to
+        # derive a default from, so a mean-reduced loss over ~10^6 elements is assumed: override with `.grad_scale = ...`
+        self._engine = Engine(self._dt, dim_emb, 1, grad_scale=float(os.environ.get("DVAE_B200_GRAD_SCALE", 0)) or
+                              (2.0 ** 20 if self._dt == lib.F16 else 1.0))
         self._param_names = [n for n, _ in self.named_parameters()]
         self._prep_cache = None
         self._debug_keep_saved = False
         self._last_saved = None
 
+    @property
+    def grad_scale(self) -> float:
+        return self._engine.grad_scale
+
+    @grad_scale.setter
+    def grad_scale(self, v: float) -> None:
+        self._engine.grad_scale = float(v)
+
     def _prepared(self) -> PreparedWeights:
+        """See DisentangledVAE._prepared: rebuilt on re-allocation, refreshed in place when a parameter was written."""
         params = list(self.parameters())
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        if self._prep_cache is None or self._prep_cache[0] != key:
+        ptrs = tuple(p.data_ptr() for p in params)
+        vers = tuple(p._version for p in params)
+        c = self._prep_cache
+        P = {n: p.data for n, p in self.named_parameters()}
+        if c is None or c[0] != ptrs:
             if params[0].device.type != "cuda":
                 raise RuntimeError("dvae_b200 runs on CUDA (sm_100a) only: move the module with .to('cuda'); there is no CPU path")
-            P = {n: p.data for n, p in self.named_parameters()}
-            W = PreparedWeights(self._dt, P, convs=[c for c, _, _ in ENC_CONVS + DEC_CONVS + POST_CONVS], linears=LINEARS,
+            W = PreparedWeights(self._dt, P, convs=[c_ for c_, _, _ in ENC_CONVS + DEC_CONVS + POST_CONVS], linears=LINEARS,
                                 lstms=LSTMS, fused_heads=False)
-            self._prep_cache = (key, W)
-        return self._prep_cache[1]
+            c = self._prep_cache = [ptrs, vers, W]
+        elif c[1] != vers:
+            c[2].refresh(P)
+            c[1] = vers
+        return c[2]
 
     # ------------------------------------------------------------------ schedule
     def _run_forward(self, x, keep):
@@ -153,11 +171,11 @@ class Generator(nn.Module):
         d_post = torch.zeros(shape, device=dev, dtype=ad)
         d_rec = torch.zeros(shape, device=dev, dtype=ad)
         if g_post is not None:
-            ops.prep_cast(dt, g_post.contiguous().view(shape), d_post)
-            ops.prep_cast(dt, g_post.contiguous().view(shape), d_rec)
+            ops.prep_cast(dt, g_post.contiguous().view(shape), d_post, scale=E.grad_scale)
+            ops.prep_cast(dt, g_post.contiguous().view(shape), d_rec, scale=E.grad_scale)
         if g_mel is not None:
             tmp = torch.empty(shape, device=dev, dtype=ad)
-            ops.prep_cast(dt, g_mel.contiguous().view(shape), tmp)
+            ops.prep_cast(dt, g_mel.contiguous().view(shape), tmp, scale=E.grad_scale)
             ops.add_inplace(dt, d_rec, tmp)
         d_in = E._conv_stack_bwd(W, d_post, saved["post_convs"], sink, 1, need_dx=True)
         ops.add_inplace(dt, d_rec, d_in)

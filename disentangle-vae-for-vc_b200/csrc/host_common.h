@@ -9,7 +9,8 @@
 
 namespace dvae {
 
-enum DType : int { kBF16 = 0, kTF32 = 1 };  // activation storage: bf16 (kind::f16 MMA) or fp32 (kind::tf32 MMA)
+// activation storage: bf16 or fp16 (tcgen05 kind::f16), or fp32 kept on the tf32 grid (kind::tf32)
+enum DType : int { kBF16 = 0, kTF32 = 1, kF16 = 2 };
 
 void set_last_error(const std::string& msg);
 

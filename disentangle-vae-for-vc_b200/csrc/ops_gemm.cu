@@ -12,8 +12,10 @@
 // Reference call sites (model/disentangled_vae.py): Conv1d :154-160,:178-189,:54-78; LSTM :163,:172,:193;
 // Linear :165-171,:194.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "host_common.h"
 #include "tc_gemm.cuh"
@@ -22,6 +24,8 @@ namespace dvae {
 
 static int env_int(const char* name, int dflt);
 static int g_background_flag();
+template <typename AT>
+constexpr int kIsF16 = std::is_same<AT, __half>::value ? 1 : 0;
 
 template <int BN>
 struct Stages {
@@ -234,6 +238,7 @@ static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, A
   wa.per_j[0] = BK; wa.per_tile[1] = 128;
   wb.per_j[0] = BK; wb.per_tile[1] = BN;
   GemmShape shp{M, N, ceil_div(K, BK), ceil_div(K, BK), 1};
+  shp.f16 = kIsF16<AT>;
   typename EpiStore<AT>::Params ep{out, out_f32, bias, nullptr, ldo, 0, relu};
   const int mt = pick_mt(M, ceil_div(N, BN));
   dim3 grid(ceil_div(M, 128 * mt), ceil_div(N, BN), 1);
@@ -292,6 +297,7 @@ static int linear_dgrad_t(const AT* dy, long lddy, const AT* w, AT* dx, float* d
   wa.per_j[0] = BK; wa.per_tile[1] = 128;
   wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN;
   GemmShape shp{M, K, ceil_div(N, BK), ceil_div(N, BK), 1};
+  shp.f16 = kIsF16<AT>;
   typename EpiStore<AT>::Params ep{dx, dx_f32, nullptr, relu_mask, ldx, 0, 0};
   const int mt = pick_mt(M, ceil_div(K, BN));
   dim3 grid(ceil_div(M, 128 * mt), ceil_div(K, BN), 1);
@@ -361,7 +367,7 @@ static int pick_splits_persistent(int tiles, int num_kb) {
 
 template <typename AT>
 static int linear_wgrad_t(const AT* dy, long lddy, const AT* x, long ldx, float* dw, long lddw, int M, int N, int K,
-                          cudaStream_t st) {
+                          float alpha, cudaStream_t st) {
   // dw[N,K] += dy[M,N]^T . x[M,K]   (reduction over the M rows; both operands MN-major)
   constexpr int EB = sizeof(AT);
   constexpr int BK = 128 / EB;
@@ -383,7 +389,8 @@ static int linear_wgrad_t(const AT* dy, long lddy, const AT* x, long ldx, float*
     if (want_persistent(probe) || wide) splits = pick_splits_persistent(tiles, num_kb);
   }
   GemmShape shp{N, K, num_kb, num_kb, splits};
-  EpiAtomic::Params ep{dw, lddw, 0};
+  shp.f16 = kIsF16<AT>;
+  EpiAtomic::Params ep{dw, lddw, 0, alpha};
   dim3 grid(ceil_div(N, 128), ceil_div(K, BN), shp.splits);
   if (wide && gemm_pair(grid.x, BN)) return launch_gemm_persistent<256, true, true, EB, EpiAtomic, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   if (wide) return launch_gemm_persistent<256, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -437,6 +444,7 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
   }
   const int kpt = ceil_div(Ca, BK);
   GemmShape shp{R * T, Cn, 5 * kpt, kpt, 1};
+  shp.f16 = kIsF16<AT>;
   typename EpiStore<AT>::Params ep{y, y_f32, bias, nullptr, (long)Cn, 0, 0};
   static const int fuse_env = env_int("DVAE_BN_FUSE_STATS", 1);
   const bool want_stats = fuse_env != 0 && bn_sums != nullptr && !dgrad && rows_half > 0 && rows_half % 128 == 0;
@@ -524,7 +532,7 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
 }
 
 template <typename AT>
-static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, int Cin, int Cout, cudaStream_t st) {
+static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, int Cin, int Cout, float alpha, cudaStream_t st) {
   // dwk[co][k][ci] += sum_{r,t} dy[r,t,co] x[r,t+k-2,ci];  one GEMM batch (blockIdx.z) per tap, split-K over sequences
   constexpr int EB = sizeof(AT);
   constexpr int BK = 128 / EB;
@@ -551,7 +559,8 @@ static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, in
     if (want_persistent(probe) || wide) splits = pick_splits_persistent(tiles, num_kb);
   }
   GemmShape shp{Cout, Cin, num_kb, kpt, splits};
-  EpiAtomic::Params ep{dwk, (long)5 * Cin, (long)Cin};
+  shp.f16 = kIsF16<AT>;
+  EpiAtomic::Params ep{dwk, (long)5 * Cin, (long)Cin, alpha};
   dim3 grid(ceil_div(Cout, 128), ceil_div(Cin, BN), 5 * shp.splits);
   if (wide && gemm_pair(grid.x, BN)) return launch_gemm_persistent<256, true, true, EB, EpiAtomic, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   if (wide) return launch_gemm_persistent<256, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -646,6 +655,7 @@ static int lstm_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int rows
     wa.base[1] = tf - 1; wa.per_j[0] = BK; wa.per_tile[2] = 128; wa.per_z[0] = H; wa.per_z[1] = (tr + 1) - (tf - 1);
     wb.per_j[0] = BK; wb.per_tile[1] = BN; wb.per_z[2] = 1;
     GemmShape shp{rows, 4 * H, s == 0 ? 0 : H / BK, H / BK, 1};
+    shp.f16 = kIsF16<AT>;
     auto fill = [&](typename EpiLstmFwd<AT>::Params& ep) {
       ep.xproj = xg + (long)tf * D * 4 * H;
       ep.gates = xg + (long)tf * D * 4 * H;
@@ -790,6 +800,7 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
         if (reduce) {
           wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = RBN; wb.per_z[2] = 1;
           GemmShape shp{rows, H, 4 * H / BK, 4 * H / BK, rsplits, nullptr, nullptr};
+          shp.f16 = kIsF16<AT>;
           EpiReduceTma::Params ep{trec};
           dim3 grid(ceil_div(rows, 128), H / RBN, D * rsplits);
           int e;
@@ -804,6 +815,7 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
           wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN; wb.per_z[2] = 1;
           const int splits = splitk_ws == nullptr ? 1 : lstm_bwd_splits(rows, H, D, EB);
           GemmShape shp{rows, H, 4 * H / BK, 4 * H / BK, splits, splitk_ws, tickets};
+          shp.f16 = kIsF16<AT>;
           typename EpiStore<AT>::Params ep{nullptr, dh_rec, nullptr, nullptr, (long)H, (long)rows * H, 0};
           dim3 grid(ceil_div(rows, 128), H / BN, D * splits);
           int e = (BN == 256)   ? launch_gemm<256, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st)
@@ -844,6 +856,7 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
     wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = BN; wb.per_z[2] = 1;
     const int splits = (s == 0 || splitk_ws == nullptr) ? 1 : lstm_bwd_splits(rows, H, D, EB);
     GemmShape shp{rows, H, s == 0 ? 0 : 4 * H / BK, 4 * H / BK, splits, splitk_ws, tickets};
+    shp.f16 = kIsF16<AT>;
     typename EpiLstmBwd<AT>::Params ep;
     ep.dh_out = dh_all + (long)tf * D * H;
     ep.gates = gates + (long)tf * D * 4 * H;
@@ -870,7 +883,8 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
 
 // dW_hh[d][4H][H] += sum_{r,t} da[r,t,d,:]^T h_prev[r,t,d,:]  with h_prev = h[t-1] (forward dir) / h[t+1] (reverse)
 template <typename AT>
-static int lstm_wgrad_hh_t(const AT* da_all, const AT* h_all, float* dwhh, int rows, int T, int H, int D, cudaStream_t st) {
+static int lstm_wgrad_hh_t(const AT* da_all, const AT* h_all, float* dwhh, int rows, int T, int H, int D, float alpha,
+                           cudaStream_t st) {
   constexpr int EB = sizeof(AT);
   constexpr int BK = 128 / EB;
   DVAE_REQUIRE(T % BK == 0, "T must be a multiple of the k-block");
@@ -890,7 +904,8 @@ static int lstm_wgrad_hh_t(const AT* da_all, const AT* h_all, float* dwhh, int r
   const int kpt = T / BK, num_kb = rows * kpt;
   const int tiles = ceil_div(4 * H, 128) * ceil_div(H, BN) * D;
   GemmShape shp{4 * H, H, num_kb, kpt, wide ? pick_splits_persistent(tiles, num_kb) : pick_splits(tiles, num_kb)};
-  EpiAtomic::Params ep{dwhh, (long)H, (long)4 * H * H};
+  shp.f16 = kIsF16<AT>;
+  EpiAtomic::Params ep{dwhh, (long)H, (long)4 * H * H, alpha};
   dim3 grid(ceil_div(4 * H, 128), ceil_div(H, BN), D * shp.splits);
   if (wide && gemm_pair(grid.x, BN)) return launch_gemm_persistent<256, true, true, EB, EpiAtomic, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   if (wide) return launch_gemm_persistent<256, true, true, EB, EpiAtomic>(ta, tb, wa, wb, shp, ep, grid, st);
@@ -900,13 +915,28 @@ static int lstm_wgrad_hh_t(const AT* da_all, const AT* h_all, float* dwhh, int r
 
 }  // namespace dvae
 
+namespace dvae {
+template <typename AT>
+static int conv5_fwd_bnstats_t(int dtype, const void* x, const void* wk, const float* bias, void* y, int R, int T, int Cin, int Cout,
+                               double* bn_ws, int rows_half, int halves, cudaStream_t st) {
+  bool fused = false;
+  if (int e = conv5_fwd_t<AT>((const AT*)x, (const AT*)wk, bias, (AT*)y, nullptr, R, T, Cin, Cout, false, st, bn_ws, rows_half, &fused))
+    return e;
+  if (!fused) return bn_stats_launch(dtype, y, bn_ws, rows_half, halves, Cout, st);
+  return 0;
+}
+}  // namespace dvae
+
 using namespace dvae;
 using bf16 = __nv_bfloat16;
+using f16 = __half;
 
-#define DISPATCH_DTYPE(dtype, CALL_BF16, CALL_F32)                      \
+// `AT` is the activation storage type selected by the dtype tag: bf16 / fp16 (tcgen05 kind::f16) or fp32 on the tf32 grid
+#define DISPATCH_AT(dtype, ...)                                         \
   do {                                                                  \
-    if ((dtype) == kBF16) return CALL_BF16;                             \
-    if ((dtype) == kTF32) return CALL_F32;                              \
+    if ((dtype) == kBF16) { using AT = bf16; return __VA_ARGS__; }      \
+    if ((dtype) == kF16) { using AT = f16; return __VA_ARGS__; }        \
+    if ((dtype) == kTF32) { using AT = tf32_t; return __VA_ARGS__; }    \
     set_last_error("unknown dtype tag");                                \
     return 1;                                                           \
   } while (0)
@@ -916,31 +946,26 @@ extern "C" {
 int dvae_linear_fwd(int dtype, const void* x, long ldx, const void* w, const float* bias, void* out, float* out_f32,
                     long ldo, int M, int N, int K, int relu, int block_n, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype,
-                 linear_fwd_t<bf16>((const bf16*)x, ldx, (const bf16*)w, bias, (bf16*)out, out_f32, ldo, M, N, K, relu, block_n, st),
-                 linear_fwd_t<tf32_t>((const tf32_t*)x, ldx, (const tf32_t*)w, bias, (tf32_t*)out, out_f32, ldo, M, N, K, relu, block_n, st));
+  DISPATCH_AT(dtype, linear_fwd_t<AT>((const AT*)x, ldx, (const AT*)w, bias, (AT*)out, out_f32, ldo, M, N, K, relu, block_n, st));
 }
 
 int dvae_linear_dgrad(int dtype, const void* dy, long lddy, const void* w, void* dx, float* dx_f32, const void* relu_mask,
                       long ldx, int M, int N, int K, int block_n, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype,
-                 linear_dgrad_t<bf16>((const bf16*)dy, lddy, (const bf16*)w, (bf16*)dx, dx_f32, (const bf16*)relu_mask, ldx, M, N, K, block_n, st),
-                 linear_dgrad_t<tf32_t>((const tf32_t*)dy, lddy, (const tf32_t*)w, (tf32_t*)dx, dx_f32, (const tf32_t*)relu_mask, ldx, M, N, K, block_n, st));
+  DISPATCH_AT(dtype, linear_dgrad_t<AT>((const AT*)dy, lddy, (const AT*)w, (AT*)dx, dx_f32, (const AT*)relu_mask, ldx, M, N, K, block_n, st));
 }
 
+// alpha scales what is added to dw (1 / gradient scale of the fp16 mode; 1 otherwise)
 int dvae_linear_wgrad(int dtype, const void* dy, long lddy, const void* x, long ldx, float* dw, long lddw, int M, int N,
-                      int K, void* stream) {
+                      int K, float alpha, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype, linear_wgrad_t<bf16>((const bf16*)dy, lddy, (const bf16*)x, ldx, dw, lddw, M, N, K, st),
-                 linear_wgrad_t<tf32_t>((const tf32_t*)dy, lddy, (const tf32_t*)x, ldx, dw, lddw, M, N, K, st));
+  DISPATCH_AT(dtype, linear_wgrad_t<AT>((const AT*)dy, lddy, (const AT*)x, ldx, dw, lddw, M, N, K, alpha, st));
 }
 
 int dvae_conv5_fwd(int dtype, const void* x, const void* wk, const float* bias, void* y, float* y_f32, int R, int T, int Cin,
                    int Cout, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype, conv5_fwd_t<bf16>((const bf16*)x, (const bf16*)wk, bias, (bf16*)y, y_f32, R, T, Cin, Cout, false, st),
-                 conv5_fwd_t<tf32_t>((const tf32_t*)x, (const tf32_t*)wk, bias, (tf32_t*)y, y_f32, R, T, Cin, Cout, false, st));
+  DISPATCH_AT(dtype, conv5_fwd_t<AT>((const AT*)x, (const AT*)wk, bias, (AT*)y, y_f32, R, T, Cin, Cout, false, st));
 }
 
 // Convolution + the statistics pass of the train-mode BatchNorm that follows it (ConvNorm -> BatchNorm1d,
@@ -951,40 +976,26 @@ int dvae_conv5_fwd_bnstats(int dtype, const void* x, const void* wk, const float
   auto st = static_cast<cudaStream_t>(stream);
   DVAE_REQUIRE(bn_ws != nullptr && halves >= 1 && (long)rows_half * halves == (long)R * T, "rows_half * halves must equal R * T");
   DVAE_CHECK_CUDA(cudaMemsetAsync(bn_ws, 0, sizeof(double) * ((long)halves * 2 * Cout + 1), st));
-  bool fused = false;
-  int e;
-  if (dtype == kBF16)
-    e = conv5_fwd_t<bf16>((const bf16*)x, (const bf16*)wk, bias, (bf16*)y, nullptr, R, T, Cin, Cout, false, st, bn_ws, rows_half, &fused);
-  else if (dtype == kTF32)
-    e = conv5_fwd_t<tf32_t>((const tf32_t*)x, (const tf32_t*)wk, bias, (tf32_t*)y, nullptr, R, T, Cin, Cout, false, st, bn_ws, rows_half, &fused);
-  else {
-    set_last_error("unknown dtype tag");
-    return 1;
-  }
-  if (e) return e;
-  if (!fused) return bn_stats_launch(dtype, y, bn_ws, rows_half, halves, Cout, st);
-  return 0;
+  DISPATCH_AT(dtype, conv5_fwd_bnstats_t<AT>(dtype, x, wk, bias, y, R, T, Cin, Cout, bn_ws, rows_half, halves, st));
 }
 
 int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,
                      void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype, conv5_fwd_t<bf16>((const bf16*)dy, (const bf16*)wk, nullptr, (bf16*)dx, dx_f32, R, T, Cin, Cout, true, st),
-                 conv5_fwd_t<tf32_t>((const tf32_t*)dy, (const tf32_t*)wk, nullptr, (tf32_t*)dx, dx_f32, R, T, Cin, Cout, true, st));
+  DISPATCH_AT(dtype, conv5_fwd_t<AT>((const AT*)dy, (const AT*)wk, nullptr, (AT*)dx, dx_f32, R, T, Cin, Cout, true, st));
 }
 
-int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R, int T, int Cin, int Cout, void* stream) {
+int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R, int T, int Cin, int Cout, float alpha,
+                     void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype, conv5_wgrad_t<bf16>((const bf16*)dy, (const bf16*)x, dwk, R, T, Cin, Cout, st),
-                 conv5_wgrad_t<tf32_t>((const tf32_t*)dy, (const tf32_t*)x, dwk, R, T, Cin, Cout, st));
+  DISPATCH_AT(dtype, conv5_wgrad_t<AT>((const AT*)dy, (const AT*)x, dwk, R, T, Cin, Cout, alpha, st));
 }
 
 int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_all, int rows, int T, int H, int D,
                   void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   if (lstm_seq_supported(H, T)) return lstm_seq_fwd(dtype, xg, whh_p, h_all, c_all, rows, T, H, D, st);
-  DISPATCH_DTYPE(dtype, lstm_fwd_t<bf16>((bf16*)xg, (const bf16*)whh_p, (bf16*)h_all, c_all, rows, T, H, D, st),
-                 lstm_fwd_t<tf32_t>((tf32_t*)xg, (const tf32_t*)whh_p, (tf32_t*)h_all, c_all, rows, T, H, D, st));
+  DISPATCH_AT(dtype, lstm_fwd_t<AT>((AT*)xg, (const AT*)whh_p, (AT*)h_all, c_all, rows, T, H, D, st));
 }
 
 // splitk_ws / tickets: fix-up workspace for the split-K backward step (sizes from dvae_lstm_bwd_workspace); may be
@@ -993,13 +1004,12 @@ int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float*
                   float* dc_ws, float* splitk_ws, int* tickets, int rows, int T, int H, int D, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   if (lstm_seq_supported(H, T)) return lstm_seq_bwd(dtype, dh_all, gates, c_all, whh_n, da_all, rows, T, H, D, st);
-  DISPATCH_DTYPE(dtype,
-                 lstm_bwd_t<bf16>((const bf16*)dh_all, (const bf16*)gates, c_all, (const bf16*)whh_n, (bf16*)da_all, dc_ws, splitk_ws, tickets, rows, T, H, D, st),
-                 lstm_bwd_t<tf32_t>((const tf32_t*)dh_all, (const tf32_t*)gates, c_all, (const tf32_t*)whh_n, (tf32_t*)da_all, dc_ws, splitk_ws, tickets, rows, T, H, D, st));
+  DISPATCH_AT(dtype, lstm_bwd_t<AT>((const AT*)dh_all, (const AT*)gates, c_all, (const AT*)whh_n, (AT*)da_all, dc_ws, splitk_ws,
+                                    tickets, rows, T, H, D, st));
 }
 // floats of fix-up workspace and number of tickets dvae_lstm_bwd wants for this shape (0 floats: no split-K)
 int dvae_lstm_bwd_workspace(int dtype, int rows, int H, int D, long* ws_floats, int* num_tickets) {
-  const int eb = dtype == kBF16 ? 2 : 4;
+  const int eb = dtype == kTF32 ? 4 : 2;
   const int bn = lstm_bwd_bn(H);
   const int tiles = ceil_div(rows, 128) * (H / bn) * D;
   const int splits = lstm_bwd_splits(rows, H, D, eb);
@@ -1009,10 +1019,9 @@ int dvae_lstm_bwd_workspace(int dtype, int rows, int H, int D, long* ws_floats, 
 }
 
 int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* dwhh, int rows, int T, int H, int D,
-                       void* stream) {
+                       float alpha, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype, lstm_wgrad_hh_t<bf16>((const bf16*)da_all, (const bf16*)h_all, dwhh, rows, T, H, D, st),
-                 lstm_wgrad_hh_t<tf32_t>((const tf32_t*)da_all, (const tf32_t*)h_all, dwhh, rows, T, H, D, st));
+  DISPATCH_AT(dtype, lstm_wgrad_hh_t<AT>((const AT*)da_all, (const AT*)h_all, dwhh, rows, T, H, D, alpha, st));
 }
 
 int dvae_lstm_gate_tile(int H) { return lstm_fwd_bn(H); }

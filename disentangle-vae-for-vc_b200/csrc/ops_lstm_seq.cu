@@ -20,6 +20,7 @@
 //   xg / gates [rows, T, D*4H] gate-interleaved (column 4u + g), h_all / c_all [rows, T, D*H],
 //   da_all [rows, T, D*4H] natural torch order (g*H + u), whh_p [D][4H][H] interleaved rows, whh_n [D][4H][H] natural.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -46,6 +47,11 @@ struct PackChunks<__nv_bfloat16> {
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
   }
+};
+template <>
+struct PackChunks<__half> {
+  static constexpr int kPer8 = 1;
+  static __device__ __forceinline__ void pack(const float* v, uint4* out) { *out = pack8_16<__half>(v); }
 };
 template <>
 struct PackChunks<tf32_t> {
@@ -98,7 +104,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmW, AT* __restrict__ xg
   constexpr int KB = H / BK;             // k-blocks: 1 (bf16) / 2 (tf32)
   constexpr int UMMA_K = 32 / EB;
   constexpr int TILE_W = 4 * H * 128;    // 256 weight rows x 128 B
-  constexpr uint32_t IDESC = instr_desc<EB, 4 * H, false, false>();
+  constexpr uint32_t IDESC = instr_desc_fmt<MmaFmt<AT>::value, 4 * H, false, false>();
   constexpr int TMEM_COLS = 4 * H;
 
   extern __shared__ uint8_t smem_raw[];
@@ -260,7 +266,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmW, const AT* __restric
   constexpr uint32_t MN_LAYOUT = (EB == 4) ? 1u : 2u;
   constexpr uint32_t MN_SBO = (EB == 4) ? 512u : 1024u;
   constexpr uint32_t ADV_B = (UMMA_K * 128) >> 4;
-  constexpr uint32_t IDESC = instr_desc<EB, H, false, true>();
+  constexpr uint32_t IDESC = instr_desc_fmt<MmaFmt<AT>::value, H, false, true>();
   constexpr int TMEM_COLS = H;
 
   extern __shared__ uint8_t smem_raw[];
@@ -470,6 +476,11 @@ template <> struct ChunkCvt<__nv_bfloat16> {
     return u;
   }
 };
+template <> struct ChunkCvt<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void unpack(const uint4& u, float* v) { Act8<__half>::unpack(u, v); }
+  static __device__ __forceinline__ uint4 pack(const float* v) { return pack8_16<__half>(v); }
+};
 template <> struct ChunkCvt<float> {
   static constexpr int N = 4;
   static __device__ __forceinline__ void unpack(const uint4& u, float* v) {
@@ -519,7 +530,7 @@ lstm_seq_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_co
   constexpr int KB = H / BK;
   constexpr int UMMA_K = 32 / EB;
   constexpr int TILE_W = 4 * H * 128;
-  constexpr uint32_t IDESC = instr_desc<EB, 4 * H, false, false>();
+  constexpr uint32_t IDESC = instr_desc_fmt<MmaFmt<AT>::value, 4 * H, false, false>();
   constexpr int TMEM_COLS = 4 * H;
   constexpr int X_BOXES = 4 * H * EB / 128, X_BYTES = X_BOXES * kSeqBoxBytes;
   constexpr int C_BOXES = H * 4 / 128, C_BYTES = C_BOXES * kSeqBoxBytes;
@@ -697,7 +708,7 @@ lstm_seq_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_co
   constexpr uint32_t MN_LAYOUT = (EB == 4) ? 1u : 2u;
   constexpr uint32_t MN_SBO = (EB == 4) ? 512u : 1024u;
   constexpr uint32_t ADV_B = (UMMA_K * 128) >> 4;
-  constexpr uint32_t IDESC = instr_desc<EB, H, false, true>();
+  constexpr uint32_t IDESC = instr_desc_fmt<MmaFmt<AT>::value, H, false, true>();
   constexpr int TMEM_COLS = H;
   constexpr int G_BOXES = 4 * H * EB / 128, G_BYTES = G_BOXES * kSeqBoxBytes;
   constexpr int DH_BOXES = H * EB / 128, DH_BYTES = DH_BOXES * kSeqBoxBytes;
@@ -988,6 +999,7 @@ int lstm_seq_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_a
                  cudaStream_t st) {
   using bf16 = __nv_bfloat16;
   if (dtype == kBF16) return lstm_seq_fwd_t<bf16>((bf16*)xg, (const bf16*)whh_p, (bf16*)h_all, c_all, rows, T, H, D, st);
+  if (dtype == kF16) return lstm_seq_fwd_t<__half>((__half*)xg, (const __half*)whh_p, (__half*)h_all, c_all, rows, T, H, D, st);
   if (dtype == kTF32) return lstm_seq_fwd_t<tf32_t>((tf32_t*)xg, (const tf32_t*)whh_p, (tf32_t*)h_all, c_all, rows, T, H, D, st);
   set_last_error("unknown dtype tag");
   return 1;
@@ -998,6 +1010,8 @@ int lstm_seq_bwd(int dtype, const void* dh_all, const void* gates, const float* 
   using bf16 = __nv_bfloat16;
   if (dtype == kBF16)
     return lstm_seq_bwd_t<bf16>((const bf16*)dh_all, (const bf16*)gates, c_all, (const bf16*)whh_n, (bf16*)da_all, rows, T, H, D, st);
+  if (dtype == kF16)
+    return lstm_seq_bwd_t<__half>((const __half*)dh_all, (const __half*)gates, c_all, (const __half*)whh_n, (__half*)da_all, rows, T, H, D, st);
   if (dtype == kTF32)
     return lstm_seq_bwd_t<tf32_t>((const tf32_t*)dh_all, (const tf32_t*)gates, c_all, (const tf32_t*)whh_n, (tf32_t*)da_all, rows,
                                   T, H, D, st);

@@ -6,6 +6,7 @@
 // variance for normalisation, unbiased for running_var, momentum 0.1, eps 1e-5; statistics are kept PER CALL
 // (x1-call, x2-call = "halves") although both halves live in one tensor here.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "act_types.cuh"
 #include "host_common.h"
@@ -23,16 +24,20 @@ static inline int grid_for(long n, int block, int max_blocks = 148 * 16) {
 
 // ------------------------------------------------------------------------------------ weight preparation
 template <typename AT>
-__global__ void cast_kernel(const float* __restrict__ src, AT* __restrict__ dst, long n) {
+__global__ void cast_kernel(const float* __restrict__ src, AT* __restrict__ dst, long n, float scale) {
   const long stride = static_cast<long>(gridDim.x) * blockDim.x * 8;
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
   for (long i = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (aligned && i + 8 <= n) {
       float v[8];
       Act8<float>::load(src + i, v);
+      if (scale != 1.f) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] *= scale;
+      }
       Act8<AT>::store(dst + i, v);
     } else {
-      for (long j = i; j < n && j < i + 8; ++j) dst[j] = from_f32<AT>(src[j]);
+      for (long j = i; j < n && j < i + 8; ++j) dst[j] = from_f32<AT>(src[j] * scale);
     }
   }
 }
@@ -159,15 +164,15 @@ __global__ void cl_to_ncl_kernel(const TA* __restrict__ a, const TB* __restrict_
 // backward of the residual output: d_rec[r][t][c] = g_rec[r][c][t] + g_hat[r][c][t];  d_post = g_hat  (either may be null)
 template <typename AT>
 __global__ void recon_out_bwd_kernel(const float* __restrict__ g_rec, const float* __restrict__ g_hat, AT* __restrict__ d_rec,
-                                     AT* __restrict__ d_post, int C, int T) {
+                                     AT* __restrict__ d_post, int C, int T, float scale) {
   extern __shared__ float tile[];
   float* ta = tile;
   float* tb = tile + C * (T + 1);
   const long r = blockIdx.x;
   for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
     const int c = i / T, t = i - c * T;
-    const float gh = g_hat ? g_hat[r * C * T + i] : 0.f;
-    const float gr = g_rec ? g_rec[r * C * T + i] : 0.f;
+    const float gh = g_hat ? scale * g_hat[r * C * T + i] : 0.f;
+    const float gr = g_rec ? scale * g_rec[r * C * T + i] : 0.f;
     ta[c * (T + 1) + t] = gr + gh;
     tb[c * (T + 1) + t] = gh;
   }
@@ -384,7 +389,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const AT* __restrict
 }
 // dgamma = sum_h sum dz*xhat, dbeta = sum_h sum dz; coef [halves][2][C] = (sum dz)/n, (sum dz*xhat)/n
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, float* __restrict__ coef, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, int halves, int C, double n) {
+                                       float* __restrict__ dbeta, int halves, int C, double n, double alpha) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double dg = 0.0, db = 0.0;
@@ -394,8 +399,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, float* _
     coef[(h * 2 + 0) * C + c] = static_cast<float>(s / n);
     coef[(h * 2 + 1) * C + c] = static_cast<float>(q / n);
   }
-  dgamma[c] = static_cast<float>(dg);
-  dbeta[c] = static_cast<float>(db);
+  dgamma[c] = static_cast<float>(dg * alpha);
+  dbeta[c] = static_cast<float>(db * alpha);
 }
 // backward pass 2: dy = scale * (dz - mean(dz) - xhat * mean(dz*xhat)); same streaming structure as bn_apply_kernel
 template <typename AT>
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const AT* __restrict_
 
 // ------------------------------------------------------------------------------------ column sums (bias gradients)
 template <typename AT>
-__global__ void colsum_kernel(const AT* __restrict__ x, float* __restrict__ out, long rows, int C, long ldx) {
+__global__ void colsum_kernel(const AT* __restrict__ x, float* __restrict__ out, long rows, int C, long ldx, float alpha) {
   // block = 256 threads; thread owns 8 channels of one row lane; grid.x over row chunks, grid.y over channel chunks of 2048
   const int c0 = blockIdx.y * 2048;
   const int cw = min(2048, C - c0);
@@ -478,7 +483,7 @@ __global__ void colsum_kernel(const AT* __restrict__ x, float* __restrict__ out,
   for (int i = threadIdx.x; i < cw; i += blockDim.x) {
     float acc = 0.f;
     for (int l = 0; l < lanes; ++l) acc += red[l * cw + i];
-    atomicAdd(out + c0 + i, acc);
+    atomicAdd(out + c0 + i, acc * alpha);
   }
 }
 
@@ -489,6 +494,7 @@ using namespace dvae;
 #define DISPATCH_AT(dtype, ...)                              \
   do {                                                       \
     if ((dtype) == kBF16) { using AT = bf16; __VA_ARGS__; }  \
+    else if ((dtype) == kF16) { using AT = __half; __VA_ARGS__; } \
     else if ((dtype) == kTF32) { using AT = tf32_t; __VA_ARGS__; } \
     else { set_last_error("unknown dtype tag"); return 1; }  \
   } while (0)
@@ -515,9 +521,9 @@ int bn_stats_launch(int dtype, const void* y, double* ws, int rows_half, int hal
 
 extern "C" {
 
-int dvae_prep_cast(int dtype, const float* src, void* dst, long n, void* stream) {
+int dvae_prep_cast(int dtype, const float* src, void* dst, long n, float scale, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  DISPATCH_AT(dtype, cast_kernel<AT><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>(src, (AT*)dst, n));
+  DISPATCH_AT(dtype, cast_kernel<AT><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>(src, (AT*)dst, n, scale));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -529,7 +535,7 @@ int dvae_add_f32_act(int dtype, const float* a, const void* b, float* out, long 
 }
 int dvae_copy_f32(const float* src, float* dst, long n, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  cast_kernel<float><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>(src, dst, n);   // exact copy (no tf32 rounding)
+  cast_kernel<float><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>(src, dst, n, 1.f);   // exact copy (no tf32 rounding)
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -589,13 +595,14 @@ int dvae_unpack_cl_to_ncl(int dtype, const void* a, int a_is_f32, const void* b,
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+// scale: the factor the activation-gradient stream is carried at from here on (fp16 mode; 1 otherwise)
 int dvae_recon_out_bwd(int dtype, const float* g_rec, const float* g_hat, void* d_rec, void* d_post, int R, int C, int T,
-                       void* stream) {
+                       float scale, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   if (R == 0) return 0;
   const int smem = 2 * C * (T + 1) * 4;
   DVAE_REQUIRE(smem <= 48 * 1024, "tile must fit 48 KB of shared memory");
-  DISPATCH_AT(dtype, recon_out_bwd_kernel<AT><<<R, 256, smem, st>>>(g_rec, g_hat, (AT*)d_rec, (AT*)d_post, C, T));
+  DISPATCH_AT(dtype, recon_out_bwd_kernel<AT><<<R, 256, smem, st>>>(g_rec, g_hat, (AT*)d_rec, (AT*)d_post, C, T, scale));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -649,8 +656,9 @@ int dvae_bn_eval_fwd(int dtype, const void* y, void* out, const float* gamma, co
   return 0;
 }
 // Train-mode BatchNorm backward (through the activation): dout -> dy, dgamma, dbeta.  coef: fp32 [halves*2*C] scratch.
+// alpha scales the two parameter gradients (1 / gradient scale of the fp16 mode); dy stays at the stream's scale.
 int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* stat, double* ws, float* coef, void* dy,
-                      float* dgamma, float* dbeta, int rows_half, int halves, int C, int act, void* stream) {
+                      float* dgamma, float* dbeta, int rows_half, int halves, int C, int act, float alpha, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DVAE_REQUIRE(C % 8 == 0 && C <= 2048, "C must be a multiple of 8 (<= 2048)");
   DVAE_REQUIRE(rows_half % kBnRowsPerBlock == 0, "rows per half must be a multiple of 64");
@@ -659,14 +667,15 @@ int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* s
   const int rb_red = bn_rows_per_block(rows_half, 512), rb_app = bn_rows_per_block(rows_half, 256);
   const dim3 g_red(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_red)), g_app(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_app));
   DISPATCH_AT(dtype, bn_bwd_reduce_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)dout, (const AT*)y, stat, ws, rows_half, C, act, rb_red));
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, coef, dgamma, dbeta, halves, C, static_cast<double>(rows_half));
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, coef, dgamma, dbeta, halves, C, static_cast<double>(rows_half),
+                                                            static_cast<double>(alpha));
   DISPATCH_AT(dtype, bn_bwd_apply_kernel<AT><<<g_app, 256, 0, st>>>((const AT*)dout, (const AT*)y, stat, coef, (AT*)dy, rows, rows_half, C, act, rb_app));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-// out[C] (fp32) += column sums of x [rows, C] (row stride ldx)
-int dvae_colsum(int dtype, const void* x, float* out, long rows, int C, long ldx, void* stream) {
+// out[C] (fp32) += alpha * column sums of x [rows, C] (row stride ldx)
+int dvae_colsum(int dtype, const void* x, float* out, long rows, int C, long ldx, float alpha, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DVAE_REQUIRE(C % 8 == 0, "C must be a multiple of 8");
   if (rows == 0) return 0;
@@ -678,7 +687,7 @@ int dvae_colsum(int dtype, const void* x, float* out, long rows, int C, long ldx
   if (gx > 148 * 4) gx = 148 * 4;
   dim3 grid(static_cast<unsigned>(gx), ychunks);
   const int smem = lanes * cw * 4;
-  DISPATCH_AT(dtype, colsum_kernel<AT><<<grid, 256, smem, st>>>((const AT*)x, out, rows, C, ldx));
+  DISPATCH_AT(dtype, colsum_kernel<AT><<<grid, 256, smem, st>>>((const AT*)x, out, rows, C, ldx, alpha));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

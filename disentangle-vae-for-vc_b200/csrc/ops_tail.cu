@@ -6,6 +6,7 @@
 //     (model/variational_base_vae.py:281-282), group-wise reparameterisation (model/utils.py:95-116), with a
 //     differentiable backward for the product of Gaussians.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "act_types.cuh"
 #include "host_common.h"
@@ -54,6 +55,7 @@ __global__ void latent_tail_fwd_kernel(const float* __restrict__ heads, const fl
 __device__ __forceinline__ float ld_or0(const float* p, long i) { return p ? p[i] : 0.f; }
 
 // dz fp32 [2R, L]; dq*, dzs* may be null.  dheads act [2R, 2L]; member 2's style columns get zero (detach, :257-258).
+// gscale: dz arrives (and dheads leaves) at the gradient stream's scale; dq* / dzs* come from the loss unscaled.
 template <typename AT>
 __global__ void latent_tail_bwd_kernel(const float* __restrict__ heads, const float* __restrict__ eps_c1,
                                        const float* __restrict__ eps_c2, const float* __restrict__ eps_s,
@@ -61,7 +63,7 @@ __global__ void latent_tail_bwd_kernel(const float* __restrict__ heads, const fl
                                        const float* __restrict__ dq1_lv, const float* __restrict__ dq2_mu,
                                        const float* __restrict__ dq2_lv, const float* __restrict__ dzs_mu,
                                        const float* __restrict__ dzs_lv, AT* __restrict__ dheads, int R, int L, int S,
-                                       int sample_content) {
+                                       int sample_content, float gscale) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= R * L) return;
   const int i = idx / L, j = idx - i * L;
@@ -74,9 +76,9 @@ __global__ void latent_tail_bwd_kernel(const float* __restrict__ heads, const fl
   if (j < S) {
     const float lv = (h1[S + j] + h2[S + j]) * 0.5f;
     const float dzs = dz1 + dz2;
-    const float dmu = dzs + ld_or0(dq1_mu, i * L + j) + ld_or0(dq2_mu, i * L + j) + ld_or0(dzs_mu, i * S + j);
-    const float dlv = dzs * eps_s[i * S + j] * 0.5f * expf(0.5f * lv) + ld_or0(dq1_lv, i * L + j) +
-                      ld_or0(dq2_lv, i * L + j) + ld_or0(dzs_lv, i * S + j);
+    const float dmu = dzs + gscale * ld_or0(dq1_mu, i * L + j) + gscale * ld_or0(dq2_mu, i * L + j) + gscale * ld_or0(dzs_mu, i * S + j);
+    const float dlv = dzs * eps_s[i * S + j] * 0.5f * expf(0.5f * lv) + gscale * ld_or0(dq1_lv, i * L + j) +
+                      gscale * ld_or0(dq2_lv, i * L + j) + gscale * ld_or0(dzs_lv, i * S + j);
     d1[j] = from_f32<AT>(0.5f * dmu);
     d1[S + j] = from_f32<AT>(0.5f * dlv);
     d2[j] = from_f32<AT>(0.f);
@@ -84,8 +86,8 @@ __global__ void latent_tail_bwd_kernel(const float* __restrict__ heads, const fl
   } else {
     const int k = j - S;
     const float lv1 = h1[2 * S + Lc + k], lv2 = h2[2 * S + Lc + k];
-    float dmu1 = dz1 + ld_or0(dq1_mu, i * L + j), dlv1 = ld_or0(dq1_lv, i * L + j);
-    float dmu2 = dz2 + ld_or0(dq2_mu, i * L + j), dlv2 = ld_or0(dq2_lv, i * L + j);
+    float dmu1 = dz1 + gscale * ld_or0(dq1_mu, i * L + j), dlv1 = gscale * ld_or0(dq1_lv, i * L + j);
+    float dmu2 = dz2 + gscale * ld_or0(dq2_mu, i * L + j), dlv2 = gscale * ld_or0(dq2_lv, i * L + j);
     if (sample_content) {
       dlv1 += dz1 * eps_c1[i * Lc + k] * 0.5f * expf(0.5f * lv1);
       dlv2 += dz2 * eps_c2[i * Lc + k] * 0.5f * expf(0.5f * lv2);
@@ -453,6 +455,7 @@ using namespace dvae;
 #define DISPATCH_AT(dtype, ...)                              \
   do {                                                       \
     if ((dtype) == kBF16) { using AT = bf16; __VA_ARGS__; }  \
+    else if ((dtype) == kF16) { using AT = __half; __VA_ARGS__; } \
     else if ((dtype) == kTF32) { using AT = tf32_t; __VA_ARGS__; } \
     else { set_last_error("unknown dtype tag"); return 1; }  \
   } while (0)
@@ -486,12 +489,12 @@ int dvae_latent_tail_fwd(int dtype, const float* heads, const float* eps_c1, con
 int dvae_latent_tail_bwd(int dtype, const float* heads, const float* eps_c1, const float* eps_c2, const float* eps_s,
                          const float* dz, const float* dq1_mu, const float* dq1_lv, const float* dq2_mu, const float* dq2_lv,
                          const float* dzs_mu, const float* dzs_lv, void* dheads, int R, int L, int S, int sample_content,
-                         void* stream) {
+                         float gscale, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   if (R == 0) return 0;
   DISPATCH_AT(dtype, latent_tail_bwd_kernel<AT><<<ceil_div((long)R * L, 256), 256, 0, st>>>(
                          heads, eps_c1, eps_c2, eps_s, dz, dq1_mu, dq1_lv, dq2_mu, dq2_lv, dzs_mu, dzs_lv, (AT*)dheads, R, L, S,
-                         sample_content));
+                         sample_content, gscale));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

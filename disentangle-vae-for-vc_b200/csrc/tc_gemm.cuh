@@ -45,7 +45,12 @@ struct GemmShape {
   int splits;      // split-K factor
   float* splitk_ws;  // fix-up workspace [tiles][splits][128][BLOCK_N] fp32 (epilogues with kFixup, splits > 1)
   int* tickets;      // [tiles] arrival counters, zero before first use, self-resetting
+  int f16;           // 16-bit operands are IEEE fp16 rather than bf16 (same kernel, other a_format / b_format bits)
 };
+// instruction descriptor of this launch: the template's bf16 descriptor with the two format fields cleared for fp16
+__device__ __forceinline__ uint32_t runtime_idesc(uint32_t idesc, const GemmShape& shp) {
+  return shp.f16 ? (idesc & ~((7u << 7) | (7u << 10))) : idesc;
+}
 
 // Per-thread view of "this row's accumulator": TMEM, plus the parked partials of the other splits when this CTA is the
 // last split to arrive.
@@ -248,6 +253,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (in a pair: the leader only)
+    const uint32_t idesc = runtime_idesc(IDESC, shp);
     if (!PAIR || cr == 0) {
       for (int it = 0; it < num_local; ++it) {
         const int s = it % STAGES;
@@ -270,9 +276,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               if constexpr (PAIR)
-                ptx::umma_pair<ELEM_BYTES>(tmem_base, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+                ptx::umma_pair<ELEM_BYTES>(tmem_base, adesc + k * ADV_A, bdesc + k * ADV_B, idesc, (it > 0 || k > 0) ? 1u : 0u);
               else
-                ptx::umma<ELEM_BYTES>(tmem_base + mt * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
+                ptx::umma<ELEM_BYTES>(tmem_base + mt * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, idesc,
                                       (it > 0 || k > 0) ? 1u : 0u);
             }
           }
@@ -518,6 +524,7 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     // ------------------------------------------------------------ MMA issuer (pair: the leader only)
     constexpr uint32_t MN_LAYOUT = (ELEM_BYTES == 4) ? 1u : 2u;
     constexpr uint32_t MN_SBO = (ELEM_BYTES == 4) ? 512u : 1024u;
+    const uint32_t idesc = runtime_idesc(IDESC, shp);
     if (!PAIR || cr == 0) {
       int it = 0, local = 0;
       for (int tile = walker; tile < items; tile += walkers, ++local) {
@@ -541,10 +548,10 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               if constexpr (PAIR)
-                ptx::umma_pair<ELEM_BYTES>(tmem_base + as * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
+                ptx::umma_pair<ELEM_BYTES>(tmem_base + as * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, idesc,
                                            (k0 > 0 || k > 0) ? 1u : 0u);
               else
-                ptx::umma<ELEM_BYTES>(tmem_base + as * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, IDESC,
+                ptx::umma<ELEM_BYTES>(tmem_base + as * BLOCK_N, adesc + k * ADV_A, bdesc + k * ADV_B, idesc,
                                       (k0 > 0 || k > 0) ? 1u : 0u);
             }
             if constexpr (PAIR) ptx::umma_commit_pair(empty_bar(s));
@@ -816,7 +823,7 @@ struct EpiStoreTma {
         if constexpr (EB == 2) {
           unsigned short u;
           asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u) : "r"(a));
-          v = __uint_as_float(static_cast<uint32_t>(u) << 16);
+          v = bits16_to_f32<OutT>(u);
         } else {
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
         }
@@ -862,15 +869,7 @@ struct EpiStoreTma {
       }
 #pragma unroll
       for (int j = 0; j < 32 * EB / 16; ++j) {
-        uint4 u;
-        if constexpr (EB == 2) {
-          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
-        } else {
-          u = make_uint4(__float_as_uint(round_tf32(v[4 * j])), __float_as_uint(round_tf32(v[4 * j + 1])),
-                         __float_as_uint(round_tf32(v[4 * j + 2])), __float_as_uint(round_tf32(v[4 * j + 3])));
-        }
+        const uint4 u = pack_chunk<OutT>(v + (16 / EB) * j);
         const int byte = c * EB + 16 * j;
         ptx::st_shared_v4(stage + static_cast<uint32_t>((byte >> 7) * (kBlockM * 128) + row * 128 +
                                                         ((((byte & 127) >> 4) ^ (row & 7)) << 4)),
@@ -898,6 +897,7 @@ struct EpiAtomic {
     float* out;
     long ldo;
     long z_stride;
+    float alpha;   // every partial sum is scaled by alpha before it is added (1 / gradient scale of the fp16 mode)
   };
   template <int BLOCK_N>
   static __device__ __forceinline__ void prefetch(const Params&, int, int, int, int, int, const GemmShape&) {}
@@ -916,6 +916,10 @@ struct EpiAtomic {
       __syncwarp();
       float v[32];
       acc.template load<32>(c, v);
+      if (p.alpha != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+      }
       const int nb = n0 + c;
       if (row_ok) {
         if (nb + 32 <= shp.N && (p.ldo & 3) == 0) {
@@ -1088,15 +1092,7 @@ struct EpiLstmFwdTma : EpiLstmFwd<ActT> {
       // gates: 32 columns = 32*EB bytes at byte c*EB of the row
 #pragma unroll
       for (int j = 0; j < 32 * EB / 16; ++j) {
-        uint4 u;
-        if constexpr (EB == 2) {
-          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(a[8 * j + 2 * i], a[8 * j + 2 * i + 1]);
-        } else {
-          u = make_uint4(__float_as_uint(round_tf32(a[4 * j])), __float_as_uint(round_tf32(a[4 * j + 1])),
-                         __float_as_uint(round_tf32(a[4 * j + 2])), __float_as_uint(round_tf32(a[4 * j + 3])));
-        }
+        const uint4 u = pack_chunk<ActT>(a + (16 / EB) * j);
         ptx::st_shared_v4(box_addr(sg, c * EB + 16 * j), u);
       }
       // c: 8 units fp32 = 32 bytes at byte c (= 4 * (c / 4)) of the row
@@ -1108,15 +1104,7 @@ struct EpiLstmFwdTma : EpiLstmFwd<ActT> {
       // h: 8 units = 8*EB bytes at byte (c / 4) * EB of the row
 #pragma unroll
       for (int j = 0; j < 8 * EB / 16; ++j) {
-        uint4 u;
-        if constexpr (EB == 2) {
-          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(hn[2 * i], hn[2 * i + 1]);
-        } else {
-          u = make_uint4(__float_as_uint(round_tf32(hn[4 * j])), __float_as_uint(round_tf32(hn[4 * j + 1])),
-                         __float_as_uint(round_tf32(hn[4 * j + 2])), __float_as_uint(round_tf32(hn[4 * j + 3])));
-        }
+        const uint4 u = pack_chunk<ActT>(hn + (16 / EB) * j);
         const int byte = (c / 4) * EB + 16 * j;
         if constexpr (h_row_bytes<BLOCK_N>() >= 128) ptx::st_shared_v4(box_addr(sh, byte), u);
         else ptx::st_shared_v4(sh + row * h_row_bytes<BLOCK_N>() + byte, u);   // narrow tile: unswizzled rows

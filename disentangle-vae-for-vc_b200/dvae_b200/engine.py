@@ -46,50 +46,61 @@ class PreparedWeights:
         self.conv: Dict[str, Tensor] = {}
         self.lin: Dict[str, Tensor] = {}
         self.lstm: Dict[str, dict] = {}
-        convs = [c for c, _, _ in ENC_CONVS + DEC_CONVS + POST_CONVS] if convs is None else convs
-        linears = LINEARS if linears is None else linears
-        lstms = LSTMS if lstms is None else lstms
-        for conv in convs:
-            self.conv[conv] = ops.prep_conv_weight(dt, P[conv + ".weight"])
-        for name in linears:
-            w = P[name + ".weight"]
-            c = torch.empty_like(w, dtype=ad)   # bf16 copy, or fp32 rounded onto the tf32 grid
-            ops.prep_cast(dt, w, c)
-            self.lin[name] = c
+        self._convs = [c for c, _, _ in ENC_CONVS + DEC_CONVS + POST_CONVS] if convs is None else convs
+        self._linears = LINEARS if linears is None else linears
+        self._lstms = LSTMS if lstms is None else lstms
+        self._fused_heads = fused_heads
+        dev = next(iter(P.values())).device
+        for conv in self._convs:
+            Co, Ci, _ = P[conv + ".weight"].shape
+            self.conv[conv] = torch.empty((Co, 5, Ci), device=dev, dtype=ad)
+        for name in self._linears:
+            self.lin[name] = torch.empty_like(P[name + ".weight"], dtype=ad)   # bf16 / fp16 copy, or fp32 on the tf32 grid
         if fused_heads:
             # style + content heads fused into one [2L, 2048] GEMM (rows: style_mu, style_logvar, content_mu, content_logvar)
             ws, wc = P["style.linear_layer.weight"], P["content.linear_layer.weight"]
             n_s, n_c = ws.shape[0], wc.shape[0]
-            heads_w = torch.empty((n_s + n_c, ws.shape[1]), device=ws.device, dtype=ad)
-            ops.prep_cast(dt, ws, heads_w[:n_s])
-            ops.prep_cast(dt, wc, heads_w[n_s:])
-            heads_b = torch.empty((n_s + n_c,), device=ws.device, dtype=torch.float32)
-            ops.copy_f32(P["style.linear_layer.bias"], heads_b[:n_s])
-            ops.copy_f32(P["content.linear_layer.bias"], heads_b[n_s:])
-            self.heads_w, self.heads_b, self.n_style = heads_w, heads_b, n_s
-        dev0 = next(iter(P.values())).device
-        for prefix, (layers, D, H) in lstms.items():
-            tile = lib.lstm_gate_tile(H)
+            self.heads_w = torch.empty((n_s + n_c, ws.shape[1]), device=dev, dtype=ad)
+            self.heads_b = torch.empty((n_s + n_c,), device=dev, dtype=torch.float32)
+            self.n_style = n_s
+        for prefix, (layers, D, H) in self._lstms.items():
             per_layer = []
             for l in range(layers):
                 In = P[f"{prefix}.weight_ih_l{l}"].shape[1]
-                dev = dev0
-                wih_p = torch.empty((D * 4 * H, In), device=dev, dtype=ad)
-                wih_n = torch.empty((D * 4 * H, In), device=dev, dtype=ad)
-                whh_p = torch.empty((D, 4 * H, H), device=dev, dtype=ad)
-                whh_n = torch.empty((D, 4 * H, H), device=dev, dtype=ad)
-                bias_p = torch.empty((D * 4 * H,), device=dev, dtype=torch.float32)
+                per_layer.append(dict(wih_p=torch.empty((D * 4 * H, In), device=dev, dtype=ad),
+                                      wih_n=torch.empty((D * 4 * H, In), device=dev, dtype=ad),
+                                      whh_p=torch.empty((D, 4 * H, H), device=dev, dtype=ad),
+                                      whh_n=torch.empty((D, 4 * H, H), device=dev, dtype=ad),
+                                      bias_p=torch.empty((D * 4 * H,), device=dev, dtype=torch.float32), In=In))
+            self.lstm[prefix] = dict(layers=per_layer, D=D, H=H)
+        self.refresh(P)
+
+    def refresh(self, P: Dict[str, Tensor]) -> None:
+        """Re-derive every tensor-core copy from the fp32 masters, in place (after an optimizer step / load_state_dict)."""
+        dt = self.dt
+        for conv in self._convs:
+            ops.prep_conv_weight(dt, P[conv + ".weight"], out=self.conv[conv])
+        for name in self._linears:
+            ops.prep_cast(dt, P[name + ".weight"], self.lin[name])
+        if self._fused_heads:
+            n_s = self.n_style
+            ops.prep_cast(dt, P["style.linear_layer.weight"], self.heads_w[:n_s])
+            ops.prep_cast(dt, P["content.linear_layer.weight"], self.heads_w[n_s:])
+            ops.copy_f32(P["style.linear_layer.bias"], self.heads_b[:n_s])
+            ops.copy_f32(P["content.linear_layer.bias"], self.heads_b[n_s:])
+        for prefix, info in self.lstm.items():
+            D, H = info["D"], info["H"]
+            tile = lib.lstm_gate_tile(H)
+            for l, lw in enumerate(info["layers"]):
                 for d in range(D):
                     suf = "_reverse" if d == 1 else ""
+                    sl = slice(d * 4 * H, (d + 1) * 4 * H)
                     w_ih, w_hh = P[f"{prefix}.weight_ih_l{l}{suf}"], P[f"{prefix}.weight_hh_l{l}{suf}"]
-                    ops.prep_lstm_weight(dt, w_ih, wih_p[d * 4 * H:(d + 1) * 4 * H], H, tile)
-                    ops.prep_lstm_weight(dt, w_hh, whh_p[d], H, tile)
-                    ops.prep_cast(dt, w_ih, wih_n[d * 4 * H:(d + 1) * 4 * H])
-                    ops.prep_cast(dt, w_hh, whh_n[d])
-                    ops.prep_lstm_bias(P[f"{prefix}.bias_ih_l{l}{suf}"], P[f"{prefix}.bias_hh_l{l}{suf}"],
-                                       bias_p[d * 4 * H:(d + 1) * 4 * H], H, tile)
-                per_layer.append(dict(wih_p=wih_p, wih_n=wih_n, whh_p=whh_p, whh_n=whh_n, bias_p=bias_p, In=In))
-            self.lstm[prefix] = dict(layers=per_layer, D=D, H=H)
+                    ops.prep_lstm_weight(dt, w_ih, lw["wih_p"][sl], H, tile)
+                    ops.prep_lstm_weight(dt, w_hh, lw["whh_p"][d], H, tile)
+                    ops.prep_cast(dt, w_ih, lw["wih_n"][sl])
+                    ops.prep_cast(dt, w_hh, lw["whh_n"][d])
+                    ops.prep_lstm_bias(P[f"{prefix}.bias_ih_l{l}{suf}"], P[f"{prefix}.bias_hh_l{l}{suf}"], lw["bias_p"][sl], H, tile)
 
 
 class GradSink:
@@ -129,7 +140,13 @@ class GradSink:
 
 
 class Engine:
-    def __init__(self, dt: int, latent_dim: int, speaker_size: int, bn_eps: float = 1e-5, bn_momentum: float = 0.1):
+    def __init__(self, dt: int, latent_dim: int, speaker_size: int, bn_eps: float = 1e-5, bn_momentum: float = 0.1,
+                 grad_scale: float = 1.0):
+        # The activation-gradient stream is carried multiplied by `grad_scale` (a power of two, so scaling is exact) and
+        # every parameter gradient is multiplied by 1 / grad_scale where it is produced.  1.0 for bf16 / tf32 storage
+        # (fp32's exponent range); the fp16 mode needs it to keep small gradients inside fp16's normal range.
+        self.grad_scale = float(grad_scale)
+        self.grad_stats = [] if os.environ.get("DVAE_DEBUG_GRAD_STATS") else None   # diagnostics: (name, amax) of the stream
         self.buckets = None   # set to a parallel.GradBuckets for data-parallel training
         self.side_stream = None     # created lazily; weight-gradient GEMMs that are off the critical path run here
         self.use_side_stream = os.environ.get("DVAE_SIDE_STREAM", "1") != "0"   # A/B switch for profiling
@@ -279,6 +296,11 @@ class Engine:
         return d
 
     # ------------------------------------------------------------------ building blocks (backward)
+    def _stat(self, name: str, t: Tensor) -> None:
+        """Diagnostics only (DVAE_DEBUG_GRAD_STATS=1): largest magnitude of a gradient-stream tensor, for choosing grad_scale."""
+        if self.grad_stats is not None and t is not None:
+            self.grad_stats.append((name, t.float().abs().max().item()))
+
     def _conv_stack_bwd(self, W, dout: Tensor, saved_layers: list, sink: GradSink, halves: int, need_dx: bool):
         dt = self.dt
         for i in range(len(saved_layers) - 1, -1, -1):
@@ -287,8 +309,9 @@ class Engine:
             C = y.shape[-1]
             gname, bname = s["bn"] + ".weight", s["bn"] + ".bias"
             dy, _, _ = ops.bn_train_bwd(dt, dout.reshape(-1, C), y.view(-1, C), s["stat"], halves, s["act"],
-                                        dgamma=sink.buf(gname, (C,)), dbeta=sink.buf(bname, (C,)))
+                                        dgamma=sink.buf(gname, (C,)), dbeta=sink.buf(bname, (C,)), alpha=1.0 / self.grad_scale)
             dy = dy.view_as(y)
+            self._stat("dy:" + s["conv"], dy)
             sink.done(gname), sink.done(bname)
             wk = W.conv[s["conv"]]
             Co, _, Ci = wk.shape
@@ -302,7 +325,7 @@ class Engine:
             self._keepalive.append((dy, s["x_in"]))
             with self._side_stream_ctx():
                 dwk = torch.zeros(wk.shape, device=wk.device, dtype=torch.float32)
-                ops.conv5_wgrad(dt, dy, s["x_in"], dwk)
+                ops.conv5_wgrad(dt, dy, s["x_in"], dwk, alpha=1.0 / self.grad_scale)
                 ops.conv_wgrad_unpack(dwk, out=sink.buf(s["conv"] + ".weight", (Co, Ci, 5)))
                 self._keepalive.append((dwk,))
             sink.done(s["conv"] + ".weight")
@@ -323,6 +346,7 @@ class Engine:
             In = lw["In"]
             da = ops.lstm_bwd(dt, dh.reshape(rows, T, D * H), s["gates"], s["c_all"], lw["whh_n"], H, D)
             da2 = da.view(rows * T, D * 4 * H)
+            self._stat(f"da:{prefix}.l{l}", da)
             x2 = s["x_in"].reshape(rows * T, In)
             if l > 0 or need_dx:
                 dh, _ = ops.linear_dgrad(dt, da2, lw["wih_n"])
@@ -342,24 +366,25 @@ class Engine:
         dt = self.dt
         D, H, lw = s["D"], s["H"], s["lw"]
         In = lw["In"]
+        inv = 1.0 / self.grad_scale
         if D == 1:   # gradients land directly in their final buffers
             n_ih, n_hh = f"{prefix}.weight_ih_l{l}", f"{prefix}.weight_hh_l{l}"
-            ops.linear_wgrad(dt, da2, x2, sink.buf(n_ih, (4 * H, In)))
+            ops.linear_wgrad(dt, da2, x2, sink.buf(n_ih, (4 * H, In)), alpha=inv)
             sink.done(n_ih)
-            ops.lstm_wgrad_hh(dt, da, s["h_all"], sink.buf(n_hh, (4 * H, H)).view(1, 4 * H, H), H, 1)
+            ops.lstm_wgrad_hh(dt, da, s["h_all"], sink.buf(n_hh, (4 * H, H)).view(1, 4 * H, H), H, 1, alpha=inv)
             sink.done(n_hh)
             db = sink.buf(f"{prefix}.bias_ih_l{l}", (4 * H,))
-            ops.colsum(dt, da2, db)
+            ops.colsum(dt, da2, db, alpha=inv)
             sink.done(f"{prefix}.bias_ih_l{l}")
             ops.copy_f32(db, sink.buf(f"{prefix}.bias_hh_l{l}", (4 * H,)))   # b_ih and b_hh: equal gradients
             sink.done(f"{prefix}.bias_hh_l{l}")
         else:        # both directions come out of one GEMM; slice per direction
             dwih = torch.zeros((D * 4 * H, In), device=da.device, dtype=torch.float32)
-            ops.linear_wgrad(dt, da2, x2, dwih)
+            ops.linear_wgrad(dt, da2, x2, dwih, alpha=inv)
             dwhh = torch.zeros((D, 4 * H, H), device=da.device, dtype=torch.float32)
-            ops.lstm_wgrad_hh(dt, da, s["h_all"], dwhh, H, D)
+            ops.lstm_wgrad_hh(dt, da, s["h_all"], dwhh, H, D, alpha=inv)
             db = torch.zeros((D * 4 * H,), device=da.device, dtype=torch.float32)
-            ops.colsum(dt, da2, db)
+            ops.colsum(dt, da2, db, alpha=inv)
             for d in range(D):
                 suf = "_reverse" if d == 1 else ""
                 sl = slice(d * 4 * H, (d + 1) * 4 * H)
@@ -372,9 +397,9 @@ class Engine:
                     want_f32=False, need_dx: bool = True):
         dt = self.dt
         N, K = W_act.shape
-        ops.linear_wgrad(dt, dy, x, sink.buf(name + ".weight", (N, K)))
+        ops.linear_wgrad(dt, dy, x, sink.buf(name + ".weight", (N, K)), alpha=1.0 / self.grad_scale)
         sink.done(name + ".weight")
-        ops.colsum(dt, dy, sink.buf(name + ".bias", (N,)))
+        ops.colsum(dt, dy, sink.buf(name + ".bias", (N,)), alpha=1.0 / self.grad_scale)
         sink.done(name + ".bias")
         if not need_dx:
             return None
@@ -395,8 +420,10 @@ class Engine:
         # ---- residual output: recon_hat = recon + postnet(recon)  (:277-278)
         d_rec = torch.empty((R2, T_FRAMES, N_MELS), device=dev, dtype=ad)
         d_post = torch.empty((R2, T_FRAMES, N_MELS), device=dev, dtype=ad)
-        ops.recon_out_bwd(dt, g[0], g[2], d_rec[:R], d_post[:R])
-        ops.recon_out_bwd(dt, g[1], g[3], d_rec[R:], d_post[R:])
+        gs = self.grad_scale
+        ops.recon_out_bwd(dt, g[0], g[2], d_rec[:R], d_post[:R], scale=gs)
+        ops.recon_out_bwd(dt, g[1], g[3], d_rec[R:], d_post[R:], scale=gs)
+        self._stat("d_rec", d_rec), self._stat("d_post", d_post)
         d_in = self._conv_stack_bwd(W, d_post, saved["post_convs"], grads, 2, need_dx=True)
         ops.add_inplace(dt, d_rec, d_in)
         # ---- decoder
@@ -412,13 +439,14 @@ class Engine:
         # ---- latent tail (:252-272)
         eps = saved["eps"]
         dheads = ops.latent_tail_bwd(dt, saved["heads"], eps[0], eps[1], eps[2], dz, g[4:8], g[8:10], R, self.L, self.S,
-                                     saved["sample_content"])
+                                     saved["sample_content"], gscale=gs)
+        self._stat("dheads", dheads)
         # ---- encoder heads + linear
         n_s = W.n_style
         dw = torch.zeros(W.heads_w.shape, device=dev, dtype=torch.float32)
-        ops.linear_wgrad(dt, dheads, saved["e"], dw)
+        ops.linear_wgrad(dt, dheads, saved["e"], dw, alpha=1.0 / gs)
         db = torch.zeros((W.heads_w.shape[0],), device=dev, dtype=torch.float32)
-        ops.colsum(dt, dheads, db)
+        ops.colsum(dt, dheads, db, alpha=1.0 / gs)
         sink.put("style.linear_layer.weight", dw[:n_s]), sink.put("content.linear_layer.weight", dw[n_s:])
         sink.put("style.linear_layer.bias", db[:n_s]), sink.put("content.linear_layer.bias", db[n_s:])
         d_e, _ = ops.linear_dgrad(dt, dheads, W.heads_w, relu_mask=saved["e"])

@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdvae_b200.so")
 
-BF16, TF32 = 0, 1
+BF16, TF32, F16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
 if not os.path.exists(LIB_PATH):
@@ -31,20 +31,20 @@ _p, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_double
 _SIGNATURES = {
     "dvae_linear_fwd": [_i, _p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
     "dvae_linear_dgrad": [_i, _p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _p],
-    "dvae_linear_wgrad": [_i, _p, _l, _p, _l, _p, _l, _i, _i, _i, _p],
+    "dvae_linear_wgrad": [_i, _p, _l, _p, _l, _p, _l, _i, _i, _i, _f, _p],
     "dvae_conv5_fwd": [_i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_conv5_fwd_bnstats": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p],
     "dvae_conv5_dgrad": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
-    "dvae_conv5_wgrad": [_i, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dvae_conv5_wgrad": [_i, _p, _p, _p, _i, _i, _i, _i, _f, _p],
     "dvae_lstm_fwd": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_lstm_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_lstm_bwd_workspace": [_i, _i, _i, _i, _p, _p],
     "dvae_debug_timing": [_p, _i],
     "dvae_debug_seq_stamps": [_p],
     "dvae_set_background": [_i],
-    "dvae_lstm_wgrad_hh": [_i, _p, _p, _p, _i, _i, _i, _i, _p],
+    "dvae_lstm_wgrad_hh": [_i, _p, _p, _p, _i, _i, _i, _i, _f, _p],
     # weight preparation / layout
-    "dvae_prep_cast": [_i, _p, _p, _l, _p],
+    "dvae_prep_cast": [_i, _p, _p, _l, _f, _p],
     "dvae_add_inplace": [_i, _p, _p, _l, _p],
     "dvae_copy_f32": [_p, _p, _l, _p],
     "dvae_add_f32_act": [_i, _p, _p, _p, _l, _p],
@@ -54,16 +54,16 @@ _SIGNATURES = {
     "dvae_prep_lstm_bias": [_p, _p, _p, _i, _i, _p],
     "dvae_pack_ncl_to_cl": [_i, _p, _p, _i, _i, _i, _p],
     "dvae_unpack_cl_to_ncl": [_i, _p, _i, _p, _p, _p, _i, _i, _i, _p],
-    "dvae_recon_out_bwd": [_i, _p, _p, _p, _p, _i, _i, _i, _p],
+    "dvae_recon_out_bwd": [_i, _p, _p, _p, _p, _i, _i, _i, _f, _p],
     # batch norm / reductions
     "dvae_bn_train_fwd": [_i] + [_p] * 9 + [_i, _i, _i, _i, _f, _f, _p],
     "dvae_bn_finalize_apply": [_i] + [_p] * 9 + [_i, _i, _i, _i, _f, _f, _p],
     "dvae_bn_eval_fwd": [_i] + [_p] * 7 + [_l, _i, _i, _f, _p],
-    "dvae_bn_train_bwd": [_i] + [_p] * 8 + [_i, _i, _i, _i, _p],
-    "dvae_colsum": [_i, _p, _p, _l, _i, _l, _p],
+    "dvae_bn_train_bwd": [_i] + [_p] * 8 + [_i, _i, _i, _i, _f, _p],
+    "dvae_colsum": [_i, _p, _p, _l, _i, _l, _f, _p],
     # latent tail / loss / speaker groups
     "dvae_latent_tail_fwd": [_i] + [_p] * 11 + [_i, _i, _i, _i, _p],
-    "dvae_latent_tail_bwd": [_i] + [_p] * 12 + [_i, _i, _i, _i, _p],
+    "dvae_latent_tail_bwd": [_i] + [_p] * 12 + [_i, _i, _i, _i, _f, _p],
     "dvae_loss_fwd": [_p] * 6 + [_l] + [_p] * 4 + [_i, _i, _p, _p, _i, _f, _f, _f, _p, _p, _p],
     "dvae_loss_bwd": [_p] * 6 + [_l] + [_p] * 4 + [_i, _i, _p, _p, _i, _f, _f, _f] + [_p] * 11 + [_p],
     "dvae_segment_ids_sorted": [_p, _p, _p, _p, _l, _p],

@@ -2,8 +2,9 @@
 
 These allocate outputs with torch (device memory / stream plumbing only) and pass raw pointers to
 libdvae_b200.so.  No arithmetic happens in Python or torch here.
-Activation storage dtype `dt` is lib.BF16 (torch.bfloat16, tcgen05 kind::f16) or lib.TF32
-(torch.float32 storage, tcgen05 kind::tf32).
+Activation storage dtype `dt` is lib.BF16 (torch.bfloat16, tcgen05 kind::f16), lib.F16 (torch.float16, kind::f16) or
+lib.TF32 (torch.float32 storage, tcgen05 kind::tf32).  `alpha` / `scale` arguments carry the power-of-two gradient
+scale of the fp16 mode (1.0 otherwise).
 """
 from __future__ import annotations
 
@@ -17,8 +18,11 @@ from .lib import call, ptr, stream
 Tensor = torch.Tensor
 
 
+_ACT_DTYPES = {lib.BF16: torch.bfloat16, lib.F16: torch.float16, lib.TF32: torch.float32}
+
+
 def act_dtype(dt: int) -> torch.dtype:
-    return torch.bfloat16 if dt == lib.BF16 else torch.float32
+    return _ACT_DTYPES[dt]
 
 
 def _chk(t: Tensor, dtype=None):
@@ -57,14 +61,14 @@ def linear_dgrad(dt: int, dy: Tensor, w: Tensor, relu_mask: Optional[Tensor] = N
     return dx, dx32
 
 
-def linear_wgrad(dt: int, dy: Tensor, x: Tensor, dw: Tensor) -> None:
-    """dw[N,K] (fp32, pre-zeroed or accumulating) += dy[M,N]^T @ x[M,K]."""
+def linear_wgrad(dt: int, dy: Tensor, x: Tensor, dw: Tensor, alpha: float = 1.0) -> None:
+    """dw[N,K] (fp32, pre-zeroed or accumulating) += alpha * dy[M,N]^T @ x[M,K]."""
     ad = act_dtype(dt)
     _chk(dy, ad), _chk(x, ad), _chk(dw, torch.float32)
     M, N = dy.shape
     K = x.shape[1]
     assert x.shape[0] == M and tuple(dw.shape) == (N, K)
-    call("dvae_linear_wgrad", dt, ptr(dy), N, ptr(x), K, ptr(dw), K, M, N, K, stream())
+    call("dvae_linear_wgrad", dt, ptr(dy), N, ptr(x), K, ptr(dw), K, M, N, K, float(alpha), stream())
 
 
 def conv5_fwd(dt: int, x: Tensor, wk: Tensor, bias: Optional[Tensor], want_f32: bool = False):
@@ -107,14 +111,14 @@ def conv5_dgrad(dt: int, dy: Tensor, wk: Tensor, want_f32: bool = False):
     return (dx, dx32) if want_f32 else dx
 
 
-def conv5_wgrad(dt: int, dy: Tensor, x: Tensor, dwk: Tensor) -> None:
-    """dwk[Cout,5,Cin] (fp32, accumulating) += sum_{r,t} dy[r,t,co] x[r,t+k-2,ci]."""
+def conv5_wgrad(dt: int, dy: Tensor, x: Tensor, dwk: Tensor, alpha: float = 1.0) -> None:
+    """dwk[Cout,5,Cin] (fp32, accumulating) += alpha * sum_{r,t} dy[r,t,co] x[r,t+k-2,ci]."""
     ad = act_dtype(dt)
     _chk(dy, ad), _chk(x, ad), _chk(dwk, torch.float32)
     R, T, Cout = dy.shape
     Cin = x.shape[2]
     assert tuple(dwk.shape) == (Cout, 5, Cin)
-    call("dvae_conv5_wgrad", dt, ptr(dy), ptr(x), ptr(dwk), R, T, Cin, Cout, stream())
+    call("dvae_conv5_wgrad", dt, ptr(dy), ptr(x), ptr(dwk), R, T, Cin, Cout, float(alpha), stream())
 
 
 def lstm_fwd(dt: int, xg: Tensor, whh_p: Tensor, H: int, D: int):
@@ -157,12 +161,12 @@ def _splitk_workspace(dt: int, rows: int, H: int, D: int, device):
     return _SPLITK_CACHE[key]
 
 
-def lstm_wgrad_hh(dt: int, da_all: Tensor, h_all: Tensor, dwhh: Tensor, H: int, D: int) -> None:
+def lstm_wgrad_hh(dt: int, da_all: Tensor, h_all: Tensor, dwhh: Tensor, H: int, D: int, alpha: float = 1.0) -> None:
     ad = act_dtype(dt)
     _chk(da_all, ad), _chk(h_all, ad), _chk(dwhh, torch.float32)
     rows, T, _ = da_all.shape
     assert tuple(dwhh.shape) == (D, 4 * H, H)
-    call("dvae_lstm_wgrad_hh", dt, ptr(da_all), ptr(h_all), ptr(dwhh), rows, T, H, D, stream())
+    call("dvae_lstm_wgrad_hh", dt, ptr(da_all), ptr(h_all), ptr(dwhh), rows, T, H, D, float(alpha), stream())
 
 
 # ------------------------------------------------------------------------------- weight preparation
@@ -173,10 +177,11 @@ def copy_f32(src: Tensor, dst: Tensor) -> None:
     call("dvae_copy_f32", ptr(src), ptr(dst), src.numel(), stream())
 
 
-def prep_cast(dt: int, src: Tensor, dst: Tensor) -> None:
+def prep_cast(dt: int, src: Tensor, dst: Tensor, scale: float = 1.0) -> None:
+    """dst (activation dtype) = scale * src (fp32)."""
     _chk(src, torch.float32), _chk(dst, act_dtype(dt))
     assert src.numel() == dst.numel()
-    call("dvae_prep_cast", dt, ptr(src), ptr(dst), src.numel(), stream())
+    call("dvae_prep_cast", dt, ptr(src), ptr(dst), src.numel(), float(scale), stream())
 
 
 def add_f32_act(dt: int, a: Tensor, b: Tensor) -> Tensor:
@@ -193,12 +198,14 @@ def add_inplace(dt: int, a: Tensor, b: Tensor) -> None:
     call("dvae_add_inplace", dt, ptr(a), ptr(b), a.numel(), stream())
 
 
-def prep_conv_weight(dt: int, w: Tensor) -> Tensor:
+def prep_conv_weight(dt: int, w: Tensor, out: Optional[Tensor] = None) -> Tensor:
     """torch Conv1d weight [Co,Ci,5] fp32 -> [Co,5,Ci] activation dtype."""
     _chk(w, torch.float32)
     Co, Ci, k = w.shape
     assert k == 5
-    wk = torch.empty((Co, 5, Ci), device=w.device, dtype=act_dtype(dt))
+    wk = out if out is not None else torch.empty((Co, 5, Ci), device=w.device, dtype=act_dtype(dt))
+    _chk(wk, act_dtype(dt))
+    assert tuple(wk.shape) == (Co, 5, Ci)
     call("dvae_prep_conv_weight", dt, ptr(w), ptr(wk), Co, Ci, stream())
     return wk
 
@@ -245,14 +252,15 @@ def unpack_cl_to_ncl(dt: int, a: Tensor, b: Optional[Tensor], want_a: bool = Tru
     return out_a, out_s
 
 
-def recon_out_bwd(dt: int, g_rec: Optional[Tensor], g_hat: Optional[Tensor], d_rec: Tensor, d_post: Tensor) -> None:
-    """g_* fp32 [R,C,T] (or None) -> d_rec = (g_rec + g_hat)^T, d_post = g_hat^T, both act [R,T,C]."""
+def recon_out_bwd(dt: int, g_rec: Optional[Tensor], g_hat: Optional[Tensor], d_rec: Tensor, d_post: Tensor,
+                  scale: float = 1.0) -> None:
+    """g_* fp32 [R,C,T] (or None) -> d_rec = scale * (g_rec + g_hat)^T, d_post = scale * g_hat^T, both act [R,T,C]."""
     R, T, Cc = d_rec.shape
     for g in (g_rec, g_hat):
         if g is not None:
             _chk(g, torch.float32)
             assert tuple(g.shape) == (R, Cc, T)
-    call("dvae_recon_out_bwd", dt, ptr(g_rec), ptr(g_hat), ptr(d_rec), ptr(d_post), R, Cc, T, stream())
+    call("dvae_recon_out_bwd", dt, ptr(g_rec), ptr(g_hat), ptr(d_rec), ptr(d_post), R, Cc, T, float(scale), stream())
 
 
 # ------------------------------------------------------------------------------- batch norm
@@ -300,8 +308,8 @@ def bn_eval_fwd(dt: int, y: Tensor, gamma: Tensor, beta: Tensor, run_mean: Tenso
 
 
 def bn_train_bwd(dt: int, dout: Tensor, y: Tensor, stat: Tensor, halves: int, act: int,
-                 dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None):
-    """Returns (dy act [rows,C], dgamma fp32 [C], dbeta fp32 [C])."""
+                 dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, alpha: float = 1.0):
+    """Returns (dy act [rows,C], dgamma fp32 [C], dbeta fp32 [C]); the two parameter gradients are scaled by alpha."""
     ad = act_dtype(dt)
     _chk(dout, ad), _chk(y, ad), _chk(stat, torch.float32)
     C = y.shape[-1]
@@ -312,16 +320,16 @@ def bn_train_bwd(dt: int, dout: Tensor, y: Tensor, stat: Tensor, halves: int, ac
     dgamma = dgamma if dgamma is not None else torch.empty((C,), device=y.device, dtype=torch.float32)
     dbeta = dbeta if dbeta is not None else torch.empty((C,), device=y.device, dtype=torch.float32)
     call("dvae_bn_train_bwd", dt, ptr(dout), ptr(y), ptr(stat), ptr(ws), ptr(coef), ptr(dy), ptr(dgamma), ptr(dbeta),
-         rows // halves, halves, C, act, stream())
+         rows // halves, halves, C, act, float(alpha), stream())
     return dy, dgamma, dbeta
 
 
-def colsum(dt: int, x: Tensor, out: Tensor) -> None:
-    """out[C] (fp32, accumulating) += column sums of x viewed as [rows, C]."""
+def colsum(dt: int, x: Tensor, out: Tensor, alpha: float = 1.0) -> None:
+    """out[C] (fp32, accumulating) += alpha * column sums of x viewed as [rows, C]."""
     _chk(x, act_dtype(dt)), _chk(out, torch.float32)
     C = out.numel()
     rows = x.numel() // C
-    call("dvae_colsum", dt, ptr(x), ptr(out), rows, C, C, stream())
+    call("dvae_colsum", dt, ptr(x), ptr(out), rows, C, C, float(alpha), stream())
 
 
 # ------------------------------------------------------------------------------- latent tail / loss
@@ -338,11 +346,11 @@ def latent_tail_fwd(dt: int, heads: Tensor, eps_c1, eps_c2, eps_s: Tensor, R: in
 
 
 def latent_tail_bwd(dt: int, heads: Tensor, eps_c1, eps_c2, eps_s, dz: Tensor, dq, dzs, R: int, L: int, S: int,
-                    sample_content: bool) -> Tensor:
+                    sample_content: bool, gscale: float = 1.0) -> Tensor:
     _chk(dz, torch.float32)
     dheads = torch.empty((2 * R, 2 * L), device=heads.device, dtype=act_dtype(dt))
     call("dvae_latent_tail_bwd", dt, ptr(heads), ptr(eps_c1), ptr(eps_c2), ptr(eps_s), ptr(dz), ptr(dq[0]), ptr(dq[1]), ptr(dq[2]),
-         ptr(dq[3]), ptr(dzs[0]), ptr(dzs[1]), ptr(dheads), R, L, S, int(sample_content), stream())
+         ptr(dq[3]), ptr(dzs[0]), ptr(dzs[1]), ptr(dheads), R, L, S, int(sample_content), float(gscale), stream())
     return dheads
 
 

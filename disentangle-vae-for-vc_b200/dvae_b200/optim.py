@@ -90,6 +90,9 @@ class Adam(torch.optim.Adam):
             lib.call("dvae_adam_step", lib.ptr(tb["p"]), lib.ptr(tb["g"]), lib.ptr(tb["m"]), lib.ptr(tb["v"]), lib.ptr(tb["sizes"]),
                      lib.ptr(tb["blk_t"]), lib.ptr(tb["blk_o"]), tb["nblk"], _CHUNK, float(group["lr"]), float(beta1), float(beta2),
                      float(group["eps"]), step, lib.stream())
+            # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on `_version`,
+            # e.g. the tensor-core weight copies of the drop-in modules) that they changed
+            torch.autograd.graph.increment_version(plist)
             for p in plist:
                 self.state[p]["step"] += 1     # CPU scalars, like torch's non-capturable Adam
         return loss

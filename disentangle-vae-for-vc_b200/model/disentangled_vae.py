@@ -7,7 +7,7 @@ their reference names, shapes and initialisation); their `forward` is never call
 libdvae_b200.so through `dvae_b200.engine`; there is no PyTorch / CPU fallback.
 
 Extras that do not change the reference API:
-  * `DisentangledVAE(..., precision="bf16"|"tf32")` (last, optional) or env DVAE_B200_PRECISION
+  * `DisentangledVAE(..., precision="fp16"|"tf32"|"bf16")` (last, optional) or env DVAE_B200_PRECISION
   * `DisentangledVAE.noise_hook`: callable(shape) -> fp32 CPU/CUDA tensor, to supply the reparameterisation noise
     externally (the reference draws it on the CPU default generator, model/disentangled_vae.py:224)
 """
@@ -26,11 +26,29 @@ from dvae_b200.engine import Engine, PreparedWeights
 from model.variational_base_vae import VariationalBaseModelVAE
 
 
+PRECISIONS = {"bf16": lib.BF16, "tf32": lib.TF32, "fp16": lib.F16}
+DEFAULT_PRECISION = "fp16"   # the fastest storage type that meets the reference-parity tolerance (DESIGN.md "Numerics")
+
+
 def _precision_tag(precision: Optional[str]) -> int:
-    p = (precision or os.environ.get("DVAE_B200_PRECISION", "bf16")).lower()
-    if p not in ("bf16", "tf32"):
-        raise ValueError(f"precision must be 'bf16' or 'tf32', got {p!r}")
-    return lib.BF16 if p == "bf16" else lib.TF32
+    p = (precision or os.environ.get("DVAE_B200_PRECISION", DEFAULT_PRECISION)).lower()
+    if p not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {p!r}")
+    return PRECISIONS[p]
+
+
+def default_grad_scale(dt: int, batch_size) -> float:
+    """Power-of-two factor the activation-gradient stream is carried at (dvae_b200.engine.Engine.grad_scale).  Only the
+    fp16 storage mode needs one: the loss hands back gradients of magnitude mse_cof / batch_size
+    (model/disentangled_vae.py:314-318), which this lifts to O(10..100) so that the small gradients further down stay in
+    fp16's normal range.  Override with DVAE_B200_GRAD_SCALE or `model.grad_scale = ...`."""
+    env = os.environ.get("DVAE_B200_GRAD_SCALE")
+    if env:
+        return float(env)
+    if dt != lib.F16:
+        return 1.0
+    import math
+    return float(2 ** (int(math.floor(math.log2(max(int(batch_size), 1)))) + 2))
 
 
 def init_weights(m):
@@ -145,7 +163,7 @@ class DisentangledVAE(nn.Module):
 
         self.postnet.__dict__["_owner"] = self  # plain attribute (not a registered sub-module): no state_dict recursion
         self._dt = _precision_tag(precision)
-        self._engine = Engine(self._dt, latent_dim, speaker_size)
+        self._engine = Engine(self._dt, latent_dim, speaker_size, grad_scale=default_grad_scale(self._dt, batch_size))
         self._param_names = [n for n, _ in self.named_parameters()]
         self._prep_cache = None
         self.noise_hook = None
@@ -153,6 +171,14 @@ class DisentangledVAE(nn.Module):
         self._last_saved = None
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def grad_scale(self) -> float:
+        return self._engine.grad_scale
+
+    @grad_scale.setter
+    def grad_scale(self, v: float) -> None:
+        self._engine.grad_scale = float(v)
+
     def _param_dict(self):
         return {n: p.data for n, p in self.named_parameters()}
 
@@ -160,15 +186,22 @@ class DisentangledVAE(nn.Module):
         return dict(self.named_buffers())
 
     def _prepared(self) -> PreparedWeights:
+        """Tensor-core copies of the parameters, re-derived whenever a parameter has been written (`_version` moves with
+        every in-place update: torch optimizers bump it themselves, dvae_b200.optim.Adam bumps it explicitly because its
+        kernel writes through raw pointers) or re-allocated."""
         params = list(self.parameters())
-        key = tuple((p.data_ptr(), p._version) for p in params) + (self._dt,)
-        if self._prep_cache is None or self._prep_cache[0] != key:
-            dev = params[0].device
-            if dev.type != "cuda":
+        ptrs = tuple(p.data_ptr() for p in params) + (self._dt,)
+        vers = tuple(p._version for p in params)
+        c = self._prep_cache
+        if c is None or c[0] != ptrs:
+            if params[0].device.type != "cuda":
                 raise RuntimeError("dvae_b200 runs on CUDA (sm_100a) only: move the module with .to('cuda'); "
                                    "there is no CPU path")
-            self._prep_cache = (key, PreparedWeights(self._dt, self._param_dict()))
-        return self._prep_cache[1]
+            c = self._prep_cache = [ptrs, vers, PreparedWeights(self._dt, self._param_dict())]
+        elif c[1] != vers:
+            c[2].refresh(self._param_dict())
+            c[1] = vers
+        return c[2]
 
     def _noise(self, shape) -> torch.Tensor:
         """ε ~ N(0,1), drawn like the reference on the CPU default generator (:224) unless noise_hook is set."""

@@ -9,8 +9,10 @@
  * Conventions: plain pointers + sizes, no allocation inside, no implicit synchronisation, everything is enqueued on
  * `stream` (a cudaStream_t passed as void*).  Return 0 = ok, 1 = invalid argument, 2 = CUDA error; the message is in
  * dvae_last_error() (thread local).  `dtype` tags the activation storage: 0 = bf16 (tcgen05 kind::f16),
- * 1 = fp32 kept on the tf32 grid (tcgen05 kind::tf32).  "act" below means that storage type.  Activations are
- * channels-last [rows, T, C]; T = 64 (model/disentangled_vae.py:165,235).
+ * 1 = fp32 kept on the tf32 grid (tcgen05 kind::tf32), 2 = IEEE fp16 (kind::f16; tf32's 10 mantissa bits at bf16's
+ * byte count and rate -- the caller keeps the activation-gradient stream scaled by a power of two: `scale` / `gscale`
+ * arguments put it on the stream, `alpha` arguments take it off the parameter gradients).  "act" below means that
+ * storage type.  Activations are channels-last [rows, T, C]; T = 64 (model/disentangled_vae.py:165,235).
  */
 #ifndef DVAE_B200_H
 #define DVAE_B200_H
@@ -33,7 +35,7 @@ int dvae_linear_fwd(int dtype, const void* x, long ldx, const void* w, const flo
 int dvae_linear_dgrad(int dtype, const void* dy, long lddy, const void* w, void* dx, float* dx_f32, const void* relu_mask,
                       long ldx, int M, int N, int K, int block_n, void* stream);
 int dvae_linear_wgrad(int dtype, const void* dy, long lddy, const void* x, long ldx, float* dw, long lddw, int M, int N,
-                      int K, void* stream);
+                      int K, float alpha, void* stream);
 
 /* ---- nn.Conv1d k=5 pad=2 (ConvNorm.forward :119-121; enc :154-160/:201-202, dec :178-189/:242-243, postnet :54-78/:81-87)
  *      x [R,T,Cin] act, wk [Cout,5,Cin] act (dvae_prep_conv_weight), y [R,T,Cout] */
@@ -45,7 +47,8 @@ int dvae_conv5_fwd_bnstats(int dtype, const void* x, const void* wk, const float
                            double* bn_ws, int rows_half, int halves, void* stream);
 int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,
                      void* stream);
-int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R, int T, int Cin, int Cout, void* stream);
+int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R, int T, int Cin, int Cout, float alpha,
+                     void* stream);
 
 /* ---- nn.LSTM recurrence (:163/:208 enc_lstm, :172/:238 dec_lstm1, :193/:246 dec_lstm2); the input projection is a
  *      dvae_linear_fwd with gate-interleaved weights.  xg [rows,T,D*4H] in: projection, out: activated gates */
@@ -55,10 +58,10 @@ int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float*
                   float* dc_ws, float* splitk_ws, int* tickets, int rows, int T, int H, int D, void* stream);
 int dvae_lstm_bwd_workspace(int dtype, int rows, int H, int D, long* ws_floats, int* num_tickets);
 int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* dwhh, int rows, int T, int H, int D,
-                       void* stream);
+                       float alpha, void* stream);
 
 /* ---- parameter re-layout (replaces cuDNN's internal filter transforms / flatten_parameters :206) */
-int dvae_prep_cast(int dtype, const float* src, void* dst, long n, void* stream);
+int dvae_prep_cast(int dtype, const float* src, void* dst, long n, float scale, void* stream);   /* dst = act(scale * src) */
 int dvae_copy_f32(const float* src, float* dst, long n, void* stream);
 int dvae_add_inplace(int dtype, void* a, const void* b, long n, void* stream);
 int dvae_add_f32_act(int dtype, const float* a, const void* b, float* out, long n, void* stream);  /* residual, channels-last */
@@ -72,7 +75,7 @@ int dvae_pack_ncl_to_cl(int dtype, const float* x, void* y, int R, int C, int T,
 int dvae_unpack_cl_to_ncl(int dtype, const void* a, int a_is_f32, const void* b, float* out_a, float* out_sum, int R, int C,
                           int T, void* stream);
 int dvae_recon_out_bwd(int dtype, const float* g_rec, const float* g_hat, void* d_rec, void* d_post, int R, int C, int T,
-                       void* stream);
+                       float scale, void* stream);
 
 /* ---- nn.BatchNorm1d + activation (:159 / :182,:189 / :58,:69,:78 with F.relu :202,:243 and torch.tanh :83) */
 int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
@@ -84,8 +87,8 @@ int dvae_bn_finalize_apply(int dtype, const void* y, void* out, const float* gam
 int dvae_bn_eval_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, const float* run_mean,
                      const float* run_var, float* stat, long rows, int C, int act, float eps, void* stream);
 int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* stat, double* ws, float* coef, void* dy,
-                      float* dgamma, float* dbeta, int rows_half, int halves, int C, int act, void* stream);
-int dvae_colsum(int dtype, const void* x, float* out, long rows, int C, long ldx, void* stream);
+                      float* dgamma, float* dbeta, int rows_half, int halves, int C, int act, float alpha, void* stream);
+int dvae_colsum(int dtype, const void* x, float* out, long rows, int C, long ldx, float alpha, void* stream);
 
 /* ---- latent tail: _reparameterize :222-228, pair-mean style posterior with detach :257-261, concatenations :263-272 */
 int dvae_latent_tail_fwd(int dtype, const float* heads, const float* eps_c1, const float* eps_c2, const float* eps_s,
@@ -94,7 +97,7 @@ int dvae_latent_tail_fwd(int dtype, const float* heads, const float* eps_c1, con
 int dvae_latent_tail_bwd(int dtype, const float* heads, const float* eps_c1, const float* eps_c2, const float* eps_s,
                          const float* dz, const float* dq1_mu, const float* dq1_lv, const float* dq2_mu, const float* dq2_lv,
                          const float* dzs_mu, const float* dzs_lv, void* dheads, int R, int L, int S, int sample_content,
-                         void* stream);
+                         float gscale, void* stream);
 
 /* ---- ConvolutionalMulVAE.loss_functionGVAE2 :310-327 (4 x L1-sum/batch_size, 2 x KL, style KL, total) */
 int dvae_loss_fwd(const float* x1, const float* x2, const float* r1, const float* r2, const float* h1, const float* h2, long n,

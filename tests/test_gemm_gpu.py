@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-DTS = ["bf16", "tf32"]
+DTS = ["bf16", "tf32", "fp16"]
 
 
 def _setup():
@@ -20,7 +20,7 @@ def _setup():
 
 def _dt(name):
     from dvae_b200 import lib
-    return lib.BF16 if name == "bf16" else lib.TF32
+    return {"bf16": lib.BF16, "tf32": lib.TF32, "fp16": lib.F16}[name]
 
 
 def _rand(shape, name, scale=1.0, seed=0):
@@ -28,6 +28,8 @@ def _rand(shape, name, scale=1.0, seed=0):
     t = torch.randn(shape, device="cuda", generator=g) * scale
     if name == "bf16":
         return t.to(torch.bfloat16)
+    if name == "fp16":
+        return t.to(torch.float16)
     # tf32: keep 10 mantissa bits so the tensor core sees exactly these values
     return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
 

@@ -20,12 +20,12 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
-DTS = ["bf16", "tf32"]
-TENSOR_TOL = {"bf16": 1.5e-2, "tf32": 2e-3}
-HAT_TOL = {"bf16": 4e-2, "tf32": 5e-3}
-LOSS_TOL = {"bf16": [1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 5e-3, 5e-3, 1e-2], "tf32": [1e-3] * 8}
-COS_TOL = {"bf16": 0.96, "tf32": 0.999}
-GLOBAL_COS_TOL = {"bf16": 0.997, "tf32": 0.9999}
+DTS = ["bf16", "tf32", "fp16"]
+TENSOR_TOL = {"bf16": 1.5e-2, "tf32": 2e-3, "fp16": 2e-3}
+HAT_TOL = {"bf16": 4e-2, "tf32": 5e-3, "fp16": 5e-3}
+LOSS_TOL = {"bf16": [1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 5e-3, 5e-3, 1e-2], "tf32": [1e-3] * 8, "fp16": [1e-3] * 8}
+COS_TOL = {"bf16": 0.96, "tf32": 0.999, "fp16": 0.999}
+GLOBAL_COS_TOL = {"bf16": 0.997, "tf32": 0.9999, "fp16": 0.9999}
 # conv biases that feed a train-mode BatchNorm have an identically-zero gradient (rounding noise in the reference)
 import re
 ZERO_GRAD = lambda k: re.search(r"(\.0\.conv\.bias$)|(^dec_modules\.\d\.0\.bias$)", k) is not None
@@ -123,6 +123,50 @@ def test_optimizer_step_and_state_dict_roundtrip(name, tmp_path):
     assert w2.load_last_model(str(tmp_path)) == 4
     for (k, a), (_, b) in zip(w.model.state_dict().items(), w2.model.state_dict().items()):
         assert torch.equal(a, b), k
+
+
+@pytest.mark.parametrize("name", ["tf32", "fp16"])
+def test_training_trajectory_follows_oracle_adam(name):
+    """Three optimizer steps through `step()` (forward, loss, backward, dvae_b200.optim.Adam) on fixed inputs and fixed
+    noise follow the oracle stepped by torch.optim.Adam: the forward of step k must see the weights written by step k-1
+    (the tensor-core weight copies are re-derived after every optimizer step).  lr is large enough that a forward at stale
+    weights would miss the oracle's trajectory by far more than the tolerance."""
+    from oracle import dvae_oracle as O
+    R, lr, steps = 8, 1e-3, 3
+    sd = O.synth_state_dict(0)
+    x1, x2, eps = O.synth_inputs(R)
+    x1, x2, eps = x1.cuda(), x2.cuda(), [e.cuda() for e in eps]
+    w = _build(name, R, sd)
+    for g in w.optimizer.param_groups:
+        g["lr"] = lr
+    w.model.train()
+    k = [0]
+
+    def hook(shape):
+        k[0] += 1
+        return eps[(k[0] - 1) % 3]
+    w.model.noise_hook = hook
+    ours = [w.step(x1, x2, torch.arange(R), train=True)[0] for _ in range(steps)]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    osd = O.clone_sd(sd, requires_grad=True, device="cuda")
+    names = [n for n, v in osd.items() if v.requires_grad]
+    opt = torch.optim.Adam([osd[n] for n in names], lr=lr)
+    ref = []
+    for _ in range(steps):
+        _, losses, grads = O.train_step(osd, x1, x2, eps, batch_size=R)
+        ref.append(losses[0].item())
+        for n in names:
+            osd[n].grad = grads[n]
+        opt.step()
+    assert abs(ref[1] - ref[0]) > 2e-2 * abs(ref[0]), f"oracle trajectory too flat to expose stale weights: {ref}"
+    for a, b in zip(ours, ref):
+        assert abs(a - b) <= 3e-3 * abs(b), (ours, ref)
+    # the fp32 master weights moved like the oracle's (Adam's first steps are sign-like: compare the update direction)
+    for n in ("dec_linear2.linear_layer.weight", "enc_modules.0.0.conv.weight", "dec_lstm2.weight_hh_l1"):
+        du = (dict(w.model.named_parameters())[n].detach() - sd[n].cuda()).flatten().double()
+        dr = (osd[n].detach() - sd[n].cuda()).flatten().double()
+        assert F.cosine_similarity(du, dr, dim=0).item() > 0.9, n
 
 
 @pytest.mark.parametrize("name", DTS)
@@ -245,47 +289,65 @@ def test_device_prefetcher_order_and_values():
     assert outs[0] is None and outs[1:] == [[float(i), 2.0 * i, 3.0 * i] for i in range(4)]
 
 
-@pytest.mark.parametrize("name", DTS)
-def test_full_size_step_equals_replicated_small_step(name):
-    """BASELINE config 2 size (R = 512 rows per call, 1024 rows in flight: persistent CTA-pair GEMMs, split-K reductions,
-    fused BatchNorm statistics, 128-CTA LSTM step kernels) through a size-independent property: a batch that repeats an
-    R = 8 batch 64 times, with `batch_size` scaled accordingly, has the same BatchNorm statistics, the same per-row outputs,
-    the same loss terms and the same parameter gradients as the R = 8 step -- which test_train_step_parity pins on the
-    oracle."""
-    from oracle import dvae_oracle as O
-    Rs, reps = 8, 64
-    sd = O.synth_state_dict(0)
-    x1, x2, eps = O.synth_inputs(Rs)
-    x1, x2, eps = x1.cuda(), x2.cuda(), [e.cuda() for e in eps]
+def _grad_report(mine, ref):
+    """(min per-tensor cosine, its name, global cosine) over the parameters whose gradient is not identically zero."""
+    worst, dot, na, nb = (1.0, ""), 0.0, 0.0, 0.0
+    for k, o in ref.items():
+        if ZERO_GRAD(k):
+            continue
+        g, o = mine[k].flatten().double(), o.flatten().double()
+        worst = min(worst, (F.cosine_similarity(g, o, dim=0).item(), k))
+        dot, na, nb = dot + (g * o).sum().item(), na + (g * g).sum().item(), nb + (o * o).sum().item()
+    return worst[0], worst[1], dot / (na * nb) ** 0.5
 
-    def run(R, a, b, noise):
-        w = _build(name, R, sd)
-        queue = list(noise)
-        w.model.noise_hook = lambda shape: queue.pop(0)
-        w.model.train()
-        out = w.model(a, b)
-        losses = w.loss_functionGVAE2(a, b, *out)
-        losses[0].backward()
-        return [t.detach() for t in out], [l.item() for l in losses], {k: p.grad.clone() for k, p in w.model.named_parameters()}
-    o_s, l_s, g_s = run(Rs, x1, x2, eps)
-    rep = lambda t: t.repeat(reps, *([1] * (t.dim() - 1)))
-    o_b, l_b, g_b = run(Rs * reps, rep(x1), rep(x2), [rep(e) for e in eps])
-    # bf16: a last-bit change of a BatchNorm statistic moves stored values by one ulp, and the postnet residual
-    # (outputs 2, 3) amplifies upstream differences ~3x (DESIGN.md section 5)
-    tol = {"bf16": (2e-2, 5e-2), "tf32": (2e-3, 6e-3)}[name]
-    for i, (a, b) in enumerate(zip(o_s, o_b)):
-        assert b.shape[0] == Rs * reps
-        for blk in (0, reps // 2, reps - 1):         # first, middle and last replica
-            d = (b[blk * Rs:(blk + 1) * Rs] - a).norm().item() / a.norm().item()
-            assert d <= tol[1 if i in (2, 3) else 0], (i, blk, d)
-    for a, b in zip(l_s, l_b):
-        assert abs(a - b) <= (4e-3 if name == "bf16" else 5e-4) * max(abs(a), 1e-3), (a, b)
-    dot = na = nb = 0.0
-    for k in g_s:
-        a, b = g_s[k].flatten().double(), g_b[k].flatten().double()
-        dot, na, nb = dot + (a * b).sum().item(), na + (a * a).sum().item(), nb + (b * b).sum().item()
-    cos, ratio = dot / (na * nb) ** 0.5, (nb / na) ** 0.5
-    # The two runs take their own ReLU / L1 branch decisions, and rounding-level differences flip a few of them: this is
-    # the "free decisions" regime of DESIGN.md section 5 (0.973 bf16 / 0.997 tf32 against the oracle), not exact equality.
-    assert cos > (0.95 if name == "bf16" else 0.99), cos
-    assert abs(ratio - 1.0) < (5e-2 if name == "bf16" else 1e-2), ratio
+
+# what each storage type is asserted to reach against the fp32 oracle at BASELINE config 2 (R = 512 distinct rows per
+# call); measured values are printed by the test and recorded in DESIGN.md "Numerics" / profiles/r02_parity_cfg2.txt
+FULL_TOL = {
+    #        8 tensors  2 hat   loss    KL     matched min / global      free min / global
+    "fp16": (1.5e-3, 4e-3, 1e-3, 2e-3, 0.999, 0.9999, 0.98, 0.99),
+    "tf32": (1.5e-3, 4e-3, 1e-3, 2e-3, 0.999, 0.9999, 0.98, 0.99),
+    "bf16": (1.5e-2, 4e-2, 1e-3, 1e-2, 0.96, 0.997, 0.90, 0.95),
+}
+
+
+@pytest.mark.parametrize("name", DTS)
+def test_config2_step_against_oracle(name):
+    """BASELINE config 2 itself (256 pairs x 128 frames = R = 512 DISTINCT rows per call, 1024 rows in flight: persistent
+    CTA-pair GEMMs, split-K reductions, fused BatchNorm statistics, 128-CTA LSTM step kernels) against the fp32 oracle
+    (cuDNN / cuBLAS with TF32 off) on the same inputs, weights and noise: all 10 outputs, the 8 loss terms and all 84
+    parameter gradients, at free AND at matched branch decisions."""
+    from oracle import dvae_oracle as O
+    from dvae_b200.engine import Engine
+    R = 512
+    sd = O.synth_state_dict(0)
+    x1, x2, eps = O.synth_inputs(R)
+    x1, x2, eps = x1.cuda(), x2.cuda(), [e.cuda() for e in eps]
+    w = _build(name, R, sd)
+    queue = list(eps)
+    w.model.noise_hook = lambda shape: queue.pop(0)
+    w.model.train()
+    w.model._debug_keep_saved = True
+    out = w.model(x1, x2)
+    losses = w.loss_functionGVAE2(x1, x2, *out)
+    losses[0].backward()
+    mine = {k: p.grad for k, p in w.model.named_parameters()}
+    o_out, o_losses, o_grads, _ = _oracle_step(sd, x1, x2, eps, R)
+    decisions = Engine.discrete_decisions(w.model._last_saved, [t.detach() for t in out], x1, x2)
+    w.model._last_saved = None
+    _, _, m_grads, _ = _oracle_step(sd, x1, x2, eps, R, decisions)
+    t_tol, h_tol, l_tol, kl_tol, c_min, c_glob, f_min, f_glob = FULL_TOL[name]
+    names = ["r1", "r2", "r1_hat", "r2_hat", "q1_mu", "q1_lv", "q2_mu", "q2_lv", "zs_mu", "zs_lv"]
+    rels = {n: (a - b).norm().item() / b.norm().item() for n, a, b in zip(names, out, o_out)}
+    lrel = [abs(a.item() - b.item()) / abs(b.item()) for a, b in zip(losses, o_losses)]
+    fm, fk, fg = _grad_report(mine, o_grads)
+    mm, mk, mg = _grad_report(mine, m_grads)
+    print(f"[config2 {name}] forward rel-L2 " + " ".join(f"{n}={v:.2e}" for n, v in rels.items()))
+    print(f"[config2 {name}] loss rel " + " ".join(f"{v:.1e}" for v in lrel))
+    print(f"[config2 {name}] gradient cosine matched: min {mm:.5f} ({mk}) global {mg:.6f}; free: min {fm:.5f} ({fk}) global {fg:.6f}")
+    for n, v in rels.items():
+        assert v <= (h_tol if n.endswith("hat") else t_tol), f"{n}: rel L2 {v:.3e}"
+    for i, v in enumerate(lrel):
+        assert v <= (l_tol if i < 5 else kl_tol), f"loss term {i}: rel {v:.3e}"
+    assert mm > c_min and mg > c_glob, f"matched decisions: min {mm} ({mk}), global {mg}"
+    assert fm > f_min and fg > f_glob, f"free decisions: min {fm} ({fk}), global {fg}"

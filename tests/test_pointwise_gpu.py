@@ -6,18 +6,20 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
-DTS = ["bf16", "tf32"]
+DTS = ["bf16", "tf32", "fp16"]
 
 
 def _dt(name):
     from dvae_b200 import lib
-    return lib.BF16 if name == "bf16" else lib.TF32
+    return {"bf16": lib.BF16, "tf32": lib.TF32, "fp16": lib.F16}[name]
 
 
 def _act(t, name):
     """Value as stored by the library: bf16 (RNE) or fp32 rounded to the tf32 grid (cvt.rna: 10 mantissa bits)."""
     if name == "bf16":
         return t.to(torch.bfloat16)
+    if name == "fp16":
+        return t.to(torch.float16)
     bits = t.float().contiguous().view(torch.int32)
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
