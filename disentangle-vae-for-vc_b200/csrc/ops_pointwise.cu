@@ -161,6 +161,57 @@ __global__ void cl_to_ncl_kernel(const TA* __restrict__ a, const TB* __restrict_
     if (out_sum != nullptr) out_sum[r * C * T + i] = tb[t * (C + 1) + c];
   }
 }
+// ---- conversion front / back end (model/variational_base_vae.py:335-348 chunking_mel, :295-296 time-concat + clamp), for
+// many utterances of different lengths in one launch.  Utterance u is a [C][T_u] fp32 matrix at mel + mel_off[u]; it owns
+// the chunks [chunk_first[u], chunk_first[u+1]) (T_u / 64 + 1 of them: the last one zero padded, a whole zero chunk when
+// T_u % 64 == 0).  One block per chunk.
+template <typename AT>
+__global__ void chunk_mel_kernel(const float* __restrict__ mel, const long* __restrict__ mel_off, const int* __restrict__ t_len,
+                                 const int* __restrict__ chunk_first, const int* __restrict__ chunk_utt, AT* __restrict__ x_cl,
+                                 int C, int T) {
+  extern __shared__ float tile[];  // [C][T+1]
+  const long k = blockIdx.x;
+  const int u = chunk_utt[k];
+  const int t0 = (static_cast<int>(k) - chunk_first[u]) * T;
+  const int Tu = t_len[u];
+  const float* m = mel + mel_off[u];
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int c = i / T, t = i - c * T;
+    tile[c * (T + 1) + t] = (t0 + t < Tu) ? m[static_cast<long>(c) * Tu + t0 + t] : 0.f;
+  }
+  __syncthreads();
+  AT* y = x_cl + k * C * T;
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    y[i] = from_f32<AT>(tile[c * (T + 1) + t]);
+  }
+}
+// chunk k of utterance u, channels-last a (fp32) [+ b (act)] -> out_u [C][n_u * T] at out + out_off[u], frames
+// [(k - chunk_first[u]) * T, +T); optionally clamped to [lo, hi]
+template <typename AT>
+__global__ void unchunk_mel_kernel(const float* __restrict__ a, const AT* __restrict__ b, const long* __restrict__ out_off,
+                                   const int* __restrict__ chunk_first, const int* __restrict__ chunk_utt, float* __restrict__ out,
+                                   int C, int T, int clamp, float lo, float hi) {
+  extern __shared__ float tile[];  // [T][C+1]
+  const long k = blockIdx.x;
+  const int u = chunk_utt[k];
+  const int kk = static_cast<int>(k) - chunk_first[u];
+  const int n_u = chunk_first[u + 1] - chunk_first[u];
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int t = i / C, c = i - t * C;
+    float v = a[k * C * T + i];
+    if (b != nullptr) v += to_f32(b[k * C * T + i]);
+    if (clamp) v = fminf(fmaxf(v, lo), hi);
+    tile[t * (C + 1) + c] = v;
+  }
+  __syncthreads();
+  float* o = out + out_off[u];
+  const long ld = static_cast<long>(n_u) * T;
+  for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
+    const int c = i / T, t = i - c * T;
+    o[c * ld + static_cast<long>(kk) * T + t] = tile[t * (C + 1) + c];
+  }
+}
 // backward of the residual output: d_rec[r][t][c] = g_rec[r][c][t] + g_hat[r][c][t];  d_post = g_hat  (either may be null)
 template <typename AT>
 __global__ void recon_out_bwd_kernel(const float* __restrict__ g_rec, const float* __restrict__ g_hat, AT* __restrict__ d_rec,
@@ -592,6 +643,29 @@ int dvae_unpack_cl_to_ncl(int dtype, const void* a, int a_is_f32, const void* b,
   } else {
     DISPATCH_AT(dtype, cl_to_ncl_kernel<AT, AT><<<R, 256, smem, st>>>((const AT*)a, (const AT*)b, out_a, out_sum, C, T));
   }
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// chunking_mel for a batch of utterances (see chunk_mel_kernel): x_cl act [n_chunks, T, C]
+int dvae_chunk_mel(int dtype, const float* mel, const long* mel_off, const int* t_len, const int* chunk_first,
+                   const int* chunk_utt, void* x_cl, int n_chunks, int C, int T, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (n_chunks == 0) return 0;
+  const int smem = C * (T + 1) * 4;
+  DVAE_REQUIRE(smem <= 48 * 1024, "C*(T+1) tile must fit 48 KB of shared memory");
+  DISPATCH_AT(dtype, chunk_mel_kernel<AT><<<n_chunks, 256, smem, st>>>(mel, mel_off, t_len, chunk_first, chunk_utt, (AT*)x_cl, C, T));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// time-concatenation of the chunks of every utterance (+ residual b, + clamp): out_u fp32 [C, n_u * T] at out + out_off[u]
+int dvae_unchunk_mel(int dtype, const float* a, const void* b, const long* out_off, const int* chunk_first, const int* chunk_utt,
+                     float* out, int n_chunks, int C, int T, int clamp, float lo, float hi, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  if (n_chunks == 0) return 0;
+  const int smem = T * (C + 1) * 4;
+  DVAE_REQUIRE(smem <= 48 * 1024, "T*(C+1) tile must fit 48 KB of shared memory");
+  DISPATCH_AT(dtype, unchunk_mel_kernel<AT><<<n_chunks, 256, smem, st>>>(a, (const AT*)b, out_off, chunk_first, chunk_utt, out, C, T,
+                                                                        clamp, lo, hi));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -89,37 +89,84 @@ class AsyncScalars:
 
 
 class SpeakerGroupBatchSampler(torch.utils.data.Sampler):
-    """Batch sampler for data-parallel training: every step draws a global batch of `world * pairs_per_rank` items and
-    hands each rank the rows of WHOLE speaker groups (`parallel.shard_pairs_by_speaker`), sorted by speaker, so that the
-    speaker-group kernels never need a cross-rank exchange.  All ranks must construct it with the same
-    `speaker_ids`, `seed` and call `set_epoch` with the same epoch: the global permutation is then identical everywhere.
+    """Batch sampler for data-parallel training: every step draws `world * pairs_per_rank / group_size` DISTINCT speakers
+    with `group_size` rows each and hands every rank the rows of `pairs_per_rank / group_size` whole speakers, sorted by
+    speaker -- so each rank gets EXACTLY `pairs_per_rank` rows every step (equal shards: the all-reduce average of the
+    per-rank losses is the global-batch loss, and shapes never change), no speaker is split across ranks, and the
+    speaker-group kernels never need a cross-rank exchange.
 
-    With equally sized speaker groups (the BASELINE configs: 8 utterances per speaker) every rank gets exactly
-    `pairs_per_rank` rows; otherwise ranks differ by at most one group.  Use as `DataLoader(ds, batch_sampler=...)`.
-    The reference (`train.py:49-58`) uses a plain shuffled DataLoader on one process."""
+    Per epoch every speaker's items are shuffled and cut into chunks of `group_size` (a remainder shorter than that is
+    dropped for the epoch); the chunks are shuffled and dealt into steps greedily so that a step never holds two chunks of
+    one speaker; chunks that cannot complete a step are dropped.  All ranks must construct the sampler with the same
+    `speaker_ids` / `seed` and call `set_epoch` with the same epoch: the plan is then identical everywhere.
+    `group_size` defaults to the largest divisor of `pairs_per_rank` that every speaker can fill (BASELINE configs:
+    8 utterances per speaker).  Use as `DataLoader(ds, batch_sampler=...)`.  The reference (`train.py:49-58`) uses a plain
+    shuffled DataLoader on one process."""
 
     def __init__(self, speaker_ids, pairs_per_rank: int, rank: int = 0, world: int = 1, shuffle: bool = True, seed: int = 0,
-                 drop_last: bool = True):
+                 drop_last: bool = True, group_size: Optional[int] = None):
         import numpy as np
         self.ids = np.asarray(speaker_ids).reshape(-1)
         self.pairs_per_rank, self.rank, self.world = int(pairs_per_rank), int(rank), int(world)
         self.shuffle, self.seed, self.drop_last, self.epoch = shuffle, seed, drop_last, 0
         if not 0 <= self.rank < self.world:
             raise ValueError("rank must be in [0, world)")
+        if not drop_last:
+            raise ValueError("equal shards need drop_last=True (a partial step cannot give every rank pairs_per_rank rows)")
+        speakers, counts = np.unique(self.ids, return_counts=True)
+        if group_size is None:
+            smallest = int(counts.min())
+            group_size = max(d for d in range(1, self.pairs_per_rank + 1) if self.pairs_per_rank % d == 0 and d <= smallest)
+        self.group_size = int(group_size)
+        if self.group_size < 1 or self.pairs_per_rank % self.group_size != 0:
+            raise ValueError("group_size must divide pairs_per_rank")
+        self.groups_per_step = self.world * self.pairs_per_rank // self.group_size
+        usable = int((counts >= self.group_size).sum())
+        if usable < self.groups_per_step:
+            raise ValueError(f"a step needs {self.groups_per_step} distinct speakers with >= {self.group_size} items each, "
+                             f"the dataset has {usable}: no rank may receive an empty shard")
+        self._plan_cache = (None, None)
 
     def set_epoch(self, epoch: int) -> None:
         self.epoch = int(epoch)
 
+    def _plan(self):
+        """Steps of this epoch: a list of [groups_per_step][group_size] index arrays, speakers sorted within a step."""
+        import numpy as np
+        if self._plan_cache[0] == self.epoch:
+            return self._plan_cache[1]
+        rng = np.random.default_rng(self.seed + self.epoch)
+        chunks = []                                    # (speaker, indices)
+        for spk in np.unique(self.ids):
+            idx = np.flatnonzero(self.ids == spk)
+            if self.shuffle:
+                idx = idx[rng.permutation(len(idx))]
+            for c in range(len(idx) // self.group_size):
+                chunks.append((spk, idx[c * self.group_size:(c + 1) * self.group_size]))
+        order = rng.permutation(len(chunks)) if self.shuffle else np.arange(len(chunks))
+        pending = [chunks[i] for i in order]
+        steps = []
+        while True:
+            taken, used, rest = [], set(), []
+            for ch in pending:
+                if len(taken) < self.groups_per_step and ch[0] not in used:
+                    taken.append(ch)
+                    used.add(ch[0])
+                else:
+                    rest.append(ch)
+            if len(taken) < self.groups_per_step:
+                break
+            taken.sort(key=lambda ch: ch[0])           # rows of a step sorted by speaker: contiguous group ranges per rank
+            steps.append(taken)
+            pending = rest
+        self._plan_cache = (self.epoch, steps)
+        return steps
+
     def __len__(self) -> int:
-        g = self.pairs_per_rank * self.world
-        return len(self.ids) // g if self.drop_last else -(-len(self.ids) // g)
+        return len(self._plan())
 
     def __iter__(self):
-        import numpy as np
-        from .parallel import shard_pairs_by_speaker
-        n, g = len(self.ids), self.pairs_per_rank * self.world
-        order = np.random.default_rng(self.seed + self.epoch).permutation(n) if self.shuffle else np.arange(n)
-        for b in range(len(self)):
-            glob = order[b * g:(b + 1) * g]
-            local = shard_pairs_by_speaker(self.ids[glob], self.rank, self.world)
-            yield glob[local].tolist()
+        k = self.pairs_per_rank // self.group_size     # whole speakers per rank and step
+        for step in self._plan():
+            mine = step[self.rank * k:(self.rank + 1) * k]
+            yield [int(i) for _, idx in mine for i in idx]

@@ -55,6 +55,8 @@ _SIGNATURES = {
     "dvae_pack_ncl_to_cl": [_i, _p, _p, _i, _i, _i, _p],
     "dvae_unpack_cl_to_ncl": [_i, _p, _i, _p, _p, _p, _i, _i, _i, _p],
     "dvae_recon_out_bwd": [_i, _p, _p, _p, _p, _i, _i, _i, _f, _p],
+    "dvae_chunk_mel": [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "dvae_unchunk_mel": [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p],
     # batch norm / reductions
     "dvae_bn_train_fwd": [_i] + [_p] * 9 + [_i, _i, _i, _i, _f, _f, _p],
     "dvae_bn_finalize_apply": [_i] + [_p] * 9 + [_i, _i, _i, _i, _f, _f, _p],

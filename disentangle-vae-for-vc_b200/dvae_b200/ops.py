@@ -263,6 +263,28 @@ def recon_out_bwd(dt: int, g_rec: Optional[Tensor], g_hat: Optional[Tensor], d_r
     call("dvae_recon_out_bwd", dt, ptr(g_rec), ptr(g_hat), ptr(d_rec), ptr(d_post), R, Cc, T, float(scale), stream())
 
 
+def chunk_mel(dt: int, mel: Tensor, mel_off: Tensor, t_len: Tensor, chunk_first: Tensor, chunk_utt: Tensor, n_chunks: int,
+              C: int = 80, T: int = 64) -> Tensor:
+    """chunking_mel for many utterances: flat fp32 `mel` holding [C, t_len[u]] matrices at mel_off[u] -> act [n_chunks, T, C]."""
+    _chk(mel, torch.float32), _chk(mel_off, torch.int64), _chk(t_len, torch.int32), _chk(chunk_first, torch.int32)
+    _chk(chunk_utt, torch.int32)
+    x_cl = torch.empty((n_chunks, T, C), device=mel.device, dtype=act_dtype(dt))
+    call("dvae_chunk_mel", dt, ptr(mel), ptr(mel_off), ptr(t_len), ptr(chunk_first), ptr(chunk_utt), ptr(x_cl), n_chunks, C, T, stream())
+    return x_cl
+
+
+def unchunk_mel(dt: int, a: Tensor, b: Optional[Tensor], out: Tensor, out_off: Tensor, chunk_first: Tensor, chunk_utt: Tensor,
+                clamp: Optional[Tuple[float, float]] = None) -> None:
+    """a fp32 [n_chunks, T, C] (+ b act) -> per-utterance [C, n_u * T] matrices inside flat fp32 `out`, optionally clamped."""
+    _chk(a, torch.float32), _chk(out, torch.float32), _chk(out_off, torch.int64)
+    n, T, C = a.shape
+    if b is not None:
+        _chk(b, act_dtype(dt))
+    lo, hi = clamp if clamp is not None else (0.0, 0.0)
+    call("dvae_unchunk_mel", dt, ptr(a), ptr(b), ptr(out_off), ptr(chunk_first), ptr(chunk_utt), ptr(out), n, C, T,
+         int(clamp is not None), float(lo), float(hi), stream())
+
+
 # ------------------------------------------------------------------------------- batch norm
 def bn_train_fwd(dt: int, y: Tensor, gamma: Tensor, beta: Tensor, run_mean: Optional[Tensor], run_var: Optional[Tensor],
                  num_batches: Optional[Tensor], halves: int, act: int, eps: float, momentum: float):

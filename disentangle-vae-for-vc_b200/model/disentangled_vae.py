@@ -40,15 +40,17 @@ def _precision_tag(precision: Optional[str]) -> int:
 def default_grad_scale(dt: int, batch_size) -> float:
     """Power-of-two factor the activation-gradient stream is carried at (dvae_b200.engine.Engine.grad_scale).  Only the
     fp16 storage mode needs one: the loss hands back gradients of magnitude mse_cof / batch_size
-    (model/disentangled_vae.py:314-318), which this lifts to O(10..100) so that the small gradients further down stay in
-    fp16's normal range.  Override with DVAE_B200_GRAD_SCALE or `model.grad_scale = ...`."""
+    (model/disentangled_vae.py:314-318), which this lifts to O(1).  Measured with random-init weights
+    (scripts/diag_gradscale.py, profiles/r02_gradscale.txt): the stream then peaks at ~1.6e3 (first decoder convolution)
+    -- 40x below fp16's 65504 -- and its smallest per-tensor maximum is ~3, 5e4 above the smallest normal number.
+    Override with DVAE_B200_GRAD_SCALE or `model.grad_scale = ...`."""
     env = os.environ.get("DVAE_B200_GRAD_SCALE")
     if env:
         return float(env)
     if dt != lib.F16:
         return 1.0
     import math
-    return float(2 ** (int(math.floor(math.log2(max(int(batch_size), 1)))) + 2))
+    return float(2.0 ** (int(math.floor(math.log2(max(int(batch_size), 1)))) - 2))
 
 
 def init_weights(m):
@@ -59,6 +61,12 @@ def init_weights(m):
     if type(m) == nn.Conv1d:
         torch.nn.init.xavier_uniform_(m.weight)
         m.bias.data.fill_(0)
+
+
+def tile(a, dim, n_tile):
+    """model/disentangled_vae.py:35-41: every slice along `dim` repeated n_tile times in place (a repeat-interleave; the
+    reference builds the index with a hard-coded torch.cuda.LongTensor).  Unused by the reference; kept for API parity."""
+    return torch.repeat_interleave(a, n_tile, dim=dim)
 
 
 class LinearNorm(nn.Module):
@@ -110,7 +118,7 @@ class _NetworkFn(torch.autograd.Function):
         W = module._prepared()
         P, B = module._param_dict(), module._buffer_dict()
         outs, saved = module._engine.forward(W, P, B, x1, x2, (e1, e2, e3), module.training, sample_content, keep)
-        ctx.engine, ctx.W, ctx.saved, ctx.names = module._engine, W, saved, module._param_names
+        ctx.engine, ctx.W, ctx.saved, ctx.names, ctx.params = module._engine, W, saved, module._param_names, params
         if module._debug_keep_saved:
             module._last_saved = saved      # diagnostics / parity tests only
         return outs
@@ -119,6 +127,11 @@ class _NetworkFn(torch.autograd.Function):
     def backward(ctx, *gouts):
         if ctx.saved is None:
             raise RuntimeError("backward through a forward that ran without gradient tracking")
+        if ctx.engine.buckets is not None and any(p.grad is not None for p in ctx.params):
+            # autograd adopts the returned bucket views as p.grad without copying; a second backward would overwrite them in
+            # place instead of accumulating
+            raise RuntimeError("bucketed (data-parallel) backward needs p.grad to be None: call optimizer.zero_grad() "
+                               "(set_to_none=True) before every backward; gradient accumulation is not supported with buckets")
         grads = ctx.engine.backward(ctx.W, ctx.saved, gouts)
         ctx.saved = None
         return (None,) * 8 + tuple(grads[n] for n in ctx.names)

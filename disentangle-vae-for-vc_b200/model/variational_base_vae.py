@@ -209,6 +209,83 @@ class VariationalBaseModelVAE():
             _, converted = m.decode_with_postnet(torch.cat([trg_style, c_mu], dim=-1))
         return recons, converted
 
+    def convert_utterances(self, sources, targets, clamp=True):
+        """Many-to-many conversion of whole utterances in one pass (BASELINE config 4; the reference loops over utterances
+        in Python, :264-296): `sources` / `targets` are either a [U, 80, T] tensor or a list of U [80, T_i] tensors / arrays
+        (any lengths); target i lends its style to source i.  Everything between the raw mels and the finished outputs runs
+        on the device: chunking_mel (:335-348: 64-frame chunks, last one zero padded, a whole zero chunk when T % 64 == 0),
+        ONE encoder pass over all source + target chunks, per-utterance style means (group-mean kernel), ONE decoder pass
+        for reconstruction + conversion, postnet on the converted half, time-concat and clamp (:288-296).
+
+        Returns (recons, converted): [U, 80, n*64] tensors for tensor input, lists of [80, n_i*64] tensors for list input;
+        `converted` = decode + postnet residual, clamped to [0, 1] like :296 unless clamp=False."""
+        from dvae_b200 import ops
+        from dvae_b200.engine import N_MELS, T_FRAMES
+        m = self.model
+        dev = next(m.parameters()).device
+        dt, E = m._dt, m._engine
+        S, L = m.speaker_size, m.latent_dim
+        as_tensor = torch.is_tensor(sources)
+
+        def flatten(mels):
+            """-> (flat fp32 device buffer, lengths)"""
+            if torch.is_tensor(mels):
+                assert mels.dim() == 3 and mels.shape[1] == N_MELS, "expected [U, 80, T]"
+                return mels.to(device=dev, dtype=torch.float32).contiguous().view(-1), [int(mels.shape[2])] * int(mels.shape[0])
+            parts = [torch.as_tensor(x).to(device=dev, dtype=torch.float32).contiguous() for x in mels]
+            assert all(p.dim() == 2 and p.shape[0] == N_MELS for p in parts), "expected a list of [80, T_i]"
+            return torch.cat([p.view(-1) for p in parts]), [int(p.shape[1]) for p in parts]
+        src_flat, src_len = flatten(sources)
+        trg_flat, trg_len = flatten(targets)
+        U = len(src_len)
+        assert len(trg_len) == U, "one target utterance per source utterance"
+
+        def plan(lengths):
+            """Integer bookkeeping of chunking_mel (host, exact): offsets of every utterance and of its chunks."""
+            n = np.asarray([t // T_FRAMES + 1 for t in lengths], dtype=np.int64)
+            first = np.concatenate([[0], np.cumsum(n)]).astype(np.int32)
+            mel_off = np.concatenate([[0], np.cumsum(np.asarray(lengths, dtype=np.int64) * N_MELS)])[:-1].astype(np.int64)
+            out_off = np.concatenate([[0], np.cumsum(n * T_FRAMES * N_MELS)]).astype(np.int64)
+            utt = np.repeat(np.arange(len(lengths), dtype=np.int32), n)
+            return n, first, mel_off, out_off, utt
+        n_s, first_s, off_s, out_off_s, utt_s = plan(src_len)
+        n_t, first_t, off_t, _, utt_t = plan(trg_len)
+        Ns, Nt = int(first_s[-1]), int(first_t[-1])
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+        d_first_s, d_off_s, d_out_off_s, d_utt_s = up(first_s), up(off_s), up(out_off_s), up(utt_s)
+        d_first_t, d_off_t, d_utt_t = up(first_t), up(off_t), up(utt_t)
+        d_len_s, d_len_t = up(np.asarray(src_len, dtype=np.int32)), up(np.asarray(trg_len, dtype=np.int32))
+        with torch.no_grad():
+            W, P, B = m._prepared(), m._param_dict(), m._buffer_dict()
+            x_cl = torch.empty((Ns + Nt, T_FRAMES, N_MELS), device=dev, dtype=ops.act_dtype(dt))
+            x_cl[:Ns] = ops.chunk_mel(dt, src_flat, d_off_s, d_len_s, d_first_s, d_utt_s, Ns)
+            x_cl[Ns:] = ops.chunk_mel(dt, trg_flat, d_off_t, d_len_t, d_first_t, d_utt_t, Nt)
+            heads, _ = E.encode_rows(W, P, B, x_cl, 1, m.training, None)          # [Ns + Nt, 2L] fp32
+            s_mu = heads[:Ns, :S].contiguous()
+            t_mu = heads[Ns:, :S].contiguous()
+            c_mu = heads[:Ns, 2 * S:2 * S + (L - S)]
+
+            def utt_mean(mu, gid_rows):
+                acc, cnt = ops.group_accumulate(ops.MODE_MEAN, mu, mu, gid_rows, U)
+                out, _ = ops.group_finalize(ops.MODE_MEAN, acc, cnt, d_utt_s, Ns, S, want_b=False)
+                return out
+            z = torch.cat([torch.cat([utt_mean(s_mu, d_utt_s), c_mu], dim=-1),
+                           torch.cat([utt_mean(t_mu, d_utt_t), c_mu], dim=-1)], dim=0).contiguous()
+            z_act = torch.empty(z.shape, device=dev, dtype=ops.act_dtype(dt))
+            ops.prep_cast(dt, z, z_act)
+            rec, rec32 = E.decode_rows(W, P, B, z_act, 1, m.training, None)        # rows [0, Ns): recons, [Ns, 2Ns): converted
+            post = E.postnet_rows(W, P, B, rec[Ns:], 1, m.training, None)
+            total = int(out_off_s[-1])
+            recons = torch.empty((total,), device=dev, dtype=torch.float32)
+            converted = torch.empty((total,), device=dev, dtype=torch.float32)
+            ops.unchunk_mel(dt, rec32[:Ns], None, recons, d_out_off_s, d_first_s, d_utt_s)
+            ops.unchunk_mel(dt, rec32[Ns:], post, converted, d_out_off_s, d_first_s, d_utt_s, clamp=(0.0, 1.0) if clamp else None)
+        if as_tensor:
+            n0 = int(n_s[0])
+            return recons.view(U, N_MELS, n0 * T_FRAMES), converted.view(U, N_MELS, n0 * T_FRAMES)
+        split = lambda flat: [flat[int(out_off_s[u]):int(out_off_s[u + 1])].view(N_MELS, int(n_s[u]) * T_FRAMES) for u in range(U)]
+        return split(recons), split(converted)
+
     def voice_conversion_mel(self, ckp_path, generation_dir, src_spk, trg_spk, dataset_fp=''):
         """Convert the first two utterances of `src_spk` to the voice of `trg_spk` (:243-330).  The mel-domain
         part runs here; waveform synthesis needs the external WaveNet vocoder + its checkpoint and is skipped
@@ -221,20 +298,21 @@ class VariationalBaseModelVAE():
         vocoder = _try_build_vocoder(dev)
         source_utt_fp = np.sort(glob(os.path.join(dataset_fp, src_spk, "*.npy")))
         target_utt_fp = glob(os.path.join(dataset_fp, trg_spk, '*.npy'))
-        for i in range(min(2, len(source_utt_fp))):
-            source_mel = chunking_mel(np.load(source_utt_fp[i])).to(dev).float()
-            rnd_trg = np.random.choice(len(target_utt_fp), 1)[0]
-            target_mel = chunking_mel(np.load(target_utt_fp[rnd_trg])).to(dev).float()
+        n_conv = min(2, len(source_utt_fp))                      # the reference converts the first two source utterances (:264)
+        if n_conv == 0:
+            return
+        sources = [np.load(source_utt_fp[i]) for i in range(n_conv)]
+        targets = [np.load(target_utt_fp[np.random.choice(len(target_utt_fp), 1)[0]]) for _ in range(n_conv)]
+        recons, converted = self.convert_utterances(sources, targets)   # chunking, encode, style mean, decode, concat, clamp: on device
+        for i in range(n_conv):
             stem = Path(source_utt_fp[i]).stem.split("_")
             utterance_id = stem[-2] if len(stem) >= 2 else stem[-1]
             print('convert utterance: {} from --->{} to --->{}'.format(utterance_id, src_spk, trg_spk))
-            zeros_s = torch.zeros(source_mel.shape[0], dtype=torch.int32, device=dev)
-            zeros_t = torch.zeros(target_mel.shape[0], dtype=torch.int32, device=dev)
-            recons, converted = self.convert_chunks(source_mel, zeros_s, target_mel, zeros_t, 1)
-            cat_t = lambda m: torch.cat([m[j] for j in range(m.shape[0])], 1)
-            recons_voice = cat_t(recons).cpu().numpy()
-            converted_voice = torch.clamp(cat_t(converted), min=0, max=1.0).cpu().numpy()
-            source_full = cat_t(source_mel).cpu().numpy()
+            recons_voice = recons[i].cpu().numpy()
+            converted_voice = converted[i].cpu().numpy()
+            n_frames = recons_voice.shape[1]
+            source_full = np.zeros((sources[i].shape[0], n_frames), dtype=np.float32)
+            source_full[:, :sources[i].shape[1]] = sources[i]
             _save_mel(source_full, os.path.join(save_dir, f'original_{src_spk}_{utterance_id}'), 'original')
             _save_mel(converted_voice, os.path.join(save_dir, f'convert_{src_spk}_{trg_spk}_{utterance_id}'), 'convert')
             _save_mel(recons_voice, os.path.join(save_dir, f'recons_{src_spk}_{utterance_id}'), 'reconstruct')

@@ -77,6 +77,15 @@ int dvae_unpack_cl_to_ncl(int dtype, const void* a, int a_is_f32, const void* b,
 int dvae_recon_out_bwd(int dtype, const float* g_rec, const float* g_hat, void* d_rec, void* d_post, int R, int C, int T,
                        float scale, void* stream);
 
+/* ---- conversion front / back end for a batch of utterances of different lengths: chunking_mel
+ *      (model/variational_base_vae.py:335-348; utterance u = fp32 [C, t_len[u]] at mel + mel_off[u], chunks
+ *      [chunk_first[u], chunk_first[u+1]), chunk_utt[k] = utterance of chunk k) and the time-concat + residual + clamp of
+ *      :288-296 (out_u = fp32 [C, n_u * T] at out + out_off[u]) */
+int dvae_chunk_mel(int dtype, const float* mel, const long* mel_off, const int* t_len, const int* chunk_first,
+                   const int* chunk_utt, void* x_cl, int n_chunks, int C, int T, void* stream);
+int dvae_unchunk_mel(int dtype, const float* a, const void* b, const long* out_off, const int* chunk_first, const int* chunk_utt,
+                     float* out, int n_chunks, int C, int T, int clamp, float lo, float hi, void* stream);
+
 /* ---- nn.BatchNorm1d + activation (:159 / :182,:189 / :58,:69,:78 with F.relu :202,:243 and torch.tanh :83) */
 int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
                       float* run_var, long long* num_batches, double* ws, float* stat, int rows_half, int halves, int C,

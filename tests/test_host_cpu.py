@@ -141,8 +141,8 @@ def test_bucket_plan_covers_all_parameters(built_lib):
 
 
 def test_speaker_group_batch_sampler(built_lib):
-    """Per step the ranks' index lists partition the global batch, every speaker's rows land on one rank, rows come sorted
-    by speaker, and all ranks agree on the permutation (same seed / epoch)."""
+    """Per step the ranks' index lists partition the global batch into EQUAL shards of whole speakers, rows come sorted by
+    speaker, and all ranks agree on the plan (same seed / epoch)."""
     import numpy as np
     from dvae_b200.data import SpeakerGroupBatchSampler
     ids = np.repeat(np.arange(12), 8)                       # 12 speakers x 8 utterances
@@ -161,8 +161,9 @@ def test_speaker_group_batch_sampler(built_lib):
         seen += union
         owners = {}
         for r in range(world):
+            assert len(steps[r][b]) == ppr                 # equal shards, every step
             spk = ids[steps[r][b]]
-            assert list(spk) == sorted(spk) or len(set(spk)) == len({k for k, _ in __import__("itertools").groupby(spk)})
+            assert list(spk) == sorted(spk)
             for sp in set(spk.tolist()):
                 assert owners.setdefault(sp, r) == r       # a speaker's rows of this batch are on one rank
     assert len(set(seen)) == len(seen)                      # no index is used twice in an epoch
@@ -170,3 +171,37 @@ def test_speaker_group_batch_sampler(built_lib):
     assert again == steps[1]                                # deterministic for a fixed (seed, epoch)
     samplers[1].set_epoch(4)
     assert list(iter(samplers[1])) != steps[1]
+
+
+def test_speaker_group_batch_sampler_uneven_speakers(built_lib):
+    """Speakers with different numbers of utterances (the advisor's scenario: 64 speakers, world 2 and 8): every rank still
+    gets exactly pairs_per_rank rows per step, never an empty shard, and a step never splits a speaker."""
+    import numpy as np
+    from dvae_b200.data import SpeakerGroupBatchSampler
+    rng = np.random.default_rng(1)
+    counts = rng.integers(8, 20, size=64)
+    ids = np.repeat(np.arange(64), counts)
+    ids = ids[rng.permutation(len(ids))]
+    for world in (2, 8):
+        ppr = 32
+        samplers = [SpeakerGroupBatchSampler(ids, ppr, r, world, seed=3) for r in range(world)]
+        assert samplers[0].group_size == 8
+        steps = [list(iter(s)) for s in samplers]
+        assert len(steps[0]) >= 1 and len({len(st) for st in steps}) == 1
+        for b in range(len(steps[0])):
+            owners = {}
+            for r in range(world):
+                assert len(steps[r][b]) == ppr
+                for sp in set(ids[steps[r][b]].tolist()):
+                    assert owners.setdefault(sp, r) == r
+    with pytest.raises(ValueError, match="distinct speakers"):
+        SpeakerGroupBatchSampler(np.repeat(np.arange(3), 8), 8, 0, 4)          # 3 speakers cannot feed 4 ranks
+
+
+def test_tile_helper(built_lib):
+    """model/disentangled_vae.py:35-41 (dead helper): every slice along `dim` repeated n times in place."""
+    from model.disentangled_vae import tile
+    a = torch.arange(6.0).view(2, 3)
+    ref_idx = np.concatenate([2 * np.arange(3) + i for i in range(2)])          # the reference's index construction
+    assert torch.equal(tile(a, 0, 3), a.repeat(3, 1)[torch.from_numpy(ref_idx)])
+    assert tuple(tile(a, 1, 2).shape) == (2, 6) and torch.equal(tile(a, 1, 2)[:, ::2], a)
