@@ -10,7 +10,7 @@
 namespace dvae {
 
 // activation storage: bf16 or fp16 (tcgen05 kind::f16), or fp32 kept on the tf32 grid (kind::tf32)
-enum DType : int { kBF16 = 0, kTF32 = 1, kF16 = 2 };
+enum DType : int { kBF16 = 0, kTF32 = 1, kF16 = 2, kF32 = 3 };   // kF32: plain fp32 (memory-bound kernels only)
 
 void set_last_error(const std::string& msg);
 

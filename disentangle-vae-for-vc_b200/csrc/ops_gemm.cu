@@ -225,21 +225,26 @@ static bool tma_store_possible(const void* out, const float* out_f32, const void
 }
 
 // ------------------------------------------------------------------------------------ Linear
+// b_terms = 2: w is the split-precision weight [N, 2K] = [w_hi | w_lo] and the product is x . w_hi^T + x . w_lo^T: the
+// k-loop runs twice over the same A tiles ("tap" 1 moves only the B coordinate by K columns).  out_cat: see EpiStore.
 template <typename AT>
 static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, AT* out, float* out_f32, long ldo, int M,
-                        int N, int K, int relu, int bn_override, cudaStream_t st) {
+                        int N, int K, int relu, int bn_override, cudaStream_t st, int b_terms = 1, AT* out_cat = nullptr) {
   constexpr int EB = sizeof(AT);
   constexpr int BK = 128 / EB;
   CUtensorMap ta, tb;
   const int BN = bn_override ? bn_override : pick_bn(N);
+  const long KW = static_cast<long>(b_terms) * K;   // row length of w
   if (int e = encode_map3(&ta, x, EB, K, M, 1, ldx * EB, (uint64_t)M * ldx * EB, BK, 128, 1)) return e;
-  if (int e = encode_map3(&tb, w, EB, K, N, 1, (uint64_t)K * EB, (uint64_t)N * K * EB, BK, BN, 1)) return e;
+  if (int e = encode_map3(&tb, w, EB, KW, N, 1, (uint64_t)KW * EB, (uint64_t)N * KW * EB, BK, BN, 1)) return e;
   OperandWalk wa = zero_walk(), wb = zero_walk();
   wa.per_j[0] = BK; wa.per_tile[1] = 128;
-  wb.per_j[0] = BK; wb.per_tile[1] = BN;
-  GemmShape shp{M, N, ceil_div(K, BK), ceil_div(K, BK), 1};
+  wb.per_j[0] = BK; wb.per_tile[1] = BN; wb.per_tap[0] = K;
+  GemmShape shp{M, N, b_terms * ceil_div(K, BK), ceil_div(K, BK), 1};
   shp.f16 = kIsF16<AT>;
-  typename EpiStore<AT>::Params ep{out, out_f32, bias, nullptr, ldo, 0, relu};
+  typename EpiStore<AT>::Params ep{out, out_f32, bias, nullptr, ldo, 0, relu, out_cat};
+  DVAE_REQUIRE(b_terms == 1 || b_terms == 2, "b_terms must be 1 or 2");
+  const bool split3 = out_cat != nullptr;
   const int mt = pick_mt(M, ceil_div(N, BN));
   dim3 grid(ceil_div(M, 128 * mt), ceil_div(N, BN), 1);
   if (mt == 2) {
@@ -250,8 +255,8 @@ static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, A
     }
   }
   if (want_persistent(grid) && mt == 1 && gemm_pair(grid.x, BN)) {   // CTA pairs: half of the weight tile per CTA
-    if (int e = encode_map3(&tb, w, EB, K, N, 1, (uint64_t)K * EB, (uint64_t)N * K * EB, BK, BN / 2, 1)) return e;
-    if (use_tma_store(out, out_f32, nullptr, ldo, EB, shp.num_kb)) {
+    if (int e = encode_map3(&tb, w, EB, KW, N, 1, (uint64_t)KW * EB, (uint64_t)N * KW * EB, BK, BN / 2, 1)) return e;
+    if (!split3 && use_tma_store(out, out_f32, nullptr, ldo, EB, shp.num_kb)) {
       typename EpiStoreTma<AT>::Params et;
       if (int e = encode_map3(&et.tm_out, out, EB, N, M, 1, (uint64_t)ldo * EB, (uint64_t)M * ldo * EB, BK, 128, 1)) return e;
       et.bias = bias; et.relu = relu; et.stat_sums = nullptr; et.rows_half = 0;
@@ -260,7 +265,7 @@ static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, A
     return launch_gemm_persistent<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   }
   if (want_persistent(grid)) {
-    if (use_tma_store(out, out_f32, nullptr, ldo, EB, shp.num_kb)) {
+    if (!split3 && use_tma_store(out, out_f32, nullptr, ldo, EB, shp.num_kb)) {
       typename EpiStoreTma<AT>::Params et;
       if (int e = encode_map3(&et.tm_out, out, EB, N, M, 1, (uint64_t)ldo * EB, (uint64_t)M * ldo * EB, BK, 128, 1)) return e;
       et.bias = bias; et.relu = relu; et.stat_sums = nullptr; et.rows_half = 0;
@@ -415,8 +420,9 @@ static bool conv_tile_geometry(int T, int* box_t, int* box_r, int* tiles_per_seq
   return true;
 }
 
-template <typename AT>
-static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, float* y_f32, int R, int T, int Cin, int Cout,
+// YT: storage type of the output (AT, or float: the fp16 mode keeps the pre-BatchNorm convolution output unrounded)
+template <typename AT, typename YT = AT>
+static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, YT* y, float* y_f32, int R, int T, int Cin, int Cout,
                        bool dgrad, cudaStream_t st, double* bn_sums = nullptr, int rows_half = 0, bool* stats_fused = nullptr) {
   // bn_sums != nullptr: also accumulate the train-mode BatchNorm statistics of y (per column sum / sum of squares of the
   // stored values, per statistics half) -- fused into the staged store epilogue when that path is taken (*stats_fused).
@@ -425,6 +431,8 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
   // In dgrad mode the caller passes x:=dy, y:=dx, and (Cin, Cout) are still the forward layer's.
   constexpr int EB = sizeof(AT);
   constexpr int BK = 128 / EB;
+  constexpr int YB = sizeof(YT);
+  constexpr int YK = 128 / YB;   // output elements per 128-byte TMA box row
   int box_t, box_r, tps;
   DVAE_REQUIRE(conv_tile_geometry(T, &box_t, &box_r, &tps), "T must divide 128 or be a multiple of 128");
   DVAE_REQUIRE(tps == 0, "T > 128 not wired for the conv path (model is locked to T = 64)");
@@ -445,7 +453,7 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
   const int kpt = ceil_div(Ca, BK);
   GemmShape shp{R * T, Cn, 5 * kpt, kpt, 1};
   shp.f16 = kIsF16<AT>;
-  typename EpiStore<AT>::Params ep{y, y_f32, bias, nullptr, (long)Cn, 0, 0};
+  typename EpiStore<YT>::Params ep{y, y_f32, bias, nullptr, (long)Cn, 0, 0};
   static const int fuse_env = env_int("DVAE_BN_FUSE_STATS", 1);
   const bool want_stats = fuse_env != 0 && bn_sums != nullptr && !dgrad && rows_half > 0 && rows_half % 128 == 0;
   if (stats_fused) *stats_fused = false;
@@ -454,80 +462,80 @@ static int conv5_fwd_t(const AT* x, const AT* wk, const float* bias, AT* y, floa
   if (mt == 2) {
     if (!dgrad) {
       switch (BN) {
-        case 64: return launch_gemm<64, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
-        case 128: return launch_gemm<128, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
-        default: return launch_gemm<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+        case 64: return launch_gemm<64, false, false, EB, EpiStore<YT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+        case 128: return launch_gemm<128, false, false, EB, EpiStore<YT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+        default: return launch_gemm<256, false, false, EB, EpiStore<YT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
       }
     }
     switch (BN) {
-      case 64: return launch_gemm<64, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
-      case 128: return launch_gemm<128, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
-      default: return launch_gemm<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 64: return launch_gemm<64, false, true, EB, EpiStore<YT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 128: return launch_gemm<128, false, true, EB, EpiStore<YT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+      default: return launch_gemm<256, false, true, EB, EpiStore<YT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
     }
   }
   if (want_persistent(grid) && mt == 1 && gemm_pair(grid.x, BN)) {   // CTA pairs (cta_group::2)
     if (!dgrad) {   // K-major filter tile: re-encode with half the rows per box
       if (int e = encode_map3(&tb, wk, EB, Cin, 5, Cout, (uint64_t)Cin * EB, (uint64_t)5 * Cin * EB, BK, 1, BN / 2)) return e;
     }
-    if (use_tma_store(y, y_f32, nullptr, Cn, EB, shp.num_kb) || (want_stats && tma_store_possible(y, y_f32, nullptr, Cn, EB))) {
-      typename EpiStoreTma<AT>::Params et;
-      if (int e = encode_map3(&et.tm_out, y, EB, Cn, (uint64_t)R * T, 1, (uint64_t)Cn * EB, (uint64_t)R * T * Cn * EB, BK, 128, 1))
+    if (use_tma_store(y, y_f32, nullptr, Cn, YB, shp.num_kb) || (want_stats && tma_store_possible(y, y_f32, nullptr, Cn, YB))) {
+      typename EpiStoreTma<YT>::Params et;
+      if (int e = encode_map3(&et.tm_out, y, YB, Cn, (uint64_t)R * T, 1, (uint64_t)Cn * YB, (uint64_t)R * T * Cn * YB, YK, 128, 1))
         return e;
       et.bias = bias; et.relu = 0;
       et.stat_sums = want_stats ? bn_sums : nullptr; et.rows_half = rows_half;
       if (want_stats && stats_fused) *stats_fused = true;
-      if (!dgrad) return launch_gemm_persistent<256, false, false, EB, EpiStoreTma<AT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
-      return launch_gemm_persistent<256, false, true, EB, EpiStoreTma<AT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
+      if (!dgrad) return launch_gemm_persistent<256, false, false, EB, EpiStoreTma<YT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
+      return launch_gemm_persistent<256, false, true, EB, EpiStoreTma<YT>, 2>(ta, tb, wa, wb, shp, et, grid, st);
     }
-    if (!dgrad) return launch_gemm_persistent<256, false, false, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
-    return launch_gemm_persistent<256, false, true, EB, EpiStore<AT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+    if (!dgrad) return launch_gemm_persistent<256, false, false, EB, EpiStore<YT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
+    return launch_gemm_persistent<256, false, true, EB, EpiStore<YT>, 2>(ta, tb, wa, wb, shp, ep, grid, st);
   }
   if (want_persistent(grid) &&
-      (use_tma_store(y, y_f32, nullptr, Cn, EB, shp.num_kb) || (want_stats && tma_store_possible(y, y_f32, nullptr, Cn, EB)))) {
-    typename EpiStoreTma<AT>::Params et;
-    if (int e = encode_map3(&et.tm_out, y, EB, Cn, (uint64_t)R * T, 1, (uint64_t)Cn * EB, (uint64_t)R * T * Cn * EB, BK, 128, 1))
+      (use_tma_store(y, y_f32, nullptr, Cn, YB, shp.num_kb) || (want_stats && tma_store_possible(y, y_f32, nullptr, Cn, YB)))) {
+    typename EpiStoreTma<YT>::Params et;
+    if (int e = encode_map3(&et.tm_out, y, YB, Cn, (uint64_t)R * T, 1, (uint64_t)Cn * YB, (uint64_t)R * T * Cn * YB, YK, 128, 1))
       return e;
     et.bias = bias; et.relu = 0;
     et.stat_sums = want_stats ? bn_sums : nullptr; et.rows_half = rows_half;
     if (want_stats && stats_fused) *stats_fused = true;
     if (!dgrad) {
       switch (BN) {
-        case 64: return launch_gemm_persistent<64, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
-        case 128: return launch_gemm_persistent<128, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
-        default: return launch_gemm_persistent<256, false, false, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+        case 64: return launch_gemm_persistent<64, false, false, EB, EpiStoreTma<YT>>(ta, tb, wa, wb, shp, et, grid, st);
+        case 128: return launch_gemm_persistent<128, false, false, EB, EpiStoreTma<YT>>(ta, tb, wa, wb, shp, et, grid, st);
+        default: return launch_gemm_persistent<256, false, false, EB, EpiStoreTma<YT>>(ta, tb, wa, wb, shp, et, grid, st);
       }
     }
     switch (BN) {
-      case 64: return launch_gemm_persistent<64, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
-      case 128: return launch_gemm_persistent<128, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
-      default: return launch_gemm_persistent<256, false, true, EB, EpiStoreTma<AT>>(ta, tb, wa, wb, shp, et, grid, st);
+      case 64: return launch_gemm_persistent<64, false, true, EB, EpiStoreTma<YT>>(ta, tb, wa, wb, shp, et, grid, st);
+      case 128: return launch_gemm_persistent<128, false, true, EB, EpiStoreTma<YT>>(ta, tb, wa, wb, shp, et, grid, st);
+      default: return launch_gemm_persistent<256, false, true, EB, EpiStoreTma<YT>>(ta, tb, wa, wb, shp, et, grid, st);
     }
   }
   if (want_persistent(grid)) {
     if (!dgrad) {
       switch (BN) {
-        case 64: return launch_gemm_persistent<64, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
-        case 128: return launch_gemm_persistent<128, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
-        default: return launch_gemm_persistent<256, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+        case 64: return launch_gemm_persistent<64, false, false, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
+        case 128: return launch_gemm_persistent<128, false, false, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
+        default: return launch_gemm_persistent<256, false, false, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
       }
     }
     switch (BN) {
-      case 64: return launch_gemm_persistent<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
-      case 128: return launch_gemm_persistent<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
-      default: return launch_gemm_persistent<256, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 64: return launch_gemm_persistent<64, false, true, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 128: return launch_gemm_persistent<128, false, true, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      default: return launch_gemm_persistent<256, false, true, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
     }
   }
   if (!dgrad) {
     switch (BN) {
-      case 64: return launch_gemm<64, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
-      case 128: return launch_gemm<128, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
-      default: return launch_gemm<256, false, false, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 64: return launch_gemm<64, false, false, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      case 128: return launch_gemm<128, false, false, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
+      default: return launch_gemm<256, false, false, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
     }
   }
   switch (BN) {
-    case 64: return launch_gemm<64, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
-    case 128: return launch_gemm<128, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
-    default: return launch_gemm<256, false, true, EB, EpiStore<AT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    case 64: return launch_gemm<64, false, true, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    case 128: return launch_gemm<128, false, true, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
+    default: return launch_gemm<256, false, true, EB, EpiStore<YT>>(ta, tb, wa, wb, shp, ep, grid, st);
   }
 }
 
@@ -917,12 +925,20 @@ static int lstm_wgrad_hh_t(const AT* da_all, const AT* h_all, float* dwhh, int r
 
 namespace dvae {
 template <typename AT>
-static int conv5_fwd_bnstats_t(int dtype, const void* x, const void* wk, const float* bias, void* y, int R, int T, int Cin, int Cout,
-                               double* bn_ws, int rows_half, int halves, cudaStream_t st) {
+static int conv5_fwd_bnstats_t(int dtype, const void* x, const void* wk, const float* bias, void* y, int y_f32, int R, int T, int Cin,
+                               int Cout, double* bn_ws, int rows_half, int halves, cudaStream_t st) {
   bool fused = false;
-  if (int e = conv5_fwd_t<AT>((const AT*)x, (const AT*)wk, bias, (AT*)y, nullptr, R, T, Cin, Cout, false, st, bn_ws, rows_half, &fused))
-    return e;
-  if (!fused) return bn_stats_launch(dtype, y, bn_ws, rows_half, halves, Cout, st);
+  int e;
+  if (y_f32) {
+    if constexpr (std::is_same<AT, __half>::value) {   // only the fp16 mode keeps y in fp32 (tf32 storage is fp32 already)
+      e = conv5_fwd_t<AT, float>((const AT*)x, (const AT*)wk, bias, (float*)y, nullptr, R, T, Cin, Cout, false, st, bn_ws, rows_half, &fused);
+    } else {
+      set_last_error("fp32 convolution output is implemented for the fp16 activation dtype only");
+      return 1;
+    }
+  } else e = conv5_fwd_t<AT>((const AT*)x, (const AT*)wk, bias, (AT*)y, nullptr, R, T, Cin, Cout, false, st, bn_ws, rows_half, &fused);
+  if (e) return e;
+  if (!fused) return bn_stats_launch(y_f32 ? kF32 : dtype, y, bn_ws, rows_half, halves, Cout, st);
   return 0;
 }
 }  // namespace dvae
@@ -948,6 +964,15 @@ int dvae_linear_fwd(int dtype, const void* x, long ldx, const void* w, const flo
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_AT(dtype, linear_fwd_t<AT>((const AT*)x, ldx, (const AT*)w, bias, (AT*)out, out_f32, ldo, M, N, K, relu, block_n, st));
 }
+// Split-precision variants for the small linear layers (M = rows, not rows x frames: their cost is negligible):
+// b_terms = 2: w is [N, 2K] = [w_hi | w_lo] (dvae_prep_cast_split) and out = x . (w_hi + w_lo)^T;
+// out_cat (may be null): additionally act [M, 3N] = [hi | lo | hi] of the result, the K-concatenated operand of a following
+// GEMM whose weight is laid out [w_hi | w_hi | w_lo] (dvae_prep_cast_split with parts = 3).
+int dvae_linear_fwd_split(int dtype, const void* x, long ldx, const void* w, const float* bias, void* out, float* out_f32,
+                          long ldo, void* out_cat, int M, int N, int K, int relu, int b_terms, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DISPATCH_AT(dtype, linear_fwd_t<AT>((const AT*)x, ldx, (const AT*)w, bias, (AT*)out, out_f32, ldo, M, N, K, relu, 0, st, b_terms, (AT*)out_cat));
+}
 
 int dvae_linear_dgrad(int dtype, const void* dy, long lddy, const void* w, void* dx, float* dx_f32, const void* relu_mask,
                       long ldx, int M, int N, int K, int block_n, void* stream) {
@@ -971,12 +996,13 @@ int dvae_conv5_fwd(int dtype, const void* x, const void* wk, const float* bias, 
 // Convolution + the statistics pass of the train-mode BatchNorm that follows it (ConvNorm -> BatchNorm1d,
 // model/disentangled_vae.py:154-160): bn_ws [halves*2*Cout + 1] doubles receives per-half column sums / sums of squares of
 // y (zeroed here).  Fused into the GEMM's staged store epilogue when possible, otherwise a separate reduction kernel.
-int dvae_conv5_fwd_bnstats(int dtype, const void* x, const void* wk, const float* bias, void* y, int R, int T, int Cin, int Cout,
-                           double* bn_ws, int rows_half, int halves, void* stream) {
+// y_f32 != 0: y is stored as unrounded fp32 whatever the activation dtype (and BatchNorm then reads it with y_f32 set too)
+int dvae_conv5_fwd_bnstats(int dtype, const void* x, const void* wk, const float* bias, void* y, int y_f32, int R, int T, int Cin,
+                           int Cout, double* bn_ws, int rows_half, int halves, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DVAE_REQUIRE(bn_ws != nullptr && halves >= 1 && (long)rows_half * halves == (long)R * T, "rows_half * halves must equal R * T");
   DVAE_CHECK_CUDA(cudaMemsetAsync(bn_ws, 0, sizeof(double) * ((long)halves * 2 * Cout + 1), st));
-  DISPATCH_AT(dtype, conv5_fwd_bnstats_t<AT>(dtype, x, wk, bias, y, R, T, Cin, Cout, bn_ws, rows_half, halves, st));
+  DISPATCH_AT(dtype, conv5_fwd_bnstats_t<AT>(dtype, x, wk, bias, y, y_f32, R, T, Cin, Cout, bn_ws, rows_half, halves, st));
 }
 
 int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,

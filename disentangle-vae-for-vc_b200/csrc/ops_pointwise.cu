@@ -42,15 +42,39 @@ __global__ void cast_kernel(const float* __restrict__ src, AT* __restrict__ dst,
   }
 }
 
-// w[Co][Ci][5] (torch Conv1d) -> wk[Co][5][Ci]: the reduction dim (ci) becomes contiguous per tap
+// w[Co][Ci][5] (torch Conv1d) -> wk[Co][5][Ci]: the reduction dim (ci) becomes contiguous per tap.
+// wk_cat (may be null): [Co][5][3Ci] = [w_hi | w_hi | w_lo], the weight side of the split-precision first convolution
 template <typename AT>
-__global__ void conv_weight_kernel(const float* __restrict__ w, AT* __restrict__ wk, int Co, int Ci) {
+__global__ void conv_weight_kernel(const float* __restrict__ w, AT* __restrict__ wk, AT* __restrict__ wk_cat, int Co, int Ci) {
   const long n = static_cast<long>(Co) * 5 * Ci;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int ci = i % Ci;
     const int k = (i / Ci) % 5;
     const int co = i / (5L * Ci);
-    wk[i] = from_f32<AT>(w[(static_cast<long>(co) * Ci + ci) * 5 + k]);
+    const float v = w[(static_cast<long>(co) * Ci + ci) * 5 + k];
+    const AT hi = from_f32<AT>(v);
+    wk[i] = hi;
+    if (wk_cat != nullptr) {
+      AT* row = wk_cat + (static_cast<long>(co) * 5 + k) * 3 * Ci;
+      row[ci] = hi;
+      row[Ci + ci] = hi;
+      row[2 * Ci + ci] = from_f32<AT>(v - to_f32(hi));
+    }
+  }
+}
+// split-precision copy of a linear weight (row-wise), w_lo = round(w - w_hi): parts = 2: dst [N][2K] = [w_hi | w_lo];
+// parts = 3: dst [N][3K] = [w_hi | w_hi | w_lo] (against an operand laid out [hi | lo | hi])
+template <typename AT>
+__global__ void cast_split_kernel(const float* __restrict__ src, AT* __restrict__ dst, long rows, long K, int parts) {
+  const long n = rows * K;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / K, c = i - r * K;
+    const float v = src[i];
+    const AT hi = from_f32<AT>(v);
+    AT* row = dst + r * parts * K;
+    row[c] = hi;
+    if (parts == 3) row[K + c] = hi;
+    row[(parts - 1) * K + c] = from_f32<AT>(v - to_f32(hi));
   }
 }
 // dwk[Co][5][Ci] fp32 -> dw[Co][Ci][5] fp32 (gradient back in the parameter's layout)
@@ -124,8 +148,11 @@ __global__ void add_f32_act_kernel(const float* __restrict__ a, const AT* __rest
 
 // ------------------------------------------------------------------------------------ layout packing
 // x fp32 [R][C][T] (reference NCL) -> y act [R][T][C] (channels-last, the GEMM A-operand layout)
+// split != 0: besides y (the rounded values, "hi") also y_cat [R][T][3C] = [hi | lo | hi] with lo = round(x - hi): the
+// K-concatenated operand that, against weights laid out [w_hi | w_hi | w_lo], makes the first convolution see its fp32
+// input and weights to ~2^-22 instead of 2^-11 (three products of a split-precision multiplication in one GEMM)
 template <typename AT>
-__global__ void ncl_to_cl_kernel(const float* __restrict__ x, AT* __restrict__ y, int C, int T) {
+__global__ void ncl_to_cl_kernel(const float* __restrict__ x, AT* __restrict__ y, AT* __restrict__ y_cat, int C, int T) {
   extern __shared__ float tile[];  // [C][T+1]
   const long r = blockIdx.x;
   const float* xr = x + r * C * T;
@@ -137,7 +164,15 @@ __global__ void ncl_to_cl_kernel(const float* __restrict__ x, AT* __restrict__ y
   AT* yr = y + r * C * T;
   for (int i = threadIdx.x; i < C * T; i += blockDim.x) {
     const int t = i / C, c = i - t * C;
-    yr[i] = from_f32<AT>(tile[c * (T + 1) + t]);
+    const float v = tile[c * (T + 1) + t];
+    const AT hi = from_f32<AT>(v);
+    yr[i] = hi;
+    if (y_cat != nullptr) {
+      AT* row = y_cat + (r * T + t) * 3L * C;
+      row[c] = hi;
+      row[C + c] = from_f32<AT>(v - to_f32(hi));
+      row[2 * C + c] = hi;
+    }
   }
 }
 // channels-last -> NCL fp32 with optional residual:  out[r][c][t] = a[r][t][c] (+ b[r][t][c]);  a is fp32 or act
@@ -351,8 +386,9 @@ __device__ __forceinline__ float act_grad_from_z(float z, int act) {
 }
 
 // out = act(y * scale[h] + shift[h]); a thread keeps the affine constants of its 8 channels in registers.
-template <typename AT>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const AT* __restrict__ y, AT* __restrict__ out,
+// YT: storage type of y (the activation type, or float when the convolution output is kept unrounded)
+template <typename AT, typename YT = AT>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const YT* __restrict__ y, AT* __restrict__ out,
                                                        const float* __restrict__ stat, long rows, int rows_half, int C, int act,
                                                        int rb) {
   const int rl = threadIdx.x >> 3, cg = threadIdx.x & 7;
@@ -367,18 +403,18 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const AT* __restrict__ y,
     sh[k] = stat[(h * 4 + 3) * C + c0 + k];
   }
   const int nr = static_cast<int>(min(static_cast<long>(rb), rows - row0));
-  const AT* src = y + row0 * C + c0;
+  const YT* src = y + row0 * C + c0;
   AT* dst = out + row0 * C + c0;
   for (int r = rl; r < nr; r += kBnLanes * kBnUnroll) {
-    typename Act8<AT>::raw_t raw[kBnUnroll];
+    typename Act8<YT>::raw_t raw[kBnUnroll];
 #pragma unroll
     for (int u = 0; u < kBnUnroll; ++u)
-      if (r + u * kBnLanes < nr) raw[u] = Act8<AT>::load_raw(src + static_cast<long>(r + u * kBnLanes) * C);
+      if (r + u * kBnLanes < nr) raw[u] = Act8<YT>::load_raw(src + static_cast<long>(r + u * kBnLanes) * C);
 #pragma unroll
     for (int u = 0; u < kBnUnroll; ++u) {
       if (r + u * kBnLanes < nr) {
         float v[8];
-        Act8<AT>::unpack(raw[u], v);
+        Act8<YT>::unpack(raw[u], v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = apply_act(fmaf(v[k], sc[k], sh[k]), act);
         Act8<AT>::store(dst + static_cast<long>(r + u * kBnLanes) * C, v);
@@ -388,8 +424,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const AT* __restrict__ y,
 }
 
 // backward pass 1: per (half, channel) sums of dz and dz*xhat, dz = dout * act'(z)
-template <typename AT>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const AT* __restrict__ dout, const AT* __restrict__ y,
+template <typename AT, typename YT = AT>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const AT* __restrict__ dout, const YT* __restrict__ y,
                                                             const float* __restrict__ stat, double* __restrict__ sums,
                                                             int rows_half, int C, int act, int rb) {
   __shared__ float red[kBnLanes * 2 * kBnSlab];
@@ -409,14 +445,15 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const AT* __restrict
       sc[i] = stat[(h * 4 + 2) * C + c0 + i];
       sh[i] = stat[(h * 4 + 3) * C + c0 + i];
     }
-    const AT* ys = y + row0 * C + c0;
+    const YT* ys = y + row0 * C + c0;
     const AT* dsrc = dout + row0 * C + c0;
     for (int r = rl; r < rb; r += kBnLanes * kBnUnroll) {
-      typename Act8<AT>::raw_t ry[kBnUnroll], rd[kBnUnroll];
+      typename Act8<YT>::raw_t ry[kBnUnroll];
+      typename Act8<AT>::raw_t rd[kBnUnroll];
 #pragma unroll
       for (int u = 0; u < kBnUnroll; ++u) {
         if (r + u * kBnLanes < rb) {
-          ry[u] = Act8<AT>::load_raw(ys + static_cast<long>(r + u * kBnLanes) * C);
+          ry[u] = Act8<YT>::load_raw(ys + static_cast<long>(r + u * kBnLanes) * C);
           rd[u] = Act8<AT>::load_raw(dsrc + static_cast<long>(r + u * kBnLanes) * C);
         }
       }
@@ -424,7 +461,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const AT* __restrict
       for (int u = 0; u < kBnUnroll; ++u) {
         if (r + u * kBnLanes < rb) {
           float v[8], d[8];
-          Act8<AT>::unpack(ry[u], v);
+          Act8<YT>::unpack(ry[u], v);
           Act8<AT>::unpack(rd[u], d);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -454,8 +491,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, float* _
   dbeta[c] = static_cast<float>(db * alpha);
 }
 // backward pass 2: dy = scale * (dz - mean(dz) - xhat * mean(dz*xhat)); same streaming structure as bn_apply_kernel
-template <typename AT>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const AT* __restrict__ dout, const AT* __restrict__ y,
+template <typename AT, typename YT = AT>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const AT* __restrict__ dout, const YT* __restrict__ y,
                                                            const float* __restrict__ stat, const float* __restrict__ coef,
                                                            AT* __restrict__ dy, long rows, int rows_half, int C, int act,
                                                            int rb) {
@@ -475,15 +512,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const AT* __restrict_
     k1[k] = coef[(h * 2 + 1) * C + c0 + k];
   }
   const int nr = static_cast<int>(min(static_cast<long>(rb), rows - row0));
-  const AT* ys = y + row0 * C + c0;
+  const YT* ys = y + row0 * C + c0;
   const AT* dsrc = dout + row0 * C + c0;
   AT* dst = dy + row0 * C + c0;
   for (int r = rl; r < nr; r += kBnLanes * kBnUnroll) {
-    typename Act8<AT>::raw_t ry[kBnUnroll], rd[kBnUnroll];
+    typename Act8<YT>::raw_t ry[kBnUnroll];
+    typename Act8<AT>::raw_t rd[kBnUnroll];
 #pragma unroll
     for (int u = 0; u < kBnUnroll; ++u) {
       if (r + u * kBnLanes < nr) {
-        ry[u] = Act8<AT>::load_raw(ys + static_cast<long>(r + u * kBnLanes) * C);
+        ry[u] = Act8<YT>::load_raw(ys + static_cast<long>(r + u * kBnLanes) * C);
         rd[u] = Act8<AT>::load_raw(dsrc + static_cast<long>(r + u * kBnLanes) * C);
       }
     }
@@ -491,7 +529,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const AT* __restrict_
     for (int u = 0; u < kBnUnroll; ++u) {
       if (r + u * kBnLanes < nr) {
         float v[8], d[8];
-        Act8<AT>::unpack(ry[u], v);
+        Act8<YT>::unpack(ry[u], v);
         Act8<AT>::unpack(rd[u], d);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -550,6 +588,13 @@ using namespace dvae;
     else { set_last_error("unknown dtype tag"); return 1; }  \
   } while (0)
 
+// y_f32: the BatchNorm input y is unrounded fp32 (fp16 mode) instead of the activation type
+#define DISPATCH_AT_Y(dtype, y_f32, ...)                                        \
+  do {                                                                          \
+    if (y_f32) { using YT = float; DISPATCH_AT(dtype, __VA_ARGS__); }           \
+    else { DISPATCH_AT(dtype, { using YT = AT; __VA_ARGS__; }); }               \
+  } while (0)
+
 // rows per block: the largest power-of-two multiple of 64 up to `want` that divides rows_half (blocks never straddle halves)
 static int bn_rows_per_block(int rows_half, int want) {
   int rb = kBnRowsPerBlock;
@@ -564,7 +609,8 @@ int bn_stats_launch(int dtype, const void* y, double* ws, int rows_half, int hal
   const long rows = static_cast<long>(rows_half) * halves;
   const int rb_red = bn_rows_per_block(rows_half, 512);
   const dim3 g_red(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_red));
-  DISPATCH_AT(dtype, bn_stats_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)y, ws, rows_half, C, rb_red));
+  if (dtype == kF32) bn_stats_kernel<float><<<g_red, 256, 0, st>>>((const float*)y, ws, rows_half, C, rb_red);
+  else DISPATCH_AT(dtype, bn_stats_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)y, ws, rows_half, C, rb_red));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -575,6 +621,15 @@ extern "C" {
 int dvae_prep_cast(int dtype, const float* src, void* dst, long n, float scale, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_AT(dtype, cast_kernel<AT><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>(src, (AT*)dst, n, scale));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// split-precision weights of the small linear layers: dst act [rows, parts*K] = [hi | lo] (parts = 2) or [hi | hi | lo]
+// (parts = 3) of src fp32 [rows, K]
+int dvae_prep_cast_split(int dtype, const float* src, void* dst, long rows, long K, int parts, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  DVAE_REQUIRE(parts == 2 || parts == 3, "parts must be 2 or 3");
+  DISPATCH_AT(dtype, cast_split_kernel<AT><<<grid_for(rows * K, 256), 256, 0, st>>>(src, (AT*)dst, rows, K, parts));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -596,9 +651,9 @@ int dvae_add_inplace(int dtype, void* a, const void* b, long n, void* stream) {
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
-int dvae_prep_conv_weight(int dtype, const float* w, void* wk, int Co, int Ci, void* stream) {
+int dvae_prep_conv_weight(int dtype, const float* w, void* wk, void* wk_cat, int Co, int Ci, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  DISPATCH_AT(dtype, conv_weight_kernel<AT><<<grid_for(5L * Co * Ci, 256), 256, 0, st>>>(w, (AT*)wk, Co, Ci));
+  DISPATCH_AT(dtype, conv_weight_kernel<AT><<<grid_for(5L * Co * Ci, 256), 256, 0, st>>>(w, (AT*)wk, (AT*)wk_cat, Co, Ci));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -622,12 +677,13 @@ int dvae_prep_lstm_bias(const float* b_ih, const float* b_hh, float* dst, int H,
   return 0;
 }
 
-int dvae_pack_ncl_to_cl(int dtype, const float* x, void* y, int R, int C, int T, void* stream) {
+// y_cat (may be null): additionally the split-precision operand [R, T, 3C] = [hi | lo | hi] (see ncl_to_cl_kernel)
+int dvae_pack_ncl_to_cl(int dtype, const float* x, void* y, void* y_cat, int R, int C, int T, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   if (R == 0) return 0;
   const int smem = C * (T + 1) * 4;
   DVAE_REQUIRE(smem <= 48 * 1024, "C*(T+1) tile must fit 48 KB of shared memory");
-  DISPATCH_AT(dtype, ncl_to_cl_kernel<AT><<<R, 256, smem, st>>>(x, (AT*)y, C, T));
+  DISPATCH_AT(dtype, ncl_to_cl_kernel<AT><<<R, 256, smem, st>>>(x, (AT*)y, (AT*)y_cat, C, T));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -683,7 +739,7 @@ int dvae_recon_out_bwd(int dtype, const float* g_rec, const float* g_hat, void* 
 
 // Train-mode BatchNorm forward over y [halves*rows_half, C]: statistics per half, then act(y*scale+shift).
 // ws: double [halves*2*C] scratch; stat: fp32 [halves*4*C] (kept for backward).
-int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
+int dvae_bn_train_fwd(int dtype, const void* y, int y_f32, void* out, const float* gamma, const float* beta, float* run_mean,
                       float* run_var, long long* num_batches, double* ws, float* stat, int rows_half, int halves, int C,
                       int act, float eps, float momentum, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
@@ -693,16 +749,16 @@ int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, c
   DVAE_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * halves * 2 * C, st));
   const int rb_red = bn_rows_per_block(rows_half, 512), rb_app = bn_rows_per_block(rows_half, 256);
   const dim3 g_red(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_red)), g_app(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_app));
-  DISPATCH_AT(dtype, bn_stats_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)y, ws, rows_half, C, rb_red));
+  DISPATCH_AT_Y(dtype, y_f32, bn_stats_kernel<YT><<<g_red, 256, 0, st>>>((const YT*)y, ws, rows_half, C, rb_red));
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, gamma, beta, stat, run_mean, run_var, num_batches, halves, C,
                                                         static_cast<double>(rows_half), eps, momentum);
-  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<g_app, 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half, C, act, rb_app));
+  DISPATCH_AT_Y(dtype, y_f32, bn_apply_kernel<AT, YT><<<g_app, 256, 0, st>>>((const YT*)y, (AT*)out, stat, rows, rows_half, C, act, rb_app));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 // Second half of dvae_bn_train_fwd for a caller that already holds the statistics sums in ws (dvae_conv5_fwd_bnstats):
 // finalise (mean / rstd / scale / shift, running statistics) and apply the affine transform + activation.
-int dvae_bn_finalize_apply(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
+int dvae_bn_finalize_apply(int dtype, const void* y, int y_f32, void* out, const float* gamma, const float* beta, float* run_mean,
                            float* run_var, long long* num_batches, const double* ws, float* stat, int rows_half, int halves,
                            int C, int act, float eps, float momentum, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
@@ -713,7 +769,7 @@ int dvae_bn_finalize_apply(int dtype, const void* y, void* out, const float* gam
   const dim3 g_app(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_app));
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, gamma, beta, stat, run_mean, run_var, num_batches, halves, C,
                                                         static_cast<double>(rows_half), eps, momentum);
-  DISPATCH_AT(dtype, bn_apply_kernel<AT><<<g_app, 256, 0, st>>>((const AT*)y, (AT*)out, stat, rows, rows_half, C, act, rb_app));
+  DISPATCH_AT_Y(dtype, y_f32, bn_apply_kernel<AT, YT><<<g_app, 256, 0, st>>>((const YT*)y, (AT*)out, stat, rows, rows_half, C, act, rb_app));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -731,7 +787,7 @@ int dvae_bn_eval_fwd(int dtype, const void* y, void* out, const float* gamma, co
 }
 // Train-mode BatchNorm backward (through the activation): dout -> dy, dgamma, dbeta.  coef: fp32 [halves*2*C] scratch.
 // alpha scales the two parameter gradients (1 / gradient scale of the fp16 mode); dy stays at the stream's scale.
-int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* stat, double* ws, float* coef, void* dy,
+int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, int y_f32, const float* stat, double* ws, float* coef, void* dy,
                       float* dgamma, float* dbeta, int rows_half, int halves, int C, int act, float alpha, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DVAE_REQUIRE(C % 8 == 0 && C <= 2048, "C must be a multiple of 8 (<= 2048)");
@@ -740,10 +796,10 @@ int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* s
   DVAE_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * halves * 2 * C, st));
   const int rb_red = bn_rows_per_block(rows_half, 512), rb_app = bn_rows_per_block(rows_half, 256);
   const dim3 g_red(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_red)), g_app(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_app));
-  DISPATCH_AT(dtype, bn_bwd_reduce_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)dout, (const AT*)y, stat, ws, rows_half, C, act, rb_red));
+  DISPATCH_AT_Y(dtype, y_f32, bn_bwd_reduce_kernel<AT, YT><<<g_red, 256, 0, st>>>((const AT*)dout, (const YT*)y, stat, ws, rows_half, C, act, rb_red));
   bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, coef, dgamma, dbeta, halves, C, static_cast<double>(rows_half),
                                                             static_cast<double>(alpha));
-  DISPATCH_AT(dtype, bn_bwd_apply_kernel<AT><<<g_app, 256, 0, st>>>((const AT*)dout, (const AT*)y, stat, coef, (AT*)dy, rows, rows_half, C, act, rb_app));
+  DISPATCH_AT_Y(dtype, y_f32, bn_bwd_apply_kernel<AT, YT><<<g_app, 256, 0, st>>>((const AT*)dout, (const YT*)y, stat, coef, (AT*)dy, rows, rows_half, C, act, rb_app));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -701,6 +701,8 @@ struct EpiStore {
     long ldo;             // row stride (elements) of out / out_f32 / mask
     long z_stride;        // batch stride (elements)
     int relu;
+    OutT* out_cat;        // optional second output [M, 3N] = [hi | lo | hi], lo = round(v - hi): the K-concatenated
+                          // split-precision operand of the next (small) GEMM, whose weight is laid out [w_hi | w_hi | w_lo]
   };
   template <int BLOCK_N>
   static __device__ __forceinline__ void prefetch(const Params& p, int m, int n0, int zb, int col0, int col1,
@@ -759,6 +761,17 @@ struct EpiStore {
           } else {
             for (int i = 0; i < 32; ++i)
               if (nb + i < shp.N) o[i] = from_f32<OutT>(v[i]);
+          }
+        }
+        if (p.out_cat != nullptr) {
+          OutT* oc = p.out_cat + static_cast<long>(zb) * 3 * p.z_stride + static_cast<long>(m) * 3 * shp.N + nb;
+          for (int i = 0; i < 32; ++i) {
+            if (nb + i < shp.N) {
+              const OutT hi = from_f32<OutT>(v[i]);
+              oc[i] = hi;
+              oc[shp.N + i] = from_f32<OutT>(v[i] - to_f32(hi));
+              oc[2 * shp.N + i] = hi;
+            }
           }
         }
         if (p.out_f32 != nullptr) {

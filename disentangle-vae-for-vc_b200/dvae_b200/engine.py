@@ -50,6 +50,11 @@ class PreparedWeights:
         self._linears = LINEARS if linears is None else linears
         self._lstms = LSTMS if lstms is None else lstms
         self._fused_heads = fused_heads
+        # fp16 mode, DisentangledVAE only: split-precision operands (hi + lo, two 11-bit halves) for the layers whose cost is
+        # negligible -- the first encoder convolution (K = 80 per tap), enc_linear (M = rows) and the heads -- so that the
+        # input mel, those weights and `e` enter at ~22 bits instead of 11 (DESIGN.md "Numerics": the error budget)
+        self.split = (dt == lib.F16 and fused_heads and convs is None
+                      and os.environ.get("DVAE_B200_SPLIT", "1") == "1")
         dev = next(iter(P.values())).device
         for conv in self._convs:
             Co, Ci, _ = P[conv + ".weight"].shape
@@ -63,6 +68,14 @@ class PreparedWeights:
             self.heads_w = torch.empty((n_s + n_c, ws.shape[1]), device=dev, dtype=ad)
             self.heads_b = torch.empty((n_s + n_c,), device=dev, dtype=torch.float32)
             self.n_style = n_s
+        if self.split:
+            c0 = ENC_CONVS[0][0]
+            Co, Ci, _ = P[c0 + ".weight"].shape
+            self.conv0_cat = torch.empty((Co, 5, 3 * Ci), device=dev, dtype=ad)            # [w_hi | w_hi | w_lo] per tap
+            wl = P["enc_linear.linear_layer.weight"]
+            self.enc_linear_split = torch.empty((wl.shape[0], 2 * wl.shape[1]), device=dev, dtype=ad)    # [w_hi | w_lo]
+            self.heads_w3 = torch.empty((self.heads_w.shape[0], 3 * self.heads_w.shape[1]), device=dev, dtype=ad)
+            self._heads_w32 = torch.empty(self.heads_w.shape, device=dev, dtype=torch.float32)
         for prefix, (layers, D, H) in self._lstms.items():
             per_layer = []
             for l in range(layers):
@@ -79,7 +92,14 @@ class PreparedWeights:
         """Re-derive every tensor-core copy from the fp32 masters, in place (after an optimizer step / load_state_dict)."""
         dt = self.dt
         for conv in self._convs:
-            ops.prep_conv_weight(dt, P[conv + ".weight"], out=self.conv[conv])
+            cat = self.conv0_cat if (self.split and conv == ENC_CONVS[0][0]) else None
+            ops.prep_conv_weight(dt, P[conv + ".weight"], out=self.conv[conv], out_cat=cat)
+        if self.split:
+            ops.prep_cast_split(dt, P["enc_linear.linear_layer.weight"], self.enc_linear_split, 2)
+            n_s = self.n_style
+            ops.copy_f32(P["style.linear_layer.weight"], self._heads_w32[:n_s])
+            ops.copy_f32(P["content.linear_layer.weight"], self._heads_w32[n_s:])
+            ops.prep_cast_split(dt, self._heads_w32, self.heads_w3, 3)
         for name in self._linears:
             ops.prep_cast(dt, P[name + ".weight"], self.lin[name])
         if self._fused_heads:
@@ -146,6 +166,9 @@ class Engine:
         # every parameter gradient is multiplied by 1 / grad_scale where it is produced.  1.0 for bf16 / tf32 storage
         # (fp32's exponent range); the fp16 mode needs it to keep small gradients inside fp16's normal range.
         self.grad_scale = float(grad_scale)
+        # fp16 mode: the convolution outputs that feed a train-mode BatchNorm are kept as unrounded fp32 (the rounding of that
+        # tensor is the largest single term of the forward error budget, scripts/rounding_budget.py); DVAE_B200_Y_F32=0/1 overrides
+        self.y_f32 = os.environ.get("DVAE_B200_Y_F32", "1" if dt == lib.F16 else "0") == "1" and dt == lib.F16
         self.grad_stats = [] if os.environ.get("DVAE_DEBUG_GRAD_STATS") else None   # diagnostics: (name, amax) of the stream
         self.buckets = None   # set to a parallel.GradBuckets for data-parallel training
         self.side_stream = None     # created lazily; weight-gradient GEMMs that are off the critical path run here
@@ -158,13 +181,19 @@ class Engine:
         self.momentum = bn_momentum
 
     # ------------------------------------------------------------------ building blocks (forward)
-    def _conv_stack(self, W: PreparedWeights, P, B, h: Tensor, convs, halves: int, training: bool, saved: Optional[list]):
+    def _conv_stack(self, W: PreparedWeights, P, B, h: Tensor, convs, halves: int, training: bool, saved: Optional[list],
+                    first_cat: Optional[Tensor] = None):
+        """first_cat: split-precision copy [rows, T, 3C] = [hi | lo | hi] of the stack's input; the first convolution then
+        contracts it with W.conv0_cat = [w_hi | w_hi | w_lo] (forward only: the backward uses the plain operands)."""
         dt = self.dt
-        for conv, bn, act in convs:
+        for li, (conv, bn, act) in enumerate(convs):
             x_in = h
             if training:
                 # the convolution's epilogue also produces the BatchNorm statistics of its output (no extra pass over y)
-                y, ws = ops.conv5_fwd_bnstats(dt, x_in, W.conv[conv], P[conv + ".bias"], halves)
+                if li == 0 and first_cat is not None:
+                    y, ws = ops.conv5_fwd_bnstats(dt, first_cat, W.conv0_cat, P[conv + ".bias"], halves, y_f32=self.y_f32)
+                else:
+                    y, ws = ops.conv5_fwd_bnstats(dt, x_in, W.conv[conv], P[conv + ".bias"], halves, y_f32=self.y_f32)
                 C = y.shape[-1]
                 h, stat = ops.bn_finalize_apply(dt, y.view(-1, C), ws, P[bn + ".weight"], P[bn + ".bias"],
                                                 B[bn + ".running_mean"], B[bn + ".running_var"],
@@ -194,17 +223,24 @@ class Engine:
             x = h_all
         return x
 
-    def encode_rows(self, W, P, B, x_cl: Tensor, halves: int, training: bool, saved: Optional[dict]):
-        """x_cl [R2, T, 80] act -> (heads fp32 [R2, 2L], e act [R2, 2048])."""
+    def encode_rows(self, W, P, B, x_cl: Tensor, halves: int, training: bool, saved: Optional[dict],
+                    x_cat: Optional[Tensor] = None):
+        """x_cl [R2, T, 80] act -> (heads fp32 [R2, 2L], e act [R2, 2048]).  x_cat: split-precision copy of x_cl (fp16
+        training step only, see PreparedWeights.split)."""
         dt = self.dt
         R2 = x_cl.shape[0]
         sv_conv = [] if saved is not None else None
         sv_lstm = [] if saved is not None else None
-        h = self._conv_stack(W, P, B, x_cl, ENC_CONVS, halves, training, sv_conv)
+        split = W.split and training and x_cat is not None
+        h = self._conv_stack(W, P, B, x_cl, ENC_CONVS, halves, training, sv_conv, first_cat=x_cat if split else None)
         h = self._lstm(W, "enc_lstm", h, sv_lstm)                      # [R2, T, 128]
         flat = h.view(R2, T_FRAMES * 128)
-        e, _ = ops.linear_fwd(dt, flat, W.lin["enc_linear.linear_layer"], P["enc_linear.linear_layer.bias"], relu=True)
-        _, heads = ops.linear_fwd(dt, e, W.heads_w, W.heads_b, want_f32=True, want_act=False)
+        if split:
+            e, e_cat = ops.linear_fwd_split(dt, flat, W.enc_linear_split, P["enc_linear.linear_layer.bias"], relu=True, want_cat=True)
+            _, heads = ops.linear_fwd(dt, e_cat, W.heads_w3, W.heads_b, want_f32=True, want_act=False)
+        else:
+            e, _ = ops.linear_fwd(dt, flat, W.lin["enc_linear.linear_layer"], P["enc_linear.linear_layer.bias"], relu=True)
+            _, heads = ops.linear_fwd(dt, e, W.heads_w, W.heads_b, want_f32=True, want_act=False)
         if saved is not None:
             saved.update(enc_convs=sv_conv, enc_lstm=sv_lstm, flat=flat, e=e, heads=heads)
         return heads, e
@@ -246,9 +282,11 @@ class Engine:
             f"expected [R, 80, 64] mel chunks, got {tuple(x1.shape)} (the network is locked to 64 frames)"
         saved: Optional[dict] = {} if keep else None
         x_cl = torch.empty((2 * R, T_FRAMES, N_MELS), device=x1.device, dtype=ops.act_dtype(dt))
-        ops.pack_ncl_to_cl(dt, x1, x_cl[:R])
-        ops.pack_ncl_to_cl(dt, x2, x_cl[R:])
-        heads, _ = self.encode_rows(W, P, B, x_cl, 2, training, saved)
+        x_cat = torch.empty((2 * R, T_FRAMES, 3 * N_MELS), device=x1.device, dtype=ops.act_dtype(dt)) \
+            if (W.split and training) else None
+        ops.pack_ncl_to_cl(dt, x1, x_cl[:R], None if x_cat is None else x_cat[:R])
+        ops.pack_ncl_to_cl(dt, x2, x_cl[R:], None if x_cat is None else x_cat[R:])
+        heads, _ = self.encode_rows(W, P, B, x_cl, 2, training, saved, x_cat=x_cat)
         z, q, zs = ops.latent_tail_fwd(dt, heads, eps[0], eps[1], eps[2], R, self.L, self.S, sample_content)
         rec, rec32 = self.decode_rows(W, P, B, z, 2, training, saved)
         post = self.postnet_rows(W, P, B, rec, 2, training, saved)

@@ -30,10 +30,11 @@ _p, _i, _l, _f, _d = C.c_void_p, C.c_int, C.c_long, C.c_float, C.c_double
 # name -> argtypes (all return int)
 _SIGNATURES = {
     "dvae_linear_fwd": [_i, _p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
+    "dvae_linear_fwd_split": [_i, _p, _l, _p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _p],
     "dvae_linear_dgrad": [_i, _p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _p],
     "dvae_linear_wgrad": [_i, _p, _l, _p, _l, _p, _l, _i, _i, _i, _f, _p],
     "dvae_conv5_fwd": [_i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
-    "dvae_conv5_fwd_bnstats": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p],
+    "dvae_conv5_fwd_bnstats": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p],
     "dvae_conv5_dgrad": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "dvae_conv5_wgrad": [_i, _p, _p, _p, _i, _i, _i, _i, _f, _p],
     "dvae_lstm_fwd": [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p],
@@ -48,20 +49,21 @@ _SIGNATURES = {
     "dvae_add_inplace": [_i, _p, _p, _l, _p],
     "dvae_copy_f32": [_p, _p, _l, _p],
     "dvae_add_f32_act": [_i, _p, _p, _p, _l, _p],
-    "dvae_prep_conv_weight": [_i, _p, _p, _i, _i, _p],
+    "dvae_prep_conv_weight": [_i, _p, _p, _p, _i, _i, _p],
+    "dvae_prep_cast_split": [_i, _p, _p, _l, _l, _i, _p],
     "dvae_conv_wgrad_unpack": [_p, _p, _i, _i, _p],
     "dvae_prep_lstm_weight": [_i, _p, _p, _i, _i, _i, _p],
     "dvae_prep_lstm_bias": [_p, _p, _p, _i, _i, _p],
-    "dvae_pack_ncl_to_cl": [_i, _p, _p, _i, _i, _i, _p],
+    "dvae_pack_ncl_to_cl": [_i, _p, _p, _p, _i, _i, _i, _p],
     "dvae_unpack_cl_to_ncl": [_i, _p, _i, _p, _p, _p, _i, _i, _i, _p],
     "dvae_recon_out_bwd": [_i, _p, _p, _p, _p, _i, _i, _i, _f, _p],
     "dvae_chunk_mel": [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "dvae_unchunk_mel": [_i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _p],
     # batch norm / reductions
-    "dvae_bn_train_fwd": [_i] + [_p] * 9 + [_i, _i, _i, _i, _f, _f, _p],
-    "dvae_bn_finalize_apply": [_i] + [_p] * 9 + [_i, _i, _i, _i, _f, _f, _p],
+    "dvae_bn_train_fwd": [_i, _p, _i] + [_p] * 8 + [_i, _i, _i, _i, _f, _f, _p],
+    "dvae_bn_finalize_apply": [_i, _p, _i] + [_p] * 8 + [_i, _i, _i, _i, _f, _f, _p],
     "dvae_bn_eval_fwd": [_i] + [_p] * 7 + [_l, _i, _i, _f, _p],
-    "dvae_bn_train_bwd": [_i] + [_p] * 8 + [_i, _i, _i, _i, _f, _p],
+    "dvae_bn_train_bwd": [_i, _p, _p, _i] + [_p] * 6 + [_i, _i, _i, _i, _f, _p],
     "dvae_colsum": [_i, _p, _p, _l, _i, _l, _f, _p],
     # latent tail / loss / speaker groups
     "dvae_latent_tail_fwd": [_i] + [_p] * 11 + [_i, _i, _i, _i, _p],

@@ -47,6 +47,28 @@ def linear_fwd(dt: int, x: Tensor, w: Tensor, bias: Optional[Tensor], relu: bool
     return out, out32
 
 
+def linear_fwd_split(dt: int, x: Tensor, w_split: Tensor, bias: Optional[Tensor], relu: bool = False, want_cat: bool = False):
+    """Split-precision forward of a small linear layer: w_split [N, 2K] = [w_hi | w_lo] (prep_cast_split), out = x @ (w_hi +
+    w_lo)^T (+bias)(relu).  Returns (out act [M,N], out_cat act [M,3N] = [hi | lo | hi] or None)."""
+    ad = act_dtype(dt)
+    _chk(x, ad), _chk(w_split, ad)
+    M, K = x.shape
+    N = w_split.shape[0]
+    assert w_split.shape[1] == 2 * K
+    out = torch.empty((M, N), device=x.device, dtype=ad)
+    out_cat = torch.empty((M, 3 * N), device=x.device, dtype=ad) if want_cat else None
+    call("dvae_linear_fwd_split", dt, ptr(x), K, ptr(w_split), ptr(bias), ptr(out), None, N, ptr(out_cat), M, N, K, int(relu), 2, stream())
+    return out, out_cat
+
+
+def prep_cast_split(dt: int, src: Tensor, dst: Tensor, parts: int) -> None:
+    """dst act [rows, parts*K] = [hi | lo] (parts 2) or [hi | hi | lo] (parts 3) of src fp32 [rows, K]."""
+    _chk(src, torch.float32), _chk(dst, act_dtype(dt))
+    rows, K = src.shape
+    assert tuple(dst.shape) == (rows, parts * K)
+    call("dvae_prep_cast_split", dt, ptr(src), ptr(dst), rows, K, parts, stream())
+
+
 def linear_dgrad(dt: int, dy: Tensor, w: Tensor, relu_mask: Optional[Tensor] = None, want_f32: bool = False,
                  want_act: bool = True, block_n: int = 0) -> Tuple[Optional[Tensor], Optional[Tensor]]:
     """dx[M,K] = dy[M,N] @ w[N,K]; optionally zeroed where relu_mask <= 0."""
@@ -84,18 +106,28 @@ def conv5_fwd(dt: int, x: Tensor, wk: Tensor, bias: Optional[Tensor], want_f32: 
     return (y, y32) if want_f32 else y
 
 
-def conv5_fwd_bnstats(dt: int, x: Tensor, wk: Tensor, bias: Optional[Tensor], halves: int):
+def _y_is_f32(dt: int, y: Tensor) -> int:
+    """1 when y is unrounded fp32 although the activation dtype is a 16-bit one (the fp16 mode's pre-BatchNorm tensors)."""
+    ad = act_dtype(dt)
+    if y.dtype == ad:
+        return 0
+    assert y.dtype == torch.float32, f"expected {ad} or float32, got {y.dtype}"
+    return 1
+
+
+def conv5_fwd_bnstats(dt: int, x: Tensor, wk: Tensor, bias: Optional[Tensor], halves: int, y_f32: bool = False):
     """conv5_fwd + the statistics pass of the train-mode BatchNorm behind it.  Returns (y, ws): ws holds the per-half
-    column sums / sums of squares of y (double [halves*2*Cout + 1]) for `bn_finalize_apply`."""
+    column sums / sums of squares of y (double [halves*2*Cout + 1]) for `bn_finalize_apply`.  y_f32: store y as
+    unrounded fp32 (fp16 activation dtype only)."""
     ad = act_dtype(dt)
     _chk(x, ad), _chk(wk, ad)
     R, T, Cin = x.shape
     Cout = wk.shape[0]
     assert tuple(wk.shape) == (Cout, 5, Cin) and (R * T) % halves == 0
-    y = torch.empty((R, T, Cout), device=x.device, dtype=ad)
+    y = torch.empty((R, T, Cout), device=x.device, dtype=torch.float32 if y_f32 else ad)
     ws = torch.empty((halves * 2 * Cout + 1,), device=x.device, dtype=torch.float64)
-    call("dvae_conv5_fwd_bnstats", dt, ptr(x), ptr(wk), ptr(bias), ptr(y), R, T, Cin, Cout, ptr(ws), R * T // halves, halves,
-         stream())
+    call("dvae_conv5_fwd_bnstats", dt, ptr(x), ptr(wk), ptr(bias), ptr(y), _y_is_f32(dt, y), R, T, Cin, Cout, ptr(ws),
+         R * T // halves, halves, stream())
     return y, ws
 
 
@@ -198,15 +230,18 @@ def add_inplace(dt: int, a: Tensor, b: Tensor) -> None:
     call("dvae_add_inplace", dt, ptr(a), ptr(b), a.numel(), stream())
 
 
-def prep_conv_weight(dt: int, w: Tensor, out: Optional[Tensor] = None) -> Tensor:
-    """torch Conv1d weight [Co,Ci,5] fp32 -> [Co,5,Ci] activation dtype."""
+def prep_conv_weight(dt: int, w: Tensor, out: Optional[Tensor] = None, out_cat: Optional[Tensor] = None) -> Tensor:
+    """torch Conv1d weight [Co,Ci,5] fp32 -> [Co,5,Ci] activation dtype (+ out_cat [Co,5,3Ci] = [hi | hi | lo])."""
     _chk(w, torch.float32)
     Co, Ci, k = w.shape
     assert k == 5
     wk = out if out is not None else torch.empty((Co, 5, Ci), device=w.device, dtype=act_dtype(dt))
     _chk(wk, act_dtype(dt))
     assert tuple(wk.shape) == (Co, 5, Ci)
-    call("dvae_prep_conv_weight", dt, ptr(w), ptr(wk), Co, Ci, stream())
+    if out_cat is not None:
+        _chk(out_cat, act_dtype(dt))
+        assert tuple(out_cat.shape) == (Co, 5, 3 * Ci)
+    call("dvae_prep_conv_weight", dt, ptr(w), ptr(wk), ptr(out_cat), Co, Ci, stream())
     return wk
 
 
@@ -234,12 +269,15 @@ def prep_lstm_bias(b_ih: Tensor, b_hh: Tensor, dst: Tensor, H: int, tile: int) -
 
 
 # ------------------------------------------------------------------------------- layout
-def pack_ncl_to_cl(dt: int, x: Tensor, out: Tensor) -> None:
-    """x fp32 [R,C,T] -> out act [R,T,C]."""
+def pack_ncl_to_cl(dt: int, x: Tensor, out: Tensor, out_cat: Optional[Tensor] = None) -> None:
+    """x fp32 [R,C,T] -> out act [R,T,C] (+ out_cat act [R,T,3C] = [hi | lo | hi], the split-precision operand)."""
     _chk(x, torch.float32), _chk(out, act_dtype(dt))
     R, Cc, T = x.shape
     assert tuple(out.shape) == (R, T, Cc)
-    call("dvae_pack_ncl_to_cl", dt, ptr(x), ptr(out), R, Cc, T, stream())
+    if out_cat is not None:
+        _chk(out_cat, act_dtype(dt))
+        assert tuple(out_cat.shape) == (R, T, 3 * Cc)
+    call("dvae_pack_ncl_to_cl", dt, ptr(x), ptr(out), ptr(out_cat), R, Cc, T, stream())
 
 
 def unpack_cl_to_ncl(dt: int, a: Tensor, b: Optional[Tensor], want_a: bool = True):
@@ -290,14 +328,14 @@ def bn_train_fwd(dt: int, y: Tensor, gamma: Tensor, beta: Tensor, run_mean: Opti
                  num_batches: Optional[Tensor], halves: int, act: int, eps: float, momentum: float):
     """y [rows, C] (rows = halves * rows_half).  Returns (out act [rows,C], stat fp32 [halves,4,C])."""
     ad = act_dtype(dt)
-    _chk(y, ad)
+    _chk(y)
     C = y.shape[-1]
     rows = y.numel() // C
     assert rows % halves == 0
-    out = torch.empty_like(y)
+    out = torch.empty_like(y, dtype=ad)
     ws = torch.empty((halves * 2 * C,), device=y.device, dtype=torch.float64)
     stat = torch.empty((halves, 4, C), device=y.device, dtype=torch.float32)
-    call("dvae_bn_train_fwd", dt, ptr(y), ptr(out), ptr(gamma), ptr(beta), ptr(run_mean), ptr(run_var), ptr(num_batches),
+    call("dvae_bn_train_fwd", dt, ptr(y), _y_is_f32(dt, y), ptr(out), ptr(gamma), ptr(beta), ptr(run_mean), ptr(run_var), ptr(num_batches),
          ptr(ws), ptr(stat), rows // halves, halves, C, act, eps, momentum, stream())
     return out, stat
 
@@ -306,13 +344,13 @@ def bn_finalize_apply(dt: int, y: Tensor, ws: Tensor, gamma: Tensor, beta: Tenso
                       run_var: Optional[Tensor], num_batches: Optional[Tensor], halves: int, act: int, eps: float, momentum: float):
     """bn_train_fwd without its statistics pass: `ws` comes from conv5_fwd_bnstats.  Returns (out, stat)."""
     ad = act_dtype(dt)
-    _chk(y, ad), _chk(ws, torch.float64)
+    _chk(y), _chk(ws, torch.float64)
     C = y.shape[-1]
     rows = y.numel() // C
     assert rows % halves == 0 and ws.numel() >= halves * 2 * C
-    out = torch.empty_like(y)
+    out = torch.empty_like(y, dtype=ad)
     stat = torch.empty((halves, 4, C), device=y.device, dtype=torch.float32)
-    call("dvae_bn_finalize_apply", dt, ptr(y), ptr(out), ptr(gamma), ptr(beta), ptr(run_mean), ptr(run_var), ptr(num_batches),
+    call("dvae_bn_finalize_apply", dt, ptr(y), _y_is_f32(dt, y), ptr(out), ptr(gamma), ptr(beta), ptr(run_mean), ptr(run_var), ptr(num_batches),
          ptr(ws), ptr(stat), rows // halves, halves, C, act, eps, momentum, stream())
     return out, stat
 
@@ -333,15 +371,15 @@ def bn_train_bwd(dt: int, dout: Tensor, y: Tensor, stat: Tensor, halves: int, ac
                  dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, alpha: float = 1.0):
     """Returns (dy act [rows,C], dgamma fp32 [C], dbeta fp32 [C]); the two parameter gradients are scaled by alpha."""
     ad = act_dtype(dt)
-    _chk(dout, ad), _chk(y, ad), _chk(stat, torch.float32)
+    _chk(dout, ad), _chk(y), _chk(stat, torch.float32)
     C = y.shape[-1]
     rows = y.numel() // C
-    dy = torch.empty_like(y)
+    dy = torch.empty_like(y, dtype=ad)
     ws = torch.empty((halves * 2 * C,), device=y.device, dtype=torch.float64)
     coef = torch.empty((halves * 2 * C,), device=y.device, dtype=torch.float32)
     dgamma = dgamma if dgamma is not None else torch.empty((C,), device=y.device, dtype=torch.float32)
     dbeta = dbeta if dbeta is not None else torch.empty((C,), device=y.device, dtype=torch.float32)
-    call("dvae_bn_train_bwd", dt, ptr(dout), ptr(y), ptr(stat), ptr(ws), ptr(coef), ptr(dy), ptr(dgamma), ptr(dbeta),
+    call("dvae_bn_train_bwd", dt, ptr(dout), ptr(y), _y_is_f32(dt, y), ptr(stat), ptr(ws), ptr(coef), ptr(dy), ptr(dgamma), ptr(dbeta),
          rows // halves, halves, C, act, float(alpha), stream())
     return dy, dgamma, dbeta
 

@@ -32,6 +32,10 @@ int dvae_debug_timing(unsigned long long* buf, int capacity);   /* optional per-
 /* ---- nn.Linear (model/disentangled_vae.py:98-100 LinearNorm.forward; :165-171, :194, :211-213, :232-233, :247) */
 int dvae_linear_fwd(int dtype, const void* x, long ldx, const void* w, const float* bias, void* out, float* out_f32,
                     long ldo, int M, int N, int K, int relu, int block_n, void* stream);
+/* split-precision variants for the small layers (M = rows): w = [N, 2K] = [w_hi | w_lo] when b_terms = 2; out_cat (may be
+ * null) = act [M, 3N] = [hi | lo | hi] of the result, the operand of a following GEMM against [w_hi | w_hi | w_lo] */
+int dvae_linear_fwd_split(int dtype, const void* x, long ldx, const void* w, const float* bias, void* out, float* out_f32,
+                          long ldo, void* out_cat, int M, int N, int K, int relu, int b_terms, void* stream);
 int dvae_linear_dgrad(int dtype, const void* dy, long lddy, const void* w, void* dx, float* dx_f32, const void* relu_mask,
                       long ldx, int M, int N, int K, int block_n, void* stream);
 int dvae_linear_wgrad(int dtype, const void* dy, long lddy, const void* x, long ldx, float* dw, long lddw, int M, int N,
@@ -42,9 +46,11 @@ int dvae_linear_wgrad(int dtype, const void* dy, long lddy, const void* x, long 
 int dvae_conv5_fwd(int dtype, const void* x, const void* wk, const float* bias, void* y, float* y_f32, int R, int T, int Cin,
                    int Cout, void* stream);
 /* conv + the statistics pass of the train-mode BatchNorm1d behind it (:154-160, :178-189, :54-78): bn_ws [halves*2*Cout + 1]
- * doubles = per-half column sums / sums of squares of y; consumed by dvae_bn_finalize_apply */
-int dvae_conv5_fwd_bnstats(int dtype, const void* x, const void* wk, const float* bias, void* y, int R, int T, int Cin, int Cout,
-                           double* bn_ws, int rows_half, int halves, void* stream);
+ * doubles = per-half column sums / sums of squares of y; consumed by dvae_bn_finalize_apply.
+ * y_f32 != 0 (fp16 activations only): y is stored as UNROUNDED fp32 -- the rounding of the pre-BatchNorm tensor is the
+ * largest single contribution to the forward error of a 16-bit pipeline; the BatchNorm entry points take the same flag */
+int dvae_conv5_fwd_bnstats(int dtype, const void* x, const void* wk, const float* bias, void* y, int y_f32, int R, int T, int Cin,
+                           int Cout, double* bn_ws, int rows_half, int halves, void* stream);
 int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,
                      void* stream);
 int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R, int T, int Cin, int Cout, float alpha,
@@ -65,13 +71,14 @@ int dvae_prep_cast(int dtype, const float* src, void* dst, long n, float scale, 
 int dvae_copy_f32(const float* src, float* dst, long n, void* stream);
 int dvae_add_inplace(int dtype, void* a, const void* b, long n, void* stream);
 int dvae_add_f32_act(int dtype, const float* a, const void* b, float* out, long n, void* stream);  /* residual, channels-last */
-int dvae_prep_conv_weight(int dtype, const float* w, void* wk, int Co, int Ci, void* stream);
+int dvae_prep_conv_weight(int dtype, const float* w, void* wk, void* wk_cat, int Co, int Ci, void* stream);   /* wk_cat (may be null): [Co,5,3Ci] = [hi | hi | lo] */
+int dvae_prep_cast_split(int dtype, const float* src, void* dst, long rows, long K, int parts, void* stream);   /* [hi | lo] or [hi | hi | lo] per row */
 int dvae_conv_wgrad_unpack(const float* dwk, float* dw, int Co, int Ci, void* stream);
 int dvae_prep_lstm_weight(int dtype, const float* w, void* dst, int H, int In, int tile, void* stream);
 int dvae_prep_lstm_bias(const float* b_ih, const float* b_hh, float* dst, int H, int tile, void* stream);
 
 /* ---- layout: NCL fp32 <-> channels-last act (the transposes at :204, :240, :244, :248), residual output :277-278 */
-int dvae_pack_ncl_to_cl(int dtype, const float* x, void* y, int R, int C, int T, void* stream);
+int dvae_pack_ncl_to_cl(int dtype, const float* x, void* y, void* y_cat, int R, int C, int T, void* stream);   /* y_cat (may be null): [R,T,3C] = [hi | lo | hi] */
 int dvae_unpack_cl_to_ncl(int dtype, const void* a, int a_is_f32, const void* b, float* out_a, float* out_sum, int R, int C,
                           int T, void* stream);
 int dvae_recon_out_bwd(int dtype, const float* g_rec, const float* g_hat, void* d_rec, void* d_post, int R, int C, int T,
@@ -87,15 +94,15 @@ int dvae_unchunk_mel(int dtype, const float* a, const void* b, const long* out_o
                      float* out, int n_chunks, int C, int T, int clamp, float lo, float hi, void* stream);
 
 /* ---- nn.BatchNorm1d + activation (:159 / :182,:189 / :58,:69,:78 with F.relu :202,:243 and torch.tanh :83) */
-int dvae_bn_train_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
+int dvae_bn_train_fwd(int dtype, const void* y, int y_f32, void* out, const float* gamma, const float* beta, float* run_mean,
                       float* run_var, long long* num_batches, double* ws, float* stat, int rows_half, int halves, int C,
                       int act, float eps, float momentum, void* stream);
-int dvae_bn_finalize_apply(int dtype, const void* y, void* out, const float* gamma, const float* beta, float* run_mean,
+int dvae_bn_finalize_apply(int dtype, const void* y, int y_f32, void* out, const float* gamma, const float* beta, float* run_mean,
                            float* run_var, long long* num_batches, const double* ws, float* stat, int rows_half, int halves,
                            int C, int act, float eps, float momentum, void* stream);
 int dvae_bn_eval_fwd(int dtype, const void* y, void* out, const float* gamma, const float* beta, const float* run_mean,
                      const float* run_var, float* stat, long rows, int C, int act, float eps, void* stream);
-int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, const float* stat, double* ws, float* coef, void* dy,
+int dvae_bn_train_bwd(int dtype, const void* dout, const void* y, int y_f32, const float* stat, double* ws, float* coef, void* dy,
                       float* dgamma, float* dbeta, int rows_half, int halves, int C, int act, float alpha, void* stream);
 int dvae_colsum(int dtype, const void* x, float* out, long rows, int C, long ldx, float alpha, void* stream);
 

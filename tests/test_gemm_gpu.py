@@ -127,6 +127,126 @@ def test_conv5(name, R, Cin, Cout, mt):
     assert (dwk - ref_dw).abs().max().item() <= 2e-5 * ref_dw.abs().max().item() + 1e-5
 
 
+@pytest.mark.parametrize("name,y_f32", [("bf16", False), ("tf32", False), ("fp16", False), ("fp16", True)])
+@pytest.mark.parametrize("R,Cin,Cout,act", [(4, 80, 512, "relu"), (16, 512, 512, "tanh"), (32, 512, 512, "relu"), (6, 512, 80, "none")])
+def test_conv5_bnstats_and_bn_apply(name, y_f32, R, Cin, Cout, act, mt):
+    """The training path of every Conv1d + BatchNorm1d (+ activation) pair: `conv5_fwd_bnstats` (BatchNorm statistics fused
+    into the convolution's staged store epilogue when the persistent kernel runs, a separate reduction otherwise) followed by
+    `bn_finalize_apply`, against F.conv1d + F.batch_norm in train mode, with TWO statistics halves (the x1 call and the x2
+    call of model/disentangled_vae.py:251-254 share one tensor) and the sequential running-statistics updates."""
+    _setup()
+    from dvae_b200 import lib, ops
+    dt = _dt(name)
+    T, halves = 64, 2
+    x = _rand((R, T, Cin), name, seed=21)
+    w = _rand((Cout, Cin, 5), name, 0.05, seed=22)
+    b = torch.randn(Cout, device="cuda")
+    gamma = torch.rand(Cout, device="cuda") + 0.5
+    beta = torch.randn(Cout, device="cuda") * 0.1
+    wk = w.permute(0, 2, 1).contiguous()
+    y, ws = ops.conv5_fwd_bnstats(dt, x, wk, b, halves, y_f32=y_f32)
+    assert y.dtype == (torch.float32 if y_f32 else ops.act_dtype(dt))
+    rm, rv = torch.zeros(Cout, device="cuda"), torch.ones(Cout, device="cuda")
+    nbt = torch.zeros((), device="cuda", dtype=torch.long)
+    code = {"relu": lib.ACT_RELU, "tanh": lib.ACT_TANH, "none": lib.ACT_NONE}[act]
+    out, stat = ops.bn_finalize_apply(dt, y.view(-1, Cout), ws, gamma, beta, rm, rv, nbt, halves, code, 1e-5, 0.1)
+    assert out.dtype == ops.act_dtype(dt)
+    # reference: the two halves are two consecutive module calls
+    rrm, rrv = torch.zeros(Cout, device="cuda"), torch.ones(Cout, device="cuda")
+    refs = []
+    for hsel in range(halves):
+        xh = x[hsel * R // halves:(hsel + 1) * R // halves].float().transpose(1, 2)
+        z = F.batch_norm(F.conv1d(xh, w.float(), b, padding=2), rrm, rrv, gamma, beta, True, 0.1, 1e-5)
+        z = F.relu(z) if act == "relu" else (torch.tanh(z) if act == "tanh" else z)
+        refs.append(z.transpose(1, 2))
+    ref = torch.cat(refs).reshape(-1, Cout)
+    # y is rounded to the storage type before normalisation unless y_f32; the output is rounded once more
+    step = 2.0 ** -8 if name == "bf16" else 2.0 ** -11
+    tol = (2.5 if not y_f32 else 1.2) * step * 4.0 + 1e-5            # |BN output| stays below ~4 for these inputs
+    assert (out.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item() / 4.0)
+    assert int(nbt.item()) == halves
+    assert torch.allclose(rm, rrm, atol=2e-3 if name == "bf16" else 2e-4, rtol=1e-2)
+    assert torch.allclose(rv, rrv, atol=2e-3 if name == "bf16" else 2e-4, rtol=1e-2)
+    # backward through the pair (BatchNorm backward reads the same y, fp32 or not)
+    dout = _rand((R * T, Cout), name, seed=23)
+    dy, dgamma, dbeta = ops.bn_train_bwd(dt, dout, y.view(-1, Cout), stat, halves, code)
+    dys, dgs, dbs = [], 0, 0
+    for hsel in range(halves):
+        sl = slice(hsel * R // halves, (hsel + 1) * R // halves)
+        yh = (y[sl].float()).transpose(1, 2).detach().requires_grad_(True)
+        g_, b_ = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        z = F.batch_norm(yh, None, None, g_, b_, True, 0.1, 1e-5)
+        z = F.relu(z) if act == "relu" else (torch.tanh(z) if act == "tanh" else z)
+        z.backward(dout.float().view(R, T, Cout)[sl].transpose(1, 2))
+        dys.append(yh.grad.transpose(1, 2))
+        dgs, dbs = dgs + g_.grad, dbs + b_.grad
+    ref_dy = torch.cat(dys).reshape(-1, Cout)
+    assert (dy.float() - ref_dy).norm().item() <= (1e-2 if name == "bf16" else 1.5e-3) * ref_dy.norm().item()
+    assert torch.allclose(dgamma, dgs, rtol=2e-3, atol=2e-3 * dgs.abs().max().item())
+    assert torch.allclose(dbeta, dbs, rtol=2e-3, atol=2e-3 * dbs.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 2048, 8192), (130, 64, 2048), (64, 2048, 32)])
+def test_linear_fwd_split_precision(M, N, K):
+    """fp16 mode's split-precision small layers: weights as [w_hi | w_lo] (two passes over the same A tiles), the result
+    optionally re-split as [hi | lo | hi] for a following GEMM against [w_hi | w_hi | w_lo].  The chain then reproduces
+    the fp32 product of the fp16 activations with the FP32 weights to ~1e-6 instead of fp16's 5e-4."""
+    _setup()
+    from dvae_b200 import lib, ops
+    dt = lib.F16
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(M, K, device="cuda", generator=g).half()
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5          # fp32 weights, NOT fp16-representable
+    b = torch.randn(N, device="cuda", generator=g)
+    w_split = torch.empty(N, 2 * K, device="cuda", dtype=torch.float16)
+    ops.prep_cast_split(dt, w, w_split, 2)
+    assert torch.equal(w_split[:, :K], w.half())
+    assert (w_split[:, :K].float() + w_split[:, K:].float() - w).abs().max().item() <= 2.0 ** -21 * w.abs().max().item()
+    out, out_cat = ops.linear_fwd_split(dt, x, w_split, b, relu=True, want_cat=True)
+    ref = torch.relu(x.double() @ w.double().t() + b.double())
+    assert torch.equal(out, out_cat[:, :N]) and torch.equal(out, out_cat[:, 2 * N:])
+    recon = out_cat[:, :N].double() + out_cat[:, N:2 * N].double()
+    # hi + lo carries the fp32 result: what is left is the tensor core's fp32 accumulation over up to 16384 products (~2e-5)
+    assert (recon - ref).norm().item() <= 4e-5 * ref.norm().item()
+    assert (out.double() - ref).norm().item() <= 4e-4 * ref.norm().item()    # hi alone is an fp16 rounding of it
+    # a following small GEMM against [v_hi | v_hi | v_lo]
+    v = torch.randn(64, N, device="cuda", generator=g) / N ** 0.5
+    v3 = torch.empty(64, 3 * N, device="cuda", dtype=torch.float16)
+    ops.prep_cast_split(dt, v, v3, 3)
+    _, y32 = ops.linear_fwd(dt, out_cat, v3, None, want_f32=True, want_act=False)
+    ref2 = ref @ v.double().t()
+    assert (y32.double() - ref2).norm().item() <= 6e-5 * ref2.norm().item()
+    plain = out.double() @ v.half().double().t()
+    assert (plain - ref2).norm().item() > 5 * (y32.double() - ref2).norm().item()      # what the split buys
+
+
+def test_pack_split_and_first_conv():
+    """[hi | lo | hi] input against [w_hi | w_hi | w_lo] weights: the first encoder convolution (80 -> 512) sees its fp32 mel
+    input and fp32 weights to ~1e-6."""
+    _setup()
+    from dvae_b200 import lib, ops
+    dt = lib.F16
+    R, T = 6, 64
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.rand(R, 80, T, device="cuda", generator=g)
+    w = (torch.rand(512, 80, 5, device="cuda", generator=g) - 0.5) * 0.2
+    b = torch.randn(512, device="cuda", generator=g) * 0.1
+    x_cl = torch.empty(R, T, 80, device="cuda", dtype=torch.float16)
+    x_cat = torch.empty(R, T, 240, device="cuda", dtype=torch.float16)
+    ops.pack_ncl_to_cl(dt, x, x_cl, x_cat)
+    assert torch.equal(x_cl, x.transpose(1, 2).half()) and torch.equal(x_cat[..., :80], x_cl) and torch.equal(x_cat[..., 160:], x_cl)
+    assert (x_cat[..., :80].float() + x_cat[..., 80:160].float() - x.transpose(1, 2)).abs().max().item() <= 2.0 ** -21
+    wk = torch.empty(512, 5, 80, device="cuda", dtype=torch.float16)
+    wk_cat = torch.empty(512, 5, 240, device="cuda", dtype=torch.float16)
+    ops.prep_conv_weight(dt, w, out=wk, out_cat=wk_cat)
+    assert torch.equal(wk, w.permute(0, 2, 1).half()) and torch.equal(wk_cat[..., :80], wk) and torch.equal(wk_cat[..., 80:160], wk)
+    y, _ = ops.conv5_fwd_bnstats(dt, x_cat, wk_cat, b, 2, y_f32=True)
+    ref = F.conv1d(x.double(), w.double(), b.double(), padding=2).transpose(1, 2)
+    assert (y.double() - ref).norm().item() <= 1e-5 * ref.norm().item()
+    y_plain, _ = ops.conv5_fwd_bnstats(dt, x_cl, wk, b, 2, y_f32=True)
+    assert (y_plain.double() - ref).norm().item() > 10 * (y.double() - ref).norm().item()
+
+
 def _gate_perm(H, tile=None):
     n = torch.arange(4 * H)
     return (n % 4) * H + n // 4            # dst row n = 4*u + g  <-  src row g*H + u
