@@ -809,7 +809,20 @@ static int lstm_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, con
           wb.per_j[1] = BK; wb.per_box[0] = BK; wb.per_tile[0] = RBN; wb.per_z[2] = 1;
           GemmShape shp{rows, H, 4 * H / BK, 4 * H / BK, rsplits, nullptr, nullptr};
           shp.f16 = kIsF16<AT>;
-          EpiReduceTma::Params ep{trec};
+          EpiReduceTma::Params ep{};
+          ep.tm_out = trec;
+          static const int pf_env = env_int("DVAE_LSTM_BWD_PREFETCH", 1);
+          if (pf_env && D == 1) {   // what this step's cell-backward kernel (next in the stream) will read: time index tf
+            const AT* g_t = gates + (long)tf * D * 4 * H;
+            const float* c_t = c_all + (long)tf * D * H;
+            const AT* dh_t = dh_all + (long)tf * D * H;
+            ep.pf_ptr[0] = g_t;  ep.pf_row_stride[0] = ldx * EB; ep.pf_row_bytes[0] = 4 * H * EB;
+            ep.pf_ptr[1] = c_t;  ep.pf_row_stride[1] = ldh * 4;  ep.pf_row_bytes[1] = H * 4;
+            ep.pf_ptr[2] = (s == T - 1) ? nullptr : c_t - (long)D * H;
+            ep.pf_row_stride[2] = ldh * 4; ep.pf_row_bytes[2] = H * 4;
+            ep.pf_ptr[3] = dh_t; ep.pf_row_stride[3] = ldh * EB; ep.pf_row_bytes[3] = H * EB;
+            ep.pf_rows = rows;
+          }
           dim3 grid(ceil_div(rows, 128), H / RBN, D * rsplits);
           int e;
           if (lstm_pair(ceil_div(rows, 128)))

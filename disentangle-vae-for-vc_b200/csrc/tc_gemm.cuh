@@ -648,6 +648,13 @@ struct EpiReduceTma {
   static constexpr int kCtasPerSm = 1;
   struct Params {
     CUtensorMap tm_out;   // fp32 {N, M, batches}, box {32, 128, 1}
+    // Optional: up to four strided row sets that the NEXT kernel in the stream streams from HBM (the LSTM cell backward
+    // reads this time step's saved gates / cell states / output gradient).  The epilogue warps are idle while the main loop
+    // runs, so they pull those lines into L2: the memory-bound consumer then runs at L2 rather than HBM bandwidth.
+    const void* pf_ptr[4];
+    long pf_row_stride[4];   // bytes between rows
+    int pf_row_bytes[4];     // contiguous bytes per row
+    int pf_rows;
   };
   template <int BLOCK_N>
   static __host__ __device__ constexpr int staging_bytes() { return BLOCK_N * 4 * kBlockM; }
@@ -656,6 +663,21 @@ struct EpiReduceTma {
   template <int BLOCK_N>
   static __device__ __forceinline__ void prefetch(const Params& p, int, int, int, int, int, const GemmShape&) {
     if ((threadIdx.x & 255) == 64) ptx::prefetch_tmap(&p.tm_out);
+    if (p.pf_rows <= 0) return;
+    const long cta = (static_cast<long>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const long nthr = static_cast<long>(gridDim.x) * gridDim.y * gridDim.z * kEpilogueThreads;
+    const long me = cta * kEpilogueThreads + (static_cast<int>(threadIdx.x) - 64);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const char* base = static_cast<const char*>(p.pf_ptr[k]);
+      if (base == nullptr) continue;
+      const int lpr = (p.pf_row_bytes[k] + 127) >> 7;
+      const long total = static_cast<long>(p.pf_rows) * lpr;
+      for (long i = me; i < total; i += nthr) {
+        const long r = i / lpr;
+        prefetch_l2(base + r * p.pf_row_stride[k] + ((i - r * lpr) << 7));
+      }
+    }
   }
   template <int BLOCK_N> struct Regs {};
   template <int BLOCK_N>
