@@ -10,7 +10,7 @@
 namespace dvae {
 
 // activation storage: bf16 or fp16 (tcgen05 kind::f16), or fp32 kept on the tf32 grid (kind::tf32)
-enum DType : int { kBF16 = 0, kTF32 = 1, kF16 = 2, kF32 = 3 };   // kF32: plain fp32 (memory-bound kernels only)
+enum DType : int { kBF16 = 0, kTF32 = 1, kF16 = 2, kF32 = 3 };   // kF32: strict fp32, CUDA cores (ops_simt.cu)
 
 void set_last_error(const std::string& msg);
 
@@ -59,5 +59,22 @@ int lstm_seq_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_a
                  cudaStream_t st);
 int lstm_seq_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all,
                  int rows, int T, int H, int D, cudaStream_t st);
+
+// Strict-fp32 mode (ops_simt.cu): CUDA-core fp32 implementations of every contraction, same index conventions as the
+// tensor-core launchers
+int simt_linear_fwd(const float* x, long ldx, const float* w, const float* bias, float* out, float* out_f32, long ldo, int M,
+                    int N, int K, int relu, cudaStream_t st);
+int simt_linear_dgrad(const float* dy, long lddy, const float* w, float* dx, float* dx_f32, const float* relu_mask, long ldx,
+                      int M, int N, int K, cudaStream_t st);
+int simt_linear_wgrad(const float* dy, long lddy, const float* x, long ldx, float* dw, long lddw, int M, int N, int K,
+                      float alpha, cudaStream_t st);
+int simt_conv5(const float* x, const float* wk, const float* bias, float* y, float* y_f32, int R, int T, int Cin, int Cout,
+               bool dgrad, cudaStream_t st);
+int simt_conv5_wgrad(const float* dy, const float* x, float* dwk, int R, int T, int Cin, int Cout, float alpha, cudaStream_t st);
+int simt_lstm_fwd(float* xg, const float* whh_p, float* h_all, float* c_all, int rows, int T, int H, int D, cudaStream_t st);
+int simt_lstm_bwd(const float* dh_all, const float* gates, const float* c_all, const float* whh_n, float* da_all, float* dc_ws,
+                  int rows, int T, int H, int D, cudaStream_t st);
+int simt_lstm_wgrad_hh(const float* da_all, const float* h_all, float* dwhh, int rows, int T, int H, int D, float alpha,
+                       cudaStream_t st);
 
 }  // namespace dvae

@@ -975,6 +975,7 @@ extern "C" {
 int dvae_linear_fwd(int dtype, const void* x, long ldx, const void* w, const float* bias, void* out, float* out_f32,
                     long ldo, int M, int N, int K, int relu, int block_n, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == kF32) return simt_linear_fwd((const float*)x, ldx, (const float*)w, bias, (float*)out, out_f32, ldo, M, N, K, relu, st);
   DISPATCH_AT(dtype, linear_fwd_t<AT>((const AT*)x, ldx, (const AT*)w, bias, (AT*)out, out_f32, ldo, M, N, K, relu, block_n, st));
 }
 // Split-precision variants for the small linear layers (M = rows, not rows x frames: their cost is negligible):
@@ -990,6 +991,7 @@ int dvae_linear_fwd_split(int dtype, const void* x, long ldx, const void* w, con
 int dvae_linear_dgrad(int dtype, const void* dy, long lddy, const void* w, void* dx, float* dx_f32, const void* relu_mask,
                       long ldx, int M, int N, int K, int block_n, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == kF32) return simt_linear_dgrad((const float*)dy, lddy, (const float*)w, (float*)dx, dx_f32, (const float*)relu_mask, ldx, M, N, K, st);
   DISPATCH_AT(dtype, linear_dgrad_t<AT>((const AT*)dy, lddy, (const AT*)w, (AT*)dx, dx_f32, (const AT*)relu_mask, ldx, M, N, K, block_n, st));
 }
 
@@ -997,12 +999,14 @@ int dvae_linear_dgrad(int dtype, const void* dy, long lddy, const void* w, void*
 int dvae_linear_wgrad(int dtype, const void* dy, long lddy, const void* x, long ldx, float* dw, long lddw, int M, int N,
                       int K, float alpha, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == kF32) return simt_linear_wgrad((const float*)dy, lddy, (const float*)x, ldx, dw, lddw, M, N, K, alpha, st);
   DISPATCH_AT(dtype, linear_wgrad_t<AT>((const AT*)dy, lddy, (const AT*)x, ldx, dw, lddw, M, N, K, alpha, st));
 }
 
 int dvae_conv5_fwd(int dtype, const void* x, const void* wk, const float* bias, void* y, float* y_f32, int R, int T, int Cin,
                    int Cout, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == kF32) return simt_conv5((const float*)x, (const float*)wk, bias, (float*)y, y_f32, R, T, Cin, Cout, false, st);
   DISPATCH_AT(dtype, conv5_fwd_t<AT>((const AT*)x, (const AT*)wk, bias, (AT*)y, y_f32, R, T, Cin, Cout, false, st));
 }
 
@@ -1015,24 +1019,31 @@ int dvae_conv5_fwd_bnstats(int dtype, const void* x, const void* wk, const float
   auto st = static_cast<cudaStream_t>(stream);
   DVAE_REQUIRE(bn_ws != nullptr && halves >= 1 && (long)rows_half * halves == (long)R * T, "rows_half * halves must equal R * T");
   DVAE_CHECK_CUDA(cudaMemsetAsync(bn_ws, 0, sizeof(double) * ((long)halves * 2 * Cout + 1), st));
+  if (dtype == kF32) {
+    if (int e = simt_conv5((const float*)x, (const float*)wk, bias, (float*)y, nullptr, R, T, Cin, Cout, false, st)) return e;
+    return bn_stats_launch(kF32, y, bn_ws, rows_half, halves, Cout, st);
+  }
   DISPATCH_AT(dtype, conv5_fwd_bnstats_t<AT>(dtype, x, wk, bias, y, y_f32, R, T, Cin, Cout, bn_ws, rows_half, halves, st));
 }
 
 int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,
                      void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == kF32) return simt_conv5((const float*)dy, (const float*)wk, nullptr, (float*)dx, dx_f32, R, T, Cin, Cout, true, st);
   DISPATCH_AT(dtype, conv5_fwd_t<AT>((const AT*)dy, (const AT*)wk, nullptr, (AT*)dx, dx_f32, R, T, Cin, Cout, true, st));
 }
 
 int dvae_conv5_wgrad(int dtype, const void* dy, const void* x, float* dwk, int R, int T, int Cin, int Cout, float alpha,
                      void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == kF32) return simt_conv5_wgrad((const float*)dy, (const float*)x, dwk, R, T, Cin, Cout, alpha, st);
   DISPATCH_AT(dtype, conv5_wgrad_t<AT>((const AT*)dy, (const AT*)x, dwk, R, T, Cin, Cout, alpha, st));
 }
 
 int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_all, int rows, int T, int H, int D,
                   void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == kF32) return simt_lstm_fwd((float*)xg, (const float*)whh_p, (float*)h_all, c_all, rows, T, H, D, st);
   if (lstm_seq_supported(H, T)) return lstm_seq_fwd(dtype, xg, whh_p, h_all, c_all, rows, T, H, D, st);
   DISPATCH_AT(dtype, lstm_fwd_t<AT>((AT*)xg, (const AT*)whh_p, (AT*)h_all, c_all, rows, T, H, D, st));
 }
@@ -1042,6 +1053,7 @@ int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_
 int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all,
                   float* dc_ws, float* splitk_ws, int* tickets, int rows, int T, int H, int D, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == kF32) return simt_lstm_bwd((const float*)dh_all, (const float*)gates, c_all, (const float*)whh_n, (float*)da_all, dc_ws, rows, T, H, D, st);
   if (lstm_seq_supported(H, T)) return lstm_seq_bwd(dtype, dh_all, gates, c_all, whh_n, da_all, rows, T, H, D, st);
   DISPATCH_AT(dtype, lstm_bwd_t<AT>((const AT*)dh_all, (const AT*)gates, c_all, (const AT*)whh_n, (AT*)da_all, dc_ws, splitk_ws,
                                     tickets, rows, T, H, D, st));
@@ -1060,6 +1072,7 @@ int dvae_lstm_bwd_workspace(int dtype, int rows, int H, int D, long* ws_floats, 
 int dvae_lstm_wgrad_hh(int dtype, const void* da_all, const void* h_all, float* dwhh, int rows, int T, int H, int D,
                        float alpha, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == kF32) return simt_lstm_wgrad_hh((const float*)da_all, (const float*)h_all, dwhh, rows, T, H, D, alpha, st);
   DISPATCH_AT(dtype, lstm_wgrad_hh_t<AT>((const AT*)da_all, (const AT*)h_all, dwhh, rows, T, H, D, alpha, st));
 }
 

@@ -374,14 +374,19 @@ __global__ void bn_eval_stat_kernel(const float* __restrict__ gamma, const float
   }
 }
 
+// tanh of the postnet activations: the fast exp-based form for the tensor-core modes, libm's for strict fp32 (AT = float)
+template <typename AT> __device__ __forceinline__ float act_tanh(float z) { return tanh_f(z); }
+template <> __device__ __forceinline__ float act_tanh<float>(float z) { return tanhf(z); }
+template <typename AT>
 __device__ __forceinline__ float apply_act(float z, int act) {
   if (act == kAct_Relu) return fmaxf(z, 0.f);
-  if (act == kAct_Tanh) return tanh_f(z);
+  if (act == kAct_Tanh) return act_tanh<AT>(z);
   return z;
 }
+template <typename AT>
 __device__ __forceinline__ float act_grad_from_z(float z, int act) {
   if (act == kAct_Relu) return z > 0.f ? 1.f : 0.f;
-  if (act == kAct_Tanh) { const float t = tanh_f(z); return 1.f - t * t; }
+  if (act == kAct_Tanh) { const float t = act_tanh<AT>(z); return 1.f - t * t; }
   return 1.f;
 }
 
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const YT* __restrict__ y,
         float v[8];
         Act8<YT>::unpack(raw[u], v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = apply_act(fmaf(v[k], sc[k], sh[k]), act);
+        for (int k = 0; k < 8; ++k) v[k] = apply_act<AT>(fmaf(v[k], sc[k], sh[k]), act);
         Act8<AT>::store(dst + static_cast<long>(r + u * kBnLanes) * C, v);
       }
     }
@@ -465,7 +470,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const AT* __restrict
           Act8<AT>::unpack(rd[u], d);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float dz = d[i] * act_grad_from_z(fmaf(v[i], sc[i], sh[i]), act);
+            const float dz = d[i] * act_grad_from_z<AT>(fmaf(v[i], sc[i], sh[i]), act);
             s[i] += dz;
             q[i] = fmaf(dz, (v[i] - mean[i]) * rstd[i], q[i]);
           }
@@ -533,7 +538,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const AT* __restrict_
         Act8<AT>::unpack(rd[u], d);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float dz = d[k] * act_grad_from_z(fmaf(v[k], sc[k], sh[k]), act);
+          const float dz = d[k] * act_grad_from_z<AT>(fmaf(v[k], sc[k], sh[k]), act);
           const float xh = (v[k] - mean[k]) * rstd[k];
           d[k] = sc[k] * (dz - k0[k] - xh * k1[k]);
         }
@@ -585,6 +590,7 @@ using namespace dvae;
     if ((dtype) == kBF16) { using AT = bf16; __VA_ARGS__; }  \
     else if ((dtype) == kF16) { using AT = __half; __VA_ARGS__; } \
     else if ((dtype) == kTF32) { using AT = tf32_t; __VA_ARGS__; } \
+    else if ((dtype) == kF32) { using AT = float; __VA_ARGS__; } \
     else { set_last_error("unknown dtype tag"); return 1; }  \
   } while (0)
 
@@ -609,8 +615,7 @@ int bn_stats_launch(int dtype, const void* y, double* ws, int rows_half, int hal
   const long rows = static_cast<long>(rows_half) * halves;
   const int rb_red = bn_rows_per_block(rows_half, 512);
   const dim3 g_red(ceil_div(C, kBnSlab), static_cast<unsigned>(rows / rb_red));
-  if (dtype == kF32) bn_stats_kernel<float><<<g_red, 256, 0, st>>>((const float*)y, ws, rows_half, C, rb_red);
-  else DISPATCH_AT(dtype, bn_stats_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)y, ws, rows_half, C, rb_red));
+  DISPATCH_AT(dtype, bn_stats_kernel<AT><<<g_red, 256, 0, st>>>((const AT*)y, ws, rows_half, C, rb_red));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -457,6 +457,7 @@ using namespace dvae;
     if ((dtype) == kBF16) { using AT = bf16; __VA_ARGS__; }  \
     else if ((dtype) == kF16) { using AT = __half; __VA_ARGS__; } \
     else if ((dtype) == kTF32) { using AT = tf32_t; __VA_ARGS__; } \
+    else if ((dtype) == kF32) { using AT = float; __VA_ARGS__; } \
     else { set_last_error("unknown dtype tag"); return 1; }  \
   } while (0)
 

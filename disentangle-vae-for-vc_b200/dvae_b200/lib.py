@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdvae_b200.so")
 
-BF16, TF32, F16 = 0, 1, 2
+BF16, TF32, F16, F32 = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
 if not os.path.exists(LIB_PATH):

@@ -3,7 +3,7 @@
 These allocate outputs with torch (device memory / stream plumbing only) and pass raw pointers to
 libdvae_b200.so.  No arithmetic happens in Python or torch here.
 Activation storage dtype `dt` is lib.BF16 (torch.bfloat16, tcgen05 kind::f16), lib.F16 (torch.float16, kind::f16) or
-lib.TF32 (torch.float32 storage, tcgen05 kind::tf32).  `alpha` / `scale` arguments carry the power-of-two gradient
+lib.TF32 (torch.float32 storage, tcgen05 kind::tf32); lib.F32 is the strict mode (fp32 on the CUDA cores, for the 1e-5 check).  `alpha` / `scale` arguments carry the power-of-two gradient
 scale of the fp16 mode (1.0 otherwise).
 """
 from __future__ import annotations
@@ -18,7 +18,7 @@ from .lib import call, ptr, stream
 Tensor = torch.Tensor
 
 
-_ACT_DTYPES = {lib.BF16: torch.bfloat16, lib.F16: torch.float16, lib.TF32: torch.float32}
+_ACT_DTYPES = {lib.BF16: torch.bfloat16, lib.F16: torch.float16, lib.TF32: torch.float32, lib.F32: torch.float32}
 
 
 def act_dtype(dt: int) -> torch.dtype:

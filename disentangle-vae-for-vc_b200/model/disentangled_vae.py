@@ -7,7 +7,7 @@ their reference names, shapes and initialisation); their `forward` is never call
 libdvae_b200.so through `dvae_b200.engine`; there is no PyTorch / CPU fallback.
 
 Extras that do not change the reference API:
-  * `DisentangledVAE(..., precision="fp16"|"tf32"|"bf16")` (last, optional) or env DVAE_B200_PRECISION
+  * `DisentangledVAE(..., precision="fp16"|"tf32"|"bf16"|"fp32")` (last, optional) or env DVAE_B200_PRECISION
   * `DisentangledVAE.noise_hook`: callable(shape) -> fp32 CPU/CUDA tensor, to supply the reparameterisation noise
     externally (the reference draws it on the CPU default generator, model/disentangled_vae.py:224)
 """
@@ -26,7 +26,7 @@ from dvae_b200.engine import Engine, PreparedWeights
 from model.variational_base_vae import VariationalBaseModelVAE
 
 
-PRECISIONS = {"bf16": lib.BF16, "tf32": lib.TF32, "fp16": lib.F16}
+PRECISIONS = {"bf16": lib.BF16, "tf32": lib.TF32, "fp16": lib.F16, "fp32": lib.F32}   # fp32: strict mode, CUDA cores (checking)
 DEFAULT_PRECISION = "fp16"   # the fastest storage type that meets the reference-parity tolerance (DESIGN.md "Numerics")
 
 

@@ -11,7 +11,8 @@
  * dvae_last_error() (thread local).  `dtype` tags the activation storage: 0 = bf16 (tcgen05 kind::f16),
  * 1 = fp32 kept on the tf32 grid (tcgen05 kind::tf32), 2 = IEEE fp16 (kind::f16; tf32's 10 mantissa bits at bf16's
  * byte count and rate -- the caller keeps the activation-gradient stream scaled by a power of two: `scale` / `gscale`
- * arguments put it on the stream, `alpha` arguments take it off the parameter gradients).  "act" below means that
+ * arguments put it on the stream, `alpha` arguments take it off the parameter gradients), 3 = strict fp32: fp32 storage,
+ * every contraction on the CUDA cores with fp32 FMA accumulation (the mode of north_star's 1e-5 check).  "act" means that
  * storage type.  Activations are channels-last [rows, T, C]; T = 64 (model/disentangled_vae.py:165,235).
  */
 #ifndef DVAE_B200_H

@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-DTS = ["bf16", "tf32", "fp16"]
+DTS = ["bf16", "tf32", "fp16", "fp32"]
 
 
 def _setup():
@@ -20,7 +20,7 @@ def _setup():
 
 def _dt(name):
     from dvae_b200 import lib
-    return {"bf16": lib.BF16, "tf32": lib.TF32, "fp16": lib.F16}[name]
+    return {"bf16": lib.BF16, "tf32": lib.TF32, "fp16": lib.F16, "fp32": lib.F32}[name]
 
 
 def _rand(shape, name, scale=1.0, seed=0):
@@ -30,6 +30,8 @@ def _rand(shape, name, scale=1.0, seed=0):
         return t.to(torch.bfloat16)
     if name == "fp16":
         return t.to(torch.float16)
+    if name == "fp32":
+        return t                      # strict mode: nothing is rounded
     # tf32: keep 10 mantissa bits so the tensor core sees exactly these values
     return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
 
@@ -37,7 +39,7 @@ def _rand(shape, name, scale=1.0, seed=0):
 def _tol(name, ref):
     # result rounding to the storage dtype + fp32 summation-order noise
     # (bf16: 8 mantissa bits; tf32 storage is rounded onto the 10-bit tf32 grid when stored)
-    return (2.0 ** -8 if name == "bf16" else 2.0 ** -11) * ref.abs().max().item() + 1e-6
+    return {"bf16": 2.0 ** -8, "fp32": 5e-6}.get(name, 2.0 ** -11) * ref.abs().max().item() + 1e-6
 
 
 @pytest.fixture(params=["1", "2", "p"], ids=["rows128", "rows256", "persistent"])
@@ -127,7 +129,7 @@ def test_conv5(name, R, Cin, Cout, mt):
     assert (dwk - ref_dw).abs().max().item() <= 2e-5 * ref_dw.abs().max().item() + 1e-5
 
 
-@pytest.mark.parametrize("name,y_f32", [("bf16", False), ("tf32", False), ("fp16", False), ("fp16", True)])
+@pytest.mark.parametrize("name,y_f32", [("bf16", False), ("tf32", False), ("fp16", False), ("fp16", True), ("fp32", False)])
 @pytest.mark.parametrize("R,Cin,Cout,act", [(4, 80, 512, "relu"), (16, 512, 512, "tanh"), (32, 512, 512, "relu"), (6, 512, 80, "none")])
 def test_conv5_bnstats_and_bn_apply(name, y_f32, R, Cin, Cout, act, mt):
     """The training path of every Conv1d + BatchNorm1d (+ activation) pair: `conv5_fwd_bnstats` (BatchNorm statistics fused
@@ -287,7 +289,7 @@ def test_lstm(name, rows, H, D, T):
     wr = whh.float().requires_grad_(True)
     ref = _lstm_ref(xr, wr, D, H)
     err = (h_all.float() - ref).abs().max().item()
-    tol = 3e-2 if name == "bf16" else 2e-3       # h is re-rounded to the storage dtype every step (64 steps)
+    tol = {"bf16": 3e-2, "fp32": 2e-5}.get(name, 2e-3)       # h is re-rounded to the storage dtype every step (64 steps)
     assert err <= tol, f"lstm fwd max err {err}"
     # backward: grad wrt the natural-order x-projection is exactly da_all
     dh = _rand((rows, T, D * H), name, seed=13)
@@ -295,11 +297,11 @@ def test_lstm(name, rows, H, D, T):
     da = ops.lstm_bwd(dt, dh, xg, c_all, whh.contiguous(), H, D)
     ref_da = xr.grad.reshape(rows, T, D * 4 * H)
     rel = (da.float() - ref_da).norm().item() / ref_da.norm().item()
-    assert rel <= (3e-2 if name == "bf16" else 3e-3), f"lstm bwd rel err {rel}"
+    assert rel <= {"bf16": 3e-2, "fp32": 2e-5}.get(name, 3e-3), f"lstm bwd rel err {rel}"
     dwhh = torch.zeros((D, 4 * H, H), device="cuda")
     ops.lstm_wgrad_hh(dt, da, h_all, dwhh, H, D)
     relw = (dwhh - wr.grad).norm().item() / wr.grad.norm().item()
-    assert relw <= (3e-2 if name == "bf16" else 3e-3), f"lstm dW_hh rel err {relw}"
+    assert relw <= {"bf16": 3e-2, "fp32": 2e-5}.get(name, 3e-3), f"lstm dW_hh rel err {relw}"
 
 
 @pytest.mark.parametrize("env", [

@@ -20,12 +20,14 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
-DTS = ["bf16", "tf32", "fp16"]
-TENSOR_TOL = {"bf16": 1.5e-2, "tf32": 2e-3, "fp16": 2e-3}
-HAT_TOL = {"bf16": 4e-2, "tf32": 5e-3, "fp16": 5e-3}
-LOSS_TOL = {"bf16": [1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 5e-3, 5e-3, 1e-2], "tf32": [1e-3] * 8, "fp16": [1e-3] * 8}
-COS_TOL = {"bf16": 0.96, "tf32": 0.999, "fp16": 0.999}
-GLOBAL_COS_TOL = {"bf16": 0.997, "tf32": 0.9999, "fp16": 0.9999}
+DTS = ["bf16", "tf32", "fp16", "fp32"]
+# fp32 = the strict mode (CUDA cores, nothing rounded below fp32): north_star's 1e-5.  Two fp32 implementations that sum in a
+# different order differ by ~1e-6 per layer; the hat outputs amplify that ~3x like every other error (DESIGN.md "Numerics")
+TENSOR_TOL = {"bf16": 1.5e-2, "tf32": 2e-3, "fp16": 1.5e-3, "fp32": 1e-5}
+HAT_TOL = {"bf16": 4e-2, "tf32": 5e-3, "fp16": 5e-3, "fp32": 3e-5}
+LOSS_TOL = {"bf16": [1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 5e-3, 5e-3, 1e-2], "tf32": [1e-3] * 8, "fp16": [1e-3] * 8, "fp32": [1e-5] * 8}
+COS_TOL = {"bf16": 0.96, "tf32": 0.999, "fp16": 0.999, "fp32": 0.99999}
+GLOBAL_COS_TOL = {"bf16": 0.997, "tf32": 0.9999, "fp16": 0.9999, "fp32": 0.999999}
 # conv biases that feed a train-mode BatchNorm have an identically-zero gradient (rounding noise in the reference)
 import re
 ZERO_GRAD = lambda k: re.search(r"(\.0\.conv\.bias$)|(^dec_modules\.\d\.0\.bias$)", k) is not None
@@ -345,9 +347,10 @@ def _grad_report(mine, ref):
 # call); measured values are printed by the test and recorded in DESIGN.md "Numerics" / profiles/r02_parity_cfg2.txt
 FULL_TOL = {
     #        8 tensors  2 hat   loss    KL     matched min / global      free min / global
-    "fp16": (1.5e-3, 4e-3, 1e-3, 2e-3, 0.999, 0.9999, 0.98, 0.99),
+    "fp16": (1e-3, 4e-3, 1e-3, 2e-3, 0.999, 0.9999, 0.98, 0.99),
     "tf32": (1.5e-3, 4e-3, 1e-3, 2e-3, 0.999, 0.9999, 0.98, 0.99),
     "bf16": (1.5e-2, 4e-2, 1e-3, 1e-2, 0.96, 0.997, 0.90, 0.95),
+    "fp32": (1e-5, 3e-5, 1e-5, 1e-5, 0.99999, 0.999999, 0.999, 0.9999),
 }
 
 

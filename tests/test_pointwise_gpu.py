@@ -6,12 +6,12 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
-DTS = ["bf16", "tf32", "fp16"]
+DTS = ["bf16", "tf32", "fp16", "fp32"]
 
 
 def _dt(name):
     from dvae_b200 import lib
-    return {"bf16": lib.BF16, "tf32": lib.TF32, "fp16": lib.F16}[name]
+    return {"bf16": lib.BF16, "tf32": lib.TF32, "fp16": lib.F16, "fp32": lib.F32}[name]
 
 
 def _act(t, name):
@@ -20,6 +20,8 @@ def _act(t, name):
         return t.to(torch.bfloat16)
     if name == "fp16":
         return t.to(torch.float16)
+    if name == "fp32":
+        return t.float()
     bits = t.float().contiguous().view(torch.int32)
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
 
