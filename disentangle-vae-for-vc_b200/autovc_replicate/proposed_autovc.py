@@ -93,10 +93,13 @@ class Generator(nn.Module):
         self.decoder = Decoder(dim_neck, dim_emb, dim_pre)
         self.postnet = Postnet()
         self._dt = _precision_tag(precision)
-        # fp16 storage carries the gradient stream scaled (see Engine.grad_scale); there is no loss in the reference to
-        # derive a default from, so a mean-reduced loss over ~10^6 elements is assumed: override with `.grad_scale = ...`
-        self._engine = Engine(self._dt, dim_emb, 1, grad_scale=float(os.environ.get("DVAE_B200_GRAD_SCALE", 0)) or
-                              (2.0 ** 20 if self._dt == lib.F16 else 1.0))
+        # fp16 storage carries the activation-gradient stream scaled by a power of two (Engine.grad_scale).  The reference
+        # defines no loss for this network, so the scale follows the incoming gradient: `_pick_grad_scale` lifts its largest
+        # magnitude to ~4 (DVAE_B200_GRAD_SCALE or `.grad_scale = ...` pins it instead).
+        env_scale = float(os.environ.get("DVAE_B200_GRAD_SCALE", 0))
+        self._engine = Engine(self._dt, dim_emb, 1, grad_scale=env_scale or 1.0)
+        self._auto_scale = self._dt == lib.F16 and not env_scale
+        self._amax_reader = None
         self._param_names = [n for n, _ in self.named_parameters()]
         self._prep_cache = None
         self._debug_keep_saved = False
@@ -109,6 +112,23 @@ class Generator(nn.Module):
     @grad_scale.setter
     def grad_scale(self, v: float) -> None:
         self._engine.grad_scale = float(v)
+        self._auto_scale = False
+
+    def _pick_grad_scale(self, grads) -> None:
+        """fp16 mode: power-of-two scale that puts the largest incoming output gradient near 4.  The magnitude is read back
+        asynchronously, one step late (the first backward waits for it once), so the launch queue never drains."""
+        import math
+        from dvae_b200.data import AsyncScalars
+        amax = torch.stack([g.detach().abs().max() for g in grads if g is not None]).max().reshape(1).float()
+        if self._amax_reader is None:
+            self._amax_reader = AsyncScalars(1, amax.device)
+            self._amax_reader.push(amax)
+            prev = [amax.item()]
+        else:
+            prev = self._amax_reader.push(amax)
+        a = prev[0] if prev else 0.0
+        if a > 0.0 and math.isfinite(a):
+            self._engine.grad_scale = float(2.0 ** math.floor(math.log2(4.0 / a)))
 
     def _prepared(self) -> PreparedWeights:
         """See DisentangledVAE._prepared: rebuilt on re-allocation, refreshed in place when a parameter was written."""
@@ -167,6 +187,8 @@ class Generator(nn.Module):
         ad = ops.act_dtype(dt)
         dev = saved["flat"].device
         sink = GradSink(dev, E.buckets)
+        if self._auto_scale:
+            self._pick_grad_scale((g_mel, g_post))
         shape = (R, T_FRAMES, N_MELS)
         d_post = torch.zeros(shape, device=dev, dtype=ad)
         d_rec = torch.zeros(shape, device=dev, dtype=ad)

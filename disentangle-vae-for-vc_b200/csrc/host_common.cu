@@ -84,6 +84,26 @@ int num_sms() {
 }  // namespace dvae
 
 extern "C" {
+// Bytes of caller-provided scratch an op needs (nothing in this library allocates): `op` names the buffer, n0..n2 its shape
+// parameters.  Returns -1 for an unknown name.
+//   "bn_stats"     (halves, C)      double sums of dvae_conv5_fwd_bnstats / dvae_bn_train_fwd / dvae_bn_train_bwd (`ws`)
+//   "bn_stat"      (halves, C)      fp32 mean / rstd / scale / shift kept for the backward (`stat`)
+//   "bn_bwd_coef"  (halves, C)      fp32 coefficients of dvae_bn_train_bwd (`coef`)
+//   "loss"         ()               accumulators + ticket of dvae_loss_fwd (`ws`)
+//   "lstm_bwd_dc"  (rows, H, D)     dc carry + dh_rec of dvae_lstm_bwd (`dc_ws`)
+//   "segment_ids"  (B)              block counts of dvae_segment_ids_sorted (`scratch`)
+//   "group_acc"    (G, D)           per-group accumulators of dvae_group_accumulate (`acc`; `cnt` is 4 * G more)
+long dvae_workspace_bytes(const char* op, long n0, long n1, long n2) {
+  const std::string s(op ? op : "");
+  if (s == "bn_stats") return 8 * (n0 * 2 * n1 + 1);
+  if (s == "bn_stat") return 4 * n0 * 4 * n1;
+  if (s == "bn_bwd_coef") return 4 * n0 * 2 * n1;
+  if (s == "loss") return 72;
+  if (s == "lstm_bwd_dc") return 4 * 2 * n2 * n0 * n1;
+  if (s == "segment_ids") return 4 * ((n0 + 1023) / 1024 > 0 ? (n0 + 1023) / 1024 : 1);
+  if (s == "group_acc") return 4 * n0 * 2 * n1;
+  return -1;
+}
 const char* dvae_last_error() { return dvae::last_error_cstr(); }
 int dvae_version() { return 100; }
 int dvae_sm_arch() { return 100; }  // built for sm_100a only

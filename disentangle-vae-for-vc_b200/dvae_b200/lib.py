@@ -97,6 +97,16 @@ _FUNCS = {n: _bind(n, a) for n, a in _SIGNATURES.items()}
 for _n in ("dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile", "dvae_lstm_launches"):
     getattr(_lib, _n).restype = C.c_int
 _lib.dvae_lstm_launches.argtypes = [C.c_int, C.c_int, C.c_int]
+_lib.dvae_workspace_bytes.restype = C.c_long
+_lib.dvae_workspace_bytes.argtypes = [C.c_char_p, C.c_long, C.c_long, C.c_long]
+
+
+def workspace_bytes(op: str, n0: int = 0, n1: int = 0, n2: int = 0) -> int:
+    """Bytes of scratch the library wants for `op` (it never allocates itself); raises for an unknown name."""
+    n = _lib.dvae_workspace_bytes(op.encode(), n0, n1, n2)
+    if n < 0:
+        raise KeyError(f"dvae_workspace_bytes: unknown op {op!r}")
+    return n
 
 
 def ptr(t):
@@ -148,4 +158,4 @@ def lstm_gate_tile(hidden: int) -> int:
 
 def exported_symbols():
     return sorted(_SIGNATURES.keys()) + ["dvae_last_error", "dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile",
-                                             "dvae_lstm_launches"]
+                                             "dvae_lstm_launches", "dvae_workspace_bytes"]

@@ -125,7 +125,7 @@ def conv5_fwd_bnstats(dt: int, x: Tensor, wk: Tensor, bias: Optional[Tensor], ha
     Cout = wk.shape[0]
     assert tuple(wk.shape) == (Cout, 5, Cin) and (R * T) % halves == 0
     y = torch.empty((R, T, Cout), device=x.device, dtype=torch.float32 if y_f32 else ad)
-    ws = torch.empty((halves * 2 * Cout + 1,), device=x.device, dtype=torch.float64)
+    ws = torch.empty((lib.workspace_bytes("bn_stats", halves, Cout) // 8,), device=x.device, dtype=torch.float64)
     call("dvae_conv5_fwd_bnstats", dt, ptr(x), ptr(wk), ptr(bias), ptr(y), _y_is_f32(dt, y), R, T, Cin, Cout, ptr(ws),
          R * T // halves, halves, stream())
     return y, ws
@@ -172,7 +172,8 @@ def lstm_bwd(dt: int, dh_all: Tensor, gates: Tensor, c_all: Tensor, whh_n: Tenso
     _chk(dh_all, ad), _chk(gates, ad), _chk(c_all, torch.float32), _chk(whh_n, ad)
     rows, T, _ = dh_all.shape
     da = torch.empty((rows, T, D * 4 * H), device=dh_all.device, dtype=ad)
-    dc = torch.empty((2, D, rows, H), device=dh_all.device, dtype=torch.float32)   # [0] dc carry, [1] dh_rec scratch
+    dc = torch.empty((lib.workspace_bytes("lstm_bwd_dc", rows, H, D) // 4,), device=dh_all.device,
+                     dtype=torch.float32)   # [2][D][rows][H]: dc carry, dh_rec scratch
     ws, tickets = _splitk_workspace(dt, rows, H, D, dh_all.device)
     call("dvae_lstm_bwd", dt, ptr(dh_all), ptr(gates), ptr(c_all), ptr(whh_n), ptr(da), ptr(dc), ptr(ws), ptr(tickets), rows, T,
          H, D, stream())
@@ -423,7 +424,7 @@ def loss_fwd(x1, x2, r1, r2, h1, h2, q1_mu, q1_lv, q2_mu, q2_lv, s_mu, s_lv, bat
     assert all(t.numel() == n for t in ts[:6])
     rows, L = q1_mu.shape
     S = s_mu.shape[1]
-    ws = torch.empty((9,), device=x1.device, dtype=torch.float64)
+    ws = torch.empty((lib.workspace_bytes("loss") // 8,), device=x1.device, dtype=torch.float64)
     out = torch.empty((8,), device=x1.device, dtype=torch.float32)
     call("dvae_loss_fwd", *[ptr(t) for t in ts[:6]], n, *[ptr(t) for t in ts[6:10]], rows, L, ptr(s_mu), ptr(s_lv), S,
          float(batch_size), float(mse_cof), float(kl_cof), ptr(ws), ptr(out), stream())

@@ -22,6 +22,10 @@ extern "C" {
 #endif
 
 const char* dvae_last_error(void);
+/* bytes of caller-provided scratch: op in {"bn_stats","bn_stat","bn_bwd_coef","loss","lstm_bwd_dc","segment_ids","group_acc"},
+ * n0..n2 = its shape parameters (see csrc/host_common.cu); -1 for an unknown name.  dvae_lstm_bwd_workspace sizes the
+ * split-K fix-up buffers of the LSTM backward. */
+long dvae_workspace_bytes(const char* op, long n0, long n1, long n2);
 int dvae_version(void);
 int dvae_sm_arch(void);              /* 100: built for sm_100a only */
 int dvae_lstm_gate_tile(int H);

@@ -41,7 +41,7 @@ def test_dropin_surface():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["bf16", "tf32"])
+@pytest.mark.parametrize("name", ["bf16", "tf32", "fp16", "fp32"])
 def test_generator_parity_gpu(name):
     from autovc_replicate.proposed_autovc import Generator
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -67,7 +67,8 @@ def test_generator_parity_gpu(name):
     osd2 = O.clone_sd(sd, requires_grad=True, device="cuda")
     _, _, o_grads = A.train_step(osd2, x, decisions=dec)
     # the postnet output re-normalises a nearly constant decoder output (see DESIGN.md Numerics): looser bound there
-    tol, hat_tol = ({"bf16": 1.5e-2, "tf32": 2e-3}[name], {"bf16": 8e-2, "tf32": 1e-2}[name])
+    tol, hat_tol = ({"bf16": 1.5e-2, "tf32": 2e-3, "fp16": 1.5e-3, "fp32": 1e-5}[name],
+                    {"bf16": 8e-2, "tf32": 1e-2, "fp16": 6e-3, "fp32": 5e-5}[name])
     e_mel = (mel - o_mel).norm().item() / o_mel.norm().item()
     e_post = (post - o_post).norm().item() / o_post.norm().item()
     assert e_mel <= tol, f"mel rel L2 {e_mel:.3e}"
@@ -82,8 +83,10 @@ def test_generator_parity_gpu(name):
         a, b = p.grad.flatten().double(), o_grads[k].flatten().double()
         worst = min(worst, (F.cosine_similarity(a, b, dim=0).item(), k))
         dot, na, nb = dot + (a * b).sum().item(), na + (a * a).sum().item(), nb + (b * b).sum().item()
-    assert worst[0] > {"bf16": 0.96, "tf32": 0.999}[name], worst
-    assert dot / (na * nb) ** 0.5 > {"bf16": 0.997, "tf32": 0.9999}[name]
+    print(f"[autovc {name}] mel rel L2 {e_mel:.2e}, mel_postnet {e_post:.2e}; gradient cosine (matched decisions) min {worst[0]:.5f} "
+          f"({worst[1]}) global {dot / (na * nb) ** 0.5:.6f}")
+    assert worst[0] > {"bf16": 0.96, "tf32": 0.999, "fp16": 0.999, "fp32": 0.99999}[name], worst
+    assert dot / (na * nb) ** 0.5 > {"bf16": 0.997, "tf32": 0.9999, "fp16": 0.9999, "fp32": 0.999999}[name]
     for k, b in g.named_buffers():
         if k.endswith("num_batches_tracked"):
             assert int(b.item()) == 1

