@@ -186,7 +186,7 @@ class Generator(nn.Module):
         W, R = saved["W"], saved["R"]
         ad = ops.act_dtype(dt)
         dev = saved["flat"].device
-        sink = GradSink(dev, E.buckets)
+        sink = GradSink(dev, E.buckets, E._sink_layout)
         if self._auto_scale:
             self._pick_grad_scale((g_mel, g_post))
         shape = (R, T_FRAMES, N_MELS)
@@ -211,6 +211,8 @@ class Generator(nn.Module):
         dh = E._lstm_bwd(W, "encoder.lstm", d_flat.view(R, T_FRAMES, 128), saved["enc_lstm"], sink, need_dx=True)
         E._conv_stack_bwd(W, dh, saved["enc_convs"], sink, 1, need_dx=False)
         E._join_side_stream()
+        if E._sink_layout is None:
+            E._sink_layout = sink.next_layout()
         return sink.finish()
 
     def forward(self, x):

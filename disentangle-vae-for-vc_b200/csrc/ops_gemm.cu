@@ -233,7 +233,9 @@ static int linear_fwd_t(const AT* x, long ldx, const AT* w, const float* bias, A
   constexpr int EB = sizeof(AT);
   constexpr int BK = 128 / EB;
   CUtensorMap ta, tb;
-  const int BN = bn_override ? bn_override : pick_bn(N);
+  int BN = bn_override ? bn_override : pick_bn(N);
+  // a long-K layer with few rows (enc_linear: 1024 x 2048 x 8192 = 64 tiles of 128 x 256) leaves most SMs idle: halve the tile
+  if (!bn_override && BN == 256 && static_cast<long>(ceil_div(M, 128)) * ceil_div(N, 256) * 10 < 6L * num_sms()) BN = 128;
   const long KW = static_cast<long>(b_terms) * K;   // row length of w
   if (int e = encode_map3(&ta, x, EB, K, M, 1, ldx * EB, (uint64_t)M * ldx * EB, BK, 128, 1)) return e;
   if (int e = encode_map3(&tb, w, EB, KW, N, 1, (uint64_t)KW * EB, (uint64_t)N * KW * EB, BK, BN, 1)) return e;

@@ -124,22 +124,48 @@ class PreparedWeights:
 
 
 class GradSink:
-    """Where parameter gradients land: private fp32 tensors, or views into the flat all-reduce buckets of
-    dvae_b200.parallel.GradBuckets (then `done()` may trigger that bucket's overlapped all-reduce)."""
+    """Where parameter gradients land: views into the flat all-reduce buckets of dvae_b200.parallel.GradBuckets (then
+    `done()` may trigger that bucket's overlapped all-reduce), or -- single process -- views into ONE flat fp32 buffer that
+    is zeroed with a single fill.  The layout of that buffer (and of the zero-initialised scratch the backward needs:
+    tap-major conv weight gradients, per-direction LSTM gradients) is learned from the first backward, which still
+    allocates tensor by tensor; every later backward does two fills instead of ~100."""
 
-    def __init__(self, device, buckets=None):
+    def __init__(self, device, buckets=None, layout: Optional[dict] = None):
         self.device = device
         self.buckets = buckets
         self.grads: Dict[str, Tensor] = {}
+        self.layout = layout
+        self.requests: List[tuple] = []          # (key, shape) in request order: what the next layout is built from
+        self._flat = {}
+        if layout is not None:
+            for kind in ("grad", "scratch"):
+                n = layout[kind]["total"]
+                if n > 0 and not (kind == "grad" and buckets is not None):
+                    self._flat[kind] = torch.zeros((n,), device=device, dtype=torch.float32)
         if buckets is not None:
             buckets.begin()
 
+    def _zeros(self, kind: str, key: str, shape) -> Tensor:
+        shape = tuple(int(d) for d in shape)
+        self.requests.append((kind, key, shape))
+        flat = self._flat.get(kind)
+        slot = self.layout[kind]["slots"].get(key) if (flat is not None) else None
+        if slot is not None and slot[1] == shape:
+            n = 1
+            for d in shape:
+                n *= d
+            return flat[slot[0]:slot[0] + n].view(shape)
+        return torch.zeros(shape, device=self.device, dtype=torch.float32)
+
     def buf(self, name: str, shape) -> Tensor:
         """Zero-initialised fp32 buffer for the gradient of `name`."""
-        t = self.buckets.view(name) if self.buckets is not None else torch.zeros(tuple(shape), device=self.device,
-                                                                               dtype=torch.float32)
+        t = self.buckets.view(name) if self.buckets is not None else self._zeros("grad", name, shape)
         self.grads[name] = t
         return t
+
+    def scratch(self, key: str, shape) -> Tensor:
+        """Zero-initialised fp32 scratch (same life time as the gradients of this backward)."""
+        return self._zeros("scratch", key, shape)
 
     def done(self, name: str) -> None:
         if self.buckets is not None:
@@ -158,6 +184,19 @@ class GradSink:
             self.buckets.finish()
         return self.grads
 
+    def next_layout(self) -> dict:
+        """Flat-buffer layout for the following backward passes: 256-byte aligned slots in request order."""
+        out = {"grad": {"slots": {}, "total": 0}, "scratch": {"slots": {}, "total": 0}}
+        for kind, key, shape in self.requests:
+            n = 1
+            for d in shape:
+                n *= d
+            L = out[kind]
+            if key not in L["slots"]:
+                L["slots"][key] = (L["total"], shape)
+                L["total"] += (n + 63) // 64 * 64
+        return out
+
 
 class Engine:
     def __init__(self, dt: int, latent_dim: int, speaker_size: int, bn_eps: float = 1e-5, bn_momentum: float = 0.1,
@@ -171,6 +210,7 @@ class Engine:
         self.y_f32 = os.environ.get("DVAE_B200_Y_F32", "1" if dt == lib.F16 else "0") == "1" and dt == lib.F16
         self.grad_stats = [] if os.environ.get("DVAE_DEBUG_GRAD_STATS") else None   # diagnostics: (name, amax) of the stream
         self.buckets = None   # set to a parallel.GradBuckets for data-parallel training
+        self._sink_layout: Optional[dict] = None   # flat gradient / scratch layout learned from the first backward (GradSink)
         self.side_stream = None     # created lazily; weight-gradient GEMMs that are off the critical path run here
         self.use_side_stream = os.environ.get("DVAE_SIDE_STREAM", "1") != "0"   # A/B switch for profiling
         self._keepalive: List[tuple] = []
@@ -362,7 +402,7 @@ class Engine:
                 dout = None
             self._keepalive.append((dy, s["x_in"]))
             with self._side_stream_ctx():
-                dwk = torch.zeros(wk.shape, device=wk.device, dtype=torch.float32)
+                dwk = sink.scratch("dwk:" + s["conv"], wk.shape)
                 ops.conv5_wgrad(dt, dy, s["x_in"], dwk, alpha=1.0 / self.grad_scale)
                 ops.conv_wgrad_unpack(dwk, out=sink.buf(s["conv"] + ".weight", (Co, Ci, 5)))
                 self._keepalive.append((dwk,))
@@ -417,11 +457,11 @@ class Engine:
             ops.copy_f32(db, sink.buf(f"{prefix}.bias_hh_l{l}", (4 * H,)))   # b_ih and b_hh: equal gradients
             sink.done(f"{prefix}.bias_hh_l{l}")
         else:        # both directions come out of one GEMM; slice per direction
-            dwih = torch.zeros((D * 4 * H, In), device=da.device, dtype=torch.float32)
+            dwih = sink.scratch(f"dwih:{prefix}.{l}", (D * 4 * H, In))
             ops.linear_wgrad(dt, da2, x2, dwih, alpha=inv)
-            dwhh = torch.zeros((D, 4 * H, H), device=da.device, dtype=torch.float32)
+            dwhh = sink.scratch(f"dwhh:{prefix}.{l}", (D, 4 * H, H))
             ops.lstm_wgrad_hh(dt, da, s["h_all"], dwhh, H, D, alpha=inv)
-            db = torch.zeros((D * 4 * H,), device=da.device, dtype=torch.float32)
+            db = sink.scratch(f"db:{prefix}.{l}", (D * 4 * H,))
             ops.colsum(dt, da2, db, alpha=inv)
             for d in range(D):
                 suf = "_reverse" if d == 1 else ""
@@ -452,7 +492,7 @@ class Engine:
         R = saved["R"]
         R2 = 2 * R
         dev = saved["heads"].device
-        sink = GradSink(dev, self.buckets)
+        sink = GradSink(dev, self.buckets, self._sink_layout)
         grads = sink   # the helpers below take the sink
         g = [t.contiguous() if t is not None else None for t in gouts]
         # ---- residual output: recon_hat = recon + postnet(recon)  (:277-278)
@@ -481,9 +521,9 @@ class Engine:
         self._stat("dheads", dheads)
         # ---- encoder heads + linear
         n_s = W.n_style
-        dw = torch.zeros(W.heads_w.shape, device=dev, dtype=torch.float32)
+        dw = sink.scratch("dw:heads", W.heads_w.shape)
         ops.linear_wgrad(dt, dheads, saved["e"], dw, alpha=1.0 / gs)
-        db = torch.zeros((W.heads_w.shape[0],), device=dev, dtype=torch.float32)
+        db = sink.scratch("db:heads", (W.heads_w.shape[0],))
         ops.colsum(dt, dheads, db, alpha=1.0 / gs)
         sink.put("style.linear_layer.weight", dw[:n_s]), sink.put("content.linear_layer.weight", dw[n_s:])
         sink.put("style.linear_layer.bias", db[:n_s]), sink.put("content.linear_layer.bias", db[n_s:])
@@ -492,4 +532,6 @@ class Engine:
         dh = self._lstm_bwd(W, "enc_lstm", d_flat.view(R2, T_FRAMES, 128), saved["enc_lstm"], grads, need_dx=True)
         self._conv_stack_bwd(W, dh, saved["enc_convs"], grads, 2, need_dx=False)
         self._join_side_stream()
+        if self._sink_layout is None:
+            self._sink_layout = sink.next_layout()
         return sink.finish()

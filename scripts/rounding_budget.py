@@ -1,5 +1,19 @@
-import sys, torch, torch.nn.functional as F
-sys.path.insert(0,'/root/repo')
+"""Rounding budget of a 16-bit storage pipeline (CPU, fp64 emulation; no GPU needed): the network's forward is evaluated in
+fp64 twice -- exactly, and with a rounding to fp16 inserted at chosen SITES (the places where the dvae_b200 engine stores a
+16-bit tensor or reads a 16-bit weight) -- and the relative L2 error of the outputs is printed per site, per group, and for
+the combinations that were candidates for removal.  This is what decided the fp16 mode's design (DESIGN.md "Numerics"):
+  x   input mel            wE/wD/wP  conv + LSTM weights (encoder / decoder / postnet)     w2  the small linears' weights
+  yE/yD/yP  pre-BatchNorm convolution outputs      aE/aD/aP  BatchNorm+activation outputs   xgE/xgD  LSTM x-projections
+  hE/hD  LSTM h per step    e  enc_linear output    z, d  decoder entry    rec  decoder output fed to the postnet
+usage: python scripts/rounding_budget.py [rows_per_call=8]      (output of the run that drove the design:
+profiles/r02_rounding_budget.txt)"""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import dvae_oracle as O
 torch.set_num_threads(8)
 R=int(sys.argv[1]) if len(sys.argv)>1 else 8

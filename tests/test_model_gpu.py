@@ -289,10 +289,14 @@ def test_pipelined_epoch_equals_step_loop():
     from oracle import dvae_oracle as O
     ds = _PairDataset(12)
     loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False, pin_memory=True)
-    noise = [torch.randn(4, 28, device="cuda"), torch.randn(4, 28, device="cuda"), torch.randn(4, 4, device="cuda")]
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    noise = [torch.randn(4, 28, device="cuda", generator=gen), torch.randn(4, 28, device="cuda", generator=gen),
+             torch.randn(4, 4, device="cuda", generator=gen)]
     results = []
     for mode in ("pipelined", "blocking"):
-        w = _build("bf16", 4, O.synth_state_dict(0))
+        # strict fp32 mode: its weight gradients are accumulated without atomics, so the two runs differ only by what the
+        # host-side pipelining could get wrong (the 16-bit modes add run-to-run noise that Adam's sign-like first steps amplify)
+        w = _build("fp32", 4, O.synth_state_dict(0))
         k = [0]
 
         def hook(shape):
@@ -310,12 +314,10 @@ def test_pipelined_epoch_equals_step_loop():
                 last = vals[7]
             out = (tot[1], tot[2], tot[3], tot[4], tot[5], tot[6], last)
         results.append((out, w.model.dec_linear2.linear_layer.weight.detach().clone()))
-    # not bit-equal run to run: the split-K weight-gradient reductions add in arrival order, and Adam amplifies the last
-    # bits of near-zero gradients (three steps of at most lr = 1e-4 each)
-    # (since the forward of step k really sees the weights written by step k-1, the three-step trajectories of the two runs
-    # separate by the run-to-run noise of the weight gradients: ~3e-3 on the small KL terms)
+    # not bit-equal run to run even so: a few reductions (bias column sums, BatchNorm statistics) add atomically in arrival
+    # order, and Adam amplifies the last bits of near-zero gradients (three steps of at most lr = 1e-4 each)
     for a, b in zip(results[0][0], results[1][0]):
-        assert abs(a - b) <= 1e-2 * max(1.0, abs(b)), (a, b)
+        assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (a, b)
     assert (results[0][1] - results[1][1]).abs().max().item() <= 6.1e-4
     assert (results[0][1] - results[1][1]).abs().mean().item() <= 5e-5
 
