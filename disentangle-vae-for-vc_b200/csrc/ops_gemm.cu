@@ -945,10 +945,10 @@ static int conv5_fwd_bnstats_t(int dtype, const void* x, const void* wk, const f
   bool fused = false;
   int e;
   if (y_f32) {
-    if constexpr (std::is_same<AT, __half>::value) {   // only the fp16 mode keeps y in fp32 (tf32 storage is fp32 already)
+    if constexpr (std::is_same<AT, __half>::value || std::is_same<AT, tf32_t>::value) {   // fp16: fp32 storage; tf32: no rounding
       e = conv5_fwd_t<AT, float>((const AT*)x, (const AT*)wk, bias, (float*)y, nullptr, R, T, Cin, Cout, false, st, bn_ws, rows_half, &fused);
     } else {
-      set_last_error("fp32 convolution output is implemented for the fp16 activation dtype only");
+      set_last_error("unrounded fp32 convolution output is implemented for the fp16 and tf32 activation dtypes");
       return 1;
     }
   } else e = conv5_fwd_t<AT>((const AT*)x, (const AT*)wk, bias, (AT*)y, nullptr, R, T, Cin, Cout, false, st, bn_ws, rows_half, &fused);

@@ -90,9 +90,18 @@ struct epi_is_staged { static constexpr bool value = false; };
 template <class Epi>
 struct epi_is_staged<Epi, decltype((void)Epi::kStaged)> { static constexpr bool value = Epi::kStaged; };
 
+// staged epilogues may drain a tile in several ROUNDS through a staging buffer that holds 1 / rounds of it (persistent
+// kernel only): `static constexpr int rounds<BLOCK_N>()`; default 1
+template <class Epi, int BLOCK_N, class = void>
+struct epi_rounds { static constexpr int value = 1; };
+template <class Epi, int BLOCK_N>
+struct epi_rounds<Epi, BLOCK_N, decltype((void)Epi::template rounds<BLOCK_N>())> {
+  static constexpr int value = Epi::template rounds<BLOCK_N>();
+};
+
 template <class Epi, int BLOCK_N>
 __host__ __device__ constexpr int persistent_staging_bytes() {
-  if constexpr (epi_is_staged<Epi>::value) return Epi::template staging_bytes<BLOCK_N>();
+  if constexpr (epi_is_staged<Epi>::value) return Epi::template staging_bytes<BLOCK_N>() / epi_rounds<Epi, BLOCK_N>::value;
   else return 0;
 }
 
@@ -601,21 +610,49 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         // the store of tile i drains while the main loop of tile i+1 runs, and is only waited for when the staging
         // buffer is needed again.
         const uint32_t stage = smem_base + RING;
-        if (local > 0) {
-          if (threadIdx.x == 64) ptx::bulk_wait_read<0>();
-          asm volatile("bar.sync 2, 256;" ::: "memory");
+        constexpr int ROUNDS = epi_rounds<Epi, BLOCK_N>::value;
+        if constexpr (ROUNDS == 1) {
+          if (local > 0) {
+            if (threadIdx.x == 64) ptx::bulk_wait_read<0>();
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+          }
+          Epi::template run_staged<BLOCK_N>(ep, acc, regs, q * 32 + lane, m, n0, zb, col0, col1, shp, stage);
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_acc(as);
+          ptx::fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (threadIdx.x == 64) {
+            Epi::template flush<BLOCK_N>(ep, stage, tm, tn, zb, shp);
+            ptx::bulk_commit();
+          }
+          Epi::template after_stage<BLOCK_N>(ep, stage, static_cast<int>(threadIdx.x) - 64, tm, tn, zb, shp);   // reads the staged tile
+        } else {
+          // Wide (fp32) output tiles: the staging buffer holds BLOCK_N / ROUNDS columns, so the ring keeps its depth.  The
+          // epilogue has the whole main loop of the next tile to hide in, so draining in rounds costs nothing.
+          constexpr int RN = BLOCK_N / ROUNDS;
+#pragma unroll 1
+          for (int r = 0; r < ROUNDS; ++r) {
+            if (local > 0 || r > 0) {
+              if (threadIdx.x == 64) ptx::bulk_wait_read<0>();
+              asm volatile("bar.sync 2, 256;" ::: "memory");
+            }
+            const int c0 = r * RN + half * (RN / 2);
+            Epi::template run_staged_r<BLOCK_N>(ep, acc, regs, q * 32 + lane, m, n0, zb, c0, c0 + RN / 2, shp, stage, r * RN);
+            if (r == ROUNDS - 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) release_acc(as);
+            }
+            ptx::fence_proxy_async_smem();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (threadIdx.x == 64) {
+              Epi::template flush_r<BLOCK_N>(ep, stage, tm, tn, zb, shp, r * RN, RN);
+              ptx::bulk_commit();
+            }
+            Epi::template after_stage_r<BLOCK_N>(ep, stage, static_cast<int>(threadIdx.x) - 64, tm, tn, zb, shp, r * RN, RN);
+          }
         }
-        Epi::template run_staged<BLOCK_N>(ep, acc, regs, q * 32 + lane, m, n0, zb, col0, col1, shp, stage);
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) release_acc(as);
-        ptx::fence_proxy_async_smem();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (threadIdx.x == 64) {
-          Epi::template flush<BLOCK_N>(ep, stage, tm, tn, zb, shp);
-          ptx::bulk_commit();
-        }
-        Epi::template after_stage<BLOCK_N>(ep, stage, static_cast<int>(threadIdx.x) - 64, tm, tn, zb, shp);   // reads the staged tile
       } else {
         Epi::template run<BLOCK_N>(ep, acc, regs, m, n0, zb, col0, col1, shp);
         ptx::tc_fence_before();
@@ -831,12 +868,21 @@ struct EpiStoreTma {
   };
   template <int BLOCK_N>
   static __host__ __device__ constexpr int staging_bytes() { return BLOCK_N * EB * kBlockM; }
+  // persistent kernel: 32-bit outputs of the widest tile (128 KB) are drained in two rounds of 128 columns (64 KB staging)
+  template <int BLOCK_N>
+  static __host__ __device__ constexpr int rounds() { return (EB == 4 && BLOCK_N == 256) ? 2 : 1; }
   // After the tile is staged (and its TMA store issued) every epilogue thread sums one column of the staged tile: the
   // statistics pass of the BatchNorm that follows costs no extra read of the activation tensor.  Column c of row r lives
   // in box c*EB/128 at chunk ((c*EB%128)/16) ^ (r&7): the 32 lanes of a warp read 32 consecutive columns of one row.
   template <int BLOCK_N>
-  static __device__ __forceinline__ void after_stage(const Params& p, uint32_t stage, int et, int tile_m, int tile_n, int,
+  static __device__ __forceinline__ void after_stage(const Params& p, uint32_t stage, int et, int tile_m, int tile_n, int zb,
                                                      const GemmShape& shp) {
+    after_stage_r<BLOCK_N>(p, stage, et, tile_m, tile_n, zb, shp, 0, BLOCK_N);
+  }
+  // the staged columns are [col_base, col_base + ncols) of the tile (one round)
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void after_stage_r(const Params& p, uint32_t stage, int et, int tile_m, int tile_n, int,
+                                                       const GemmShape& shp, int col_base, int ncols) {
     if (p.stat_sums == nullptr) return;
     constexpr int CPT = BLOCK_N / kEpilogueThreads;          // columns per thread (1 for BLOCK_N = 256)
     const int m0 = tile_m * kBlockM;
@@ -844,9 +890,9 @@ struct EpiStoreTma {
     const int half = m0 / p.rows_half;
 #pragma unroll
     for (int cc = 0; cc < (CPT > 0 ? CPT : 1); ++cc) {
-      const int c = (CPT > 0) ? et * CPT + cc : et;
-      if (c >= BLOCK_N) return;
-      const int n = tile_n * BLOCK_N + c;
+      const int c = (CPT > 0) ? et * CPT + cc : et;          // column inside the staged round
+      if (c >= ncols) return;
+      const int n = tile_n * BLOCK_N + col_base + c;
       if (n >= shp.N) continue;
       const int byte = c * EB;
       const uint32_t base = stage + static_cast<uint32_t>((byte >> 7) * (kBlockM * 128) + (byte & 15));
@@ -875,9 +921,16 @@ struct EpiStoreTma {
   template <int BLOCK_N>
   static __device__ __forceinline__ void preload(const Params&, Regs<BLOCK_N>&, int, int, int, int, int, const GemmShape&) {}
   template <int BLOCK_N>
-  static __device__ __forceinline__ void run_staged(const Params& p, const AccSource& acc, const Regs<BLOCK_N>&, int row, int m,
+  static __device__ __forceinline__ void run_staged(const Params& p, const AccSource& acc, const Regs<BLOCK_N>& regs, int row, int m,
                                                     int n0, int zb, int col0, int col1, const GemmShape& shp,
                                                     uint32_t stage) {
+    run_staged_r<BLOCK_N>(p, acc, regs, row, m, n0, zb, col0, col1, shp, stage, 0);
+  }
+  // columns [col0, col1) of the tile go to staging column (c - col_base)
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run_staged_r(const Params& p, const AccSource& acc, const Regs<BLOCK_N>&, int row, int m,
+                                                      int n0, int zb, int col0, int col1, const GemmShape& shp,
+                                                      uint32_t stage, int col_base) {
 #pragma unroll 1
     for (int c = col0; c < col1; c += 32) {
       if (n0 + c >= shp.N) break;
@@ -905,7 +958,7 @@ struct EpiStoreTma {
 #pragma unroll
       for (int j = 0; j < 32 * EB / 16; ++j) {
         const uint4 u = pack_chunk<OutT>(v + (16 / EB) * j);
-        const int byte = c * EB + 16 * j;
+        const int byte = (c - col_base) * EB + 16 * j;
         ptx::st_shared_v4(stage + static_cast<uint32_t>((byte >> 7) * (kBlockM * 128) + row * 128 +
                                                         ((((byte & 127) >> 4) ^ (row & 7)) << 4)),
                           u);
@@ -915,11 +968,17 @@ struct EpiStoreTma {
   template <int BLOCK_N>
   static __device__ __forceinline__ void flush(const Params& p, uint32_t stage, int tile_m, int tile_n, int zb,
                                                const GemmShape& shp) {
+    flush_r<BLOCK_N>(p, stage, tile_m, tile_n, zb, shp, 0, BLOCK_N);
+  }
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void flush_r(const Params& p, uint32_t stage, int tile_m, int tile_n, int zb,
+                                                 const GemmShape& shp, int col_base, int ncols) {
     constexpr int GE = 128 / EB;
 #pragma unroll 1
-    for (int b = 0; b < BLOCK_N / GE; ++b) {
-      if (tile_n * BLOCK_N + b * GE >= shp.N) break;
-      ptx::tma_store_3d(&p.tm_out, stage + b * (kBlockM * 128), tile_n * BLOCK_N + b * GE, tile_m * kBlockM, zb);
+    for (int b = 0; b < ncols / GE; ++b) {
+      const int n = tile_n * BLOCK_N + col_base + b * GE;
+      if (n >= shp.N) break;
+      ptx::tma_store_3d(&p.tm_out, stage + b * (kBlockM * 128), n, tile_m * kBlockM, zb);
     }
   }
 };

@@ -205,9 +205,10 @@ class Engine:
         # every parameter gradient is multiplied by 1 / grad_scale where it is produced.  1.0 for bf16 / tf32 storage
         # (fp32's exponent range); the fp16 mode needs it to keep small gradients inside fp16's normal range.
         self.grad_scale = float(grad_scale)
-        # fp16 mode: the convolution outputs that feed a train-mode BatchNorm are kept as unrounded fp32 (the rounding of that
-        # tensor is the largest single term of the forward error budget, scripts/rounding_budget.py); DVAE_B200_Y_F32=0/1 overrides
-        self.y_f32 = os.environ.get("DVAE_B200_Y_F32", "1" if dt == lib.F16 else "0") == "1" and dt == lib.F16
+        # fp16 / tf32 modes: the convolution outputs that feed a train-mode BatchNorm are kept as unrounded fp32 (the rounding
+        # of that tensor is the largest single term of the forward error budget, scripts/rounding_budget.py; it feeds
+        # BatchNorm, not a tensor-core operand, so nothing requires the narrow grid); DVAE_B200_Y_F32=0 switches it off
+        self.y_f32 = os.environ.get("DVAE_B200_Y_F32", "1") == "1" and dt in (lib.F16, lib.TF32)
         self.grad_stats = [] if os.environ.get("DVAE_DEBUG_GRAD_STATS") else None   # diagnostics: (name, amax) of the stream
         self.buckets = None   # set to a parallel.GradBuckets for data-parallel training
         self._sink_layout: Optional[dict] = None   # flat gradient / scratch layout learned from the first backward (GradSink)

@@ -118,7 +118,8 @@ def _y_is_f32(dt: int, y: Tensor) -> int:
 def conv5_fwd_bnstats(dt: int, x: Tensor, wk: Tensor, bias: Optional[Tensor], halves: int, y_f32: bool = False):
     """conv5_fwd + the statistics pass of the train-mode BatchNorm behind it.  Returns (y, ws): ws holds the per-half
     column sums / sums of squares of y (double [halves*2*Cout + 1]) for `bn_finalize_apply`.  y_f32: store y as
-    unrounded fp32 (fp16 activation dtype only)."""
+    unrounded fp32 (fp16 mode: fp32 instead of fp16 storage; tf32 mode: the fp32 storage is not rounded to the tf32 grid --
+    y feeds BatchNorm, not a tensor-core operand)."""
     ad = act_dtype(dt)
     _chk(x, ad), _chk(wk, ad)
     R, T, Cin = x.shape
@@ -126,7 +127,7 @@ def conv5_fwd_bnstats(dt: int, x: Tensor, wk: Tensor, bias: Optional[Tensor], ha
     assert tuple(wk.shape) == (Cout, 5, Cin) and (R * T) % halves == 0
     y = torch.empty((R, T, Cout), device=x.device, dtype=torch.float32 if y_f32 else ad)
     ws = torch.empty((lib.workspace_bytes("bn_stats", halves, Cout) // 8,), device=x.device, dtype=torch.float64)
-    call("dvae_conv5_fwd_bnstats", dt, ptr(x), ptr(wk), ptr(bias), ptr(y), _y_is_f32(dt, y), R, T, Cin, Cout, ptr(ws),
+    call("dvae_conv5_fwd_bnstats", dt, ptr(x), ptr(wk), ptr(bias), ptr(y), int(bool(y_f32)), R, T, Cin, Cout, ptr(ws),
          R * T // halves, halves, stream())
     return y, ws
 

@@ -52,8 +52,9 @@ int dvae_conv5_fwd(int dtype, const void* x, const void* wk, const float* bias, 
                    int Cout, void* stream);
 /* conv + the statistics pass of the train-mode BatchNorm1d behind it (:154-160, :178-189, :54-78): bn_ws [halves*2*Cout + 1]
  * doubles = per-half column sums / sums of squares of y; consumed by dvae_bn_finalize_apply.
- * y_f32 != 0 (fp16 activations only): y is stored as UNROUNDED fp32 -- the rounding of the pre-BatchNorm tensor is the
- * largest single contribution to the forward error of a 16-bit pipeline; the BatchNorm entry points take the same flag */
+ * y_f32 != 0 (fp16 / tf32 activations): y is stored as UNROUNDED fp32 -- the rounding of the pre-BatchNorm tensor is the
+ * largest single contribution to the forward error; the BatchNorm entry points take a flag for the fp16 case (y wider
+ * than the activations) */
 int dvae_conv5_fwd_bnstats(int dtype, const void* x, const void* wk, const float* bias, void* y, int y_f32, int R, int T, int Cin,
                            int Cout, double* bn_ws, int rows_half, int halves, void* stream);
 int dvae_conv5_dgrad(int dtype, const void* dy, const void* wk, void* dx, float* dx_f32, int R, int T, int Cin, int Cout,

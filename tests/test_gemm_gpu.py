@@ -129,7 +129,7 @@ def test_conv5(name, R, Cin, Cout, mt):
     assert (dwk - ref_dw).abs().max().item() <= 2e-5 * ref_dw.abs().max().item() + 1e-5
 
 
-@pytest.mark.parametrize("name,y_f32", [("bf16", False), ("tf32", False), ("fp16", False), ("fp16", True), ("fp32", False)])
+@pytest.mark.parametrize("name,y_f32", [("bf16", False), ("tf32", False), ("tf32", True), ("fp16", False), ("fp16", True), ("fp32", False)])
 @pytest.mark.parametrize("R,Cin,Cout,act", [(4, 80, 512, "relu"), (16, 512, 512, "tanh"), (32, 512, 512, "relu"), (6, 512, 80, "none")])
 def test_conv5_bnstats_and_bn_apply(name, y_f32, R, Cin, Cout, act, mt):
     """The training path of every Conv1d + BatchNorm1d (+ activation) pair: `conv5_fwd_bnstats` (BatchNorm statistics fused
