@@ -50,7 +50,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DVAE_B200_PRECISION", "fp16"), choices=["fp16", "bf16", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("DVAE_B200_PRECISION", "fp16"), choices=["fp16", "bf16", "tf32", "fp32"],
+                    help="activation storage / MMA mode; fp32 = the strict checking mode on the CUDA cores (use with --lean)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5], help="BASELINE config: 2 training step (3 at N > 1), "
                     "4 many-to-many conversion, 5 AutoVC generator fwd+bwd")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
@@ -201,7 +202,7 @@ def tensor_rooflines(args, dev, R, peaks):
     > L2 operand sets.  Returns (headline roofline dict, list of the others)."""
     import torch
     from dvae_b200 import lib, ops
-    dt = {"bf16": lib.BF16, "fp16": lib.F16, "tf32": lib.TF32}[args.precision]
+    dt = {"bf16": lib.BF16, "fp16": lib.F16, "tf32": lib.TF32, "fp32": lib.F32}[args.precision]
     ad = ops.act_dtype(dt)
     scale = 0.5 if args.precision == "tf32" else 1.0
     peak_tf = peaks.get("bf16_tflops", 1590.0) * scale

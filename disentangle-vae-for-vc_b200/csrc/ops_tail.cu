@@ -306,13 +306,25 @@ __global__ void group_accumulate_kernel(const float* __restrict__ a, const float
     float n = 0.f;
     int cur = -1;
     bool single = true;  // the whole chunk is one run
+    // all loads of the chunk first (16 independent 16-byte loads per lane in flight): the kernel is a pure HBM stream
+    float4 ua[kGroupChunk], va[kGroupChunk];
+    int ga[kGroupChunk];
 #pragma unroll
     for (int k = 0; k < kGroupChunk; ++k) {
       const long r = r0 + k;
       if (r < B) {
-        const int g = gid[r];
-        float4 u = reinterpret_cast<const float4*>(a + r * D)[c];
-        float4 v = reinterpret_cast<const float4*>(b + r * D)[c];
+        ga[k] = __ldg(gid + r);
+        ua[k] = __ldg(reinterpret_cast<const float4*>(a + r * D) + c);
+        va[k] = __ldg(reinterpret_cast<const float4*>(b + r * D) + c);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kGroupChunk; ++k) {
+      const long r = r0 + k;
+      if (r < B) {
+        const int g = ga[k];
+        float4 u = ua[k];
+        float4 v = va[k];
         if (mode == kModePoG) {
           float4 var = make_float4(expf(v.x), expf(v.y), expf(v.z), expf(v.w));
           var.x = var.x == 0.f ? 1e-6f : var.x; var.y = var.y == 0.f ? 1e-6f : var.y;
