@@ -570,6 +570,8 @@ static int conv5_wgrad_t(const AT* dy, const AT* x, float* dwk, int R, int T, in
   }
   GemmShape shp{Cout, Cin, num_kb, kpt, splits};
   shp.f16 = kIsF16<AT>;
+  static const int tap_fast = env_int("DVAE_WGRAD_TAP_FAST", 1);
+  shp.batches = tap_fast ? 5 : 0;   // persistent kernel: the 5 taps of a K-slab run side by side (L2 reuse of dy and x)
   EpiAtomic::Params ep{dwk, (long)5 * Cin, (long)Cin, alpha};
   dim3 grid(ceil_div(Cout, 128), ceil_div(Cin, BN), 5 * shp.splits);
   if (wide && gemm_pair(grid.x, BN)) return launch_gemm_persistent<256, true, true, EB, EpiAtomic, 2>(ta, tb, wa, wb, shp, ep, grid, st);

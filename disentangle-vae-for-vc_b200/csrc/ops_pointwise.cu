@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const AT* __restrict
                                                             const float* __restrict__ stat, double* __restrict__ sums,
                                                             int rows_half, int C, int act, int rb) {
   __shared__ float red[kBnLanes * 2 * kBnSlab];
+  constexpr int UNROLL = kBnUnroll;   // (halving it for a 32-bit y, as bn_bwd_apply_kernel does, measured slower here: 46.9 vs 41.9 us)
   const int rl = threadIdx.x >> 3, cg = threadIdx.x & 7;
   const int c_slab = blockIdx.x * kBnSlab, c0 = c_slab + cg * 8;
   const long row0 = static_cast<long>(blockIdx.y) * rb;
@@ -452,18 +453,18 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const AT* __restrict
     }
     const YT* ys = y + row0 * C + c0;
     const AT* dsrc = dout + row0 * C + c0;
-    for (int r = rl; r < rb; r += kBnLanes * kBnUnroll) {
-      typename Act8<YT>::raw_t ry[kBnUnroll];
-      typename Act8<AT>::raw_t rd[kBnUnroll];
+    for (int r = rl; r < rb; r += kBnLanes * UNROLL) {
+      typename Act8<YT>::raw_t ry[UNROLL];
+      typename Act8<AT>::raw_t rd[UNROLL];
 #pragma unroll
-      for (int u = 0; u < kBnUnroll; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         if (r + u * kBnLanes < rb) {
           ry[u] = Act8<YT>::load_raw(ys + static_cast<long>(r + u * kBnLanes) * C);
           rd[u] = Act8<AT>::load_raw(dsrc + static_cast<long>(r + u * kBnLanes) * C);
         }
       }
 #pragma unroll
-      for (int u = 0; u < kBnUnroll; ++u) {
+      for (int u = 0; u < UNROLL; ++u) {
         if (r + u * kBnLanes < rb) {
           float v[8], d[8];
           Act8<YT>::unpack(ry[u], v);
@@ -501,6 +502,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const AT* __restrict_
                                                            const float* __restrict__ stat, const float* __restrict__ coef,
                                                            AT* __restrict__ dy, long rows, int rows_half, int C, int act,
                                                            int rb) {
+  // a 32-bit y doubles the bytes (and registers) in flight per row: half the unroll keeps the occupancy
+  constexpr int UNROLL = sizeof(YT) == 4 ? kBnUnroll / 2 : kBnUnroll;
   const int rl = threadIdx.x >> 3, cg = threadIdx.x & 7;
   const int c0 = blockIdx.x * kBnSlab + cg * 8;
   if (c0 >= C) return;
@@ -520,18 +523,18 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const AT* __restrict_
   const YT* ys = y + row0 * C + c0;
   const AT* dsrc = dout + row0 * C + c0;
   AT* dst = dy + row0 * C + c0;
-  for (int r = rl; r < nr; r += kBnLanes * kBnUnroll) {
-    typename Act8<YT>::raw_t ry[kBnUnroll];
-    typename Act8<AT>::raw_t rd[kBnUnroll];
+  for (int r = rl; r < nr; r += kBnLanes * UNROLL) {
+    typename Act8<YT>::raw_t ry[UNROLL];
+    typename Act8<AT>::raw_t rd[UNROLL];
 #pragma unroll
-    for (int u = 0; u < kBnUnroll; ++u) {
+    for (int u = 0; u < UNROLL; ++u) {
       if (r + u * kBnLanes < nr) {
         ry[u] = Act8<YT>::load_raw(ys + static_cast<long>(r + u * kBnLanes) * C);
         rd[u] = Act8<AT>::load_raw(dsrc + static_cast<long>(r + u * kBnLanes) * C);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kBnUnroll; ++u) {
+    for (int u = 0; u < UNROLL; ++u) {
       if (r + u * kBnLanes < nr) {
         float v[8], d[8];
         Act8<YT>::unpack(ry[u], v);

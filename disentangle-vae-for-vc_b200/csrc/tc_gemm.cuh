@@ -46,6 +46,10 @@ struct GemmShape {
   float* splitk_ws;  // fix-up workspace [tiles][splits][128][BLOCK_N] fp32 (epilogues with kFixup, splits > 1)
   int* tickets;      // [tiles] arrival counters, zero before first use, self-resetting
   int f16;           // 16-bit operands are IEEE fp16 rather than bf16 (same kernel, other a_format / b_format bits)
+  int batches;       // persistent kernel, > 0: work items are ordered with the BATCH index fastest inside a split (z = split *
+                     // batches + batch) instead of the split fastest.  Conv weight gradients: the batch is the filter tap, and
+                     // the five taps of a K-slab read the same rows of dy and (shifted by a frame) of x -- running them side by
+                     // side keeps that slab in L2 instead of re-reading both tensors from HBM once per tap
 };
 // instruction descriptor of this launch: the template's bf16 descriptor with the two format fields cleared for fp16
 __device__ __forceinline__ uint32_t runtime_idesc(uint32_t idesc, const GemmShape& shp) {
@@ -482,8 +486,13 @@ tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const int rest = item / items_m;
     tn = rest % tiles_n;
     const int zz = rest / tiles_n;
-    zb = zz / shp.splits;
-    split = zz - zb * shp.splits;
+    if (shp.batches > 0) {
+      split = zz / shp.batches;
+      zb = zz - split * shp.batches;
+    } else {
+      zb = zz / shp.splits;
+      split = zz - zb * shp.splits;
+    }
   };
 
   if (warp == 0) {
