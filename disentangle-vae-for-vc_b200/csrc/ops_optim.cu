@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(kAdamThreads)
 adam_multi_kernel(float* const* __restrict__ ps, const float* const* __restrict__ gs, float* const* __restrict__ ms,
                   float* const* __restrict__ vs, const long* __restrict__ sizes, const int* __restrict__ blk_tensor,
                   const long* __restrict__ blk_off, int chunk, float w1, float beta2, float w2, float eps, float step_size,
-                  float inv_bc2_sqrt) {
+                  float inv_bc2_sqrt, int* __restrict__ found_inf) {
   const int t = blk_tensor[blockIdx.x];
   const long off = blk_off[blockIdx.x];
   const long n = min(static_cast<long>(chunk), sizes[t] - off);
@@ -30,7 +30,12 @@ adam_multi_kernel(float* const* __restrict__ ps, const float* const* __restrict_
   const float* __restrict__ g = gs[t] + off;
   float* __restrict__ m = ms[t] + off;
   float* __restrict__ v = vs[t] + off;
+  // An element whose gradient is not finite is left untouched (p, m, v) and reported through found_inf: the fp16 mode
+  // carries gradients scaled into a 16-bit range, and an overflow there must not poison the weights (torch.optim.Adam
+  // would write NaN; a GradScaler would skip the step -- the caller lowers the scale when the flag comes back).
+  bool bad = false;
   auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+    if (!isfinite(gg)) { bad = true; return; }
     mm = mm + w1 * (gg - mm);
     vv = vv * beta2 + w2 * gg * gg;
     const float denom = sqrtf(vv) * inv_bc2_sqrt + eps;
@@ -70,6 +75,7 @@ adam_multi_kernel(float* const* __restrict__ ps, const float* const* __restrict_
       p[i] = pp; m[i] = mm; v[i] = vv;
     }
   }
+  if (bad && found_inf != nullptr) atomicOr(found_inf, 1);
 }
 
 }  // namespace dvae
@@ -78,9 +84,10 @@ extern "C" {
 
 // One Adam step for every tensor in the tables (all arrays are DEVICE memory; `step` is the 1-based step count the bias
 // corrections use).  blk_tensor / blk_off: for each block, which tensor and which element offset its chunk starts at.
+// found_inf (device int, may be null): set to 1 when a gradient element was not finite; such elements are skipped.
 int dvae_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                    const long* sizes, const int* blk_tensor, const long* blk_off, int num_blocks, int chunk, double lr,
-                   double beta1, double beta2, double eps, long step, void* stream) {
+                   double beta1, double beta2, double eps, long step, int* found_inf, void* stream) {
   using namespace dvae;
   DVAE_REQUIRE(chunk > 0 && chunk % 4 == 0, "chunk must be a positive multiple of 4");
   DVAE_REQUIRE(step >= 1, "step counts from 1");
@@ -93,7 +100,7 @@ int dvae_adam_step(float* const* params, const float* const* grads, float* const
   const float inv_bc2_sqrt = static_cast<float>(1.0 / sqrt(bc2));
   adam_multi_kernel<<<num_blocks, kAdamThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       params, grads, exp_avg, exp_avg_sq, sizes, blk_tensor, blk_off, chunk, static_cast<float>(1.0 - beta1),
-      static_cast<float>(beta2), static_cast<float>(1.0 - beta2), static_cast<float>(eps), step_size, inv_bc2_sqrt);
+      static_cast<float>(beta2), static_cast<float>(1.0 - beta2), static_cast<float>(eps), step_size, inv_bc2_sqrt, found_inf);
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

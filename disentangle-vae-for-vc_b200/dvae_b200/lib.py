@@ -76,7 +76,7 @@ _SIGNATURES = {
     "dvae_group_pog_bwd": [_p] * 7 + [_l, _i, _p],
     "dvae_group_reparam": [_p] * 5 + [_l, _i, _p],
     # optimizer
-    "dvae_adam_step": [_p] * 7 + [_i, _i, _d, _d, _d, _d, _l, _p],
+    "dvae_adam_step": [_p] * 7 + [_i, _i, _d, _d, _d, _d, _l, _p, _p],
 }
 _OPTIONAL = {}
 

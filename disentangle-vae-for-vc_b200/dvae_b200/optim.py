@@ -26,6 +26,27 @@ class Adam(torch.optim.Adam):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad)
         self._tables = {}     # per param group: device pointer / size / block tables
         self._grad_ptrs = {}  # per param group: the gradient addresses uploaded last
+        # Non-finite gradients: the kernel leaves such elements untouched and raises a device flag, which is read back one
+        # step late (pinned buffer + event: no host sync in the step).  `overflow_hook()` is then called -- the fp16 drop-in
+        # model halves its gradient scale there -- and `overflow_steps` counts the occurrences.
+        self.overflow_hook = None
+        self.overflow_steps = 0
+        self._inf_flag = None
+        self._inf_host = None
+        self._inf_event = None
+
+    def _check_overflow(self, device):
+        if self._inf_flag is None:
+            self._inf_flag = torch.zeros(1, dtype=torch.int32, device=device)
+            self._inf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._inf_event = torch.cuda.Event()
+            return
+        self._inf_event.synchronize()           # the previous step's flag: that step finished long ago
+        if int(self._inf_host[0]) != 0:
+            self.overflow_steps += 1
+            if self.overflow_hook is not None:
+                self.overflow_hook()
+        self._inf_flag.zero_()
 
     def _build(self, gi: int, plist: List[torch.Tensor]):
         dev = plist[0].device
@@ -66,6 +87,7 @@ class Adam(torch.optim.Adam):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        launched = False
         for gi, group in enumerate(self.param_groups):
             plist = [p for p in group["params"] if p.grad is not None]
             if not plist:
@@ -84,15 +106,21 @@ class Adam(torch.optim.Adam):
             if gptrs != self._grad_ptrs[gi]:     # the allocator hands back the same blocks step after step: rare upload
                 tb["g"].copy_(torch.tensor(gptrs, dtype=torch.int64))
                 self._grad_ptrs[gi] = gptrs
+            if not launched:
+                self._check_overflow(plist[0].device)       # once per step, before the first launch
+                launched = True
             st0 = self.state[plist[0]]["step"]
             step = int(st0.item()) + 1
             beta1, beta2 = group["betas"]
             lib.call("dvae_adam_step", lib.ptr(tb["p"]), lib.ptr(tb["g"]), lib.ptr(tb["m"]), lib.ptr(tb["v"]), lib.ptr(tb["sizes"]),
                      lib.ptr(tb["blk_t"]), lib.ptr(tb["blk_o"]), tb["nblk"], _CHUNK, float(group["lr"]), float(beta1), float(beta2),
-                     float(group["eps"]), step, lib.stream())
+                     float(group["eps"]), step, lib.ptr(self._inf_flag), lib.stream())
             # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on `_version`,
             # e.g. the tensor-core weight copies of the drop-in modules) that they changed
             torch.autograd.graph.increment_version(plist)
             for p in plist:
                 self.state[p]["step"] += 1     # CPU scalars, like torch's non-capturable Adam
+        if launched:
+            self._inf_host.copy_(self._inf_flag, non_blocking=True)
+            self._inf_event.record()
         return loss

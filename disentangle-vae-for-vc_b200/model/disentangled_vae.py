@@ -342,6 +342,7 @@ class ConvolutionalMulVAE(VariationalBaseModelVAE):
         self.model = DisentangledVAE(latent_dim=self.latent_dim, beta=0.1, batch_size=batch_size,
                                      speaker_size=speaker_size).to(device)
         self.optimizer = fused_optim.Adam(self.model.parameters(), lr=self.lr)   # torch.optim.Adam semantics, one launch
+        self.optimizer.overflow_hook = self._on_gradient_overflow
         self.train_losses = []
         self.test_losses = []
 
@@ -352,6 +353,12 @@ class ConvolutionalMulVAE(VariationalBaseModelVAE):
         return _LossFn.apply(float(self.batch_size), float(self.mse_cof), float(self.kl_cof), x1, x2, x_recon1, x_recon2,
                              recons_x1_hat, recons_x2_hat, q_z1_mu, q_z1_logvar, q_z2_mu, q_z2_logvar, style_mu1,
                              style_logvar1)
+
+    def _on_gradient_overflow(self):
+        """fp16 mode: a gradient left fp16's range (the optimizer skipped those elements): halve the gradient scale."""
+        if self.model._dt == lib.F16 and self.model.grad_scale > 2.0 ** -24:
+            self.model.grad_scale = self.model.grad_scale / 2
+            print(f"[dvae_b200] non-finite gradient: gradient scale lowered to {self.model.grad_scale:g}")
 
     def update_(self):
         self.model.update_c()

@@ -148,9 +148,10 @@ int dvae_group_reparam(const float* mu, const float* logvar, const int* gid, con
 /* ---- optimizer: optim.Adam(...) (model/disentangled_vae.py:304) stepped at model/variational_base_vae.py:69.  One launch
  *      for all tensors; every pointer is DEVICE memory: arrays of tensor base pointers / sizes, and for each block the
  *      tensor index and element offset of its chunk.  `step` counts from 1 (bias corrections). */
+/* found_inf (device int, may be null): set to 1 when a gradient element is not finite; such elements are left untouched */
 int dvae_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                    const long* sizes, const int* blk_tensor, const long* blk_off, int num_blocks, int chunk, double lr,
-                   double beta1, double beta2, double eps, long step, void* stream);
+                   double beta1, double beta2, double eps, long step, int* found_inf, void* stream);
 
 #ifdef __cplusplus
 }

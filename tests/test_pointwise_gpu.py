@@ -274,3 +274,41 @@ def test_fused_adam_survives_state_reload():
     ours = run(Adam, 2)
     for a, b in zip(ref, ours):
         assert torch.allclose(a, b, rtol=2e-6, atol=1e-7)
+
+
+def test_fused_adam_skips_and_reports_non_finite_gradients():
+    """fp16 mode safety net: an element whose gradient is inf / nan is left untouched (parameter and both moments), every
+    other element steps normally, and the overflow hook fires at the next step (the flag is read back one step late)."""
+    from dvae_b200.optim import Adam
+    torch.manual_seed(9)
+    p_ref = [torch.randn(1000, device="cuda").requires_grad_(True), torch.randn(64, 33, device="cuda").requires_grad_(True)]
+    p_our = [p.detach().clone().requires_grad_(True) for p in p_ref]
+    ref, our = torch.optim.Adam(p_ref, lr=1e-2), Adam(p_our, lr=1e-2)
+    calls = []
+    our.overflow_hook = lambda: calls.append(1)
+    g0 = [torch.randn_like(p) for p in p_ref]
+    for a, b, g in zip(p_ref, p_our, g0):
+        a.grad, b.grad = g.clone(), g.clone()
+    ref.step(), our.step()
+    before = [p.detach().clone() for p in p_our]
+    m_before = our.state[p_our[0]]["exp_avg"].clone()
+    g1 = [torch.randn_like(p) for p in p_ref]
+    bad = g1[0].clone()
+    bad[5], bad[17] = float("inf"), float("nan")
+    p_our[0].grad, p_our[1].grad = bad, g1[1].clone()
+    p_ref[0].grad, p_ref[1].grad = g1[0].clone(), g1[1].clone()
+    ref.step(), our.step()
+    assert calls == []                                   # reported one step late
+    ok = torch.ones(1000, dtype=torch.bool, device="cuda")
+    ok[5] = ok[17] = False
+    assert torch.equal(p_our[0].detach()[~ok], before[0][~ok])                       # skipped elements: untouched
+    assert torch.equal(our.state[p_our[0]]["exp_avg"][~ok], m_before[~ok])
+    assert torch.allclose(p_our[0].detach()[ok], p_ref[0].detach()[ok], rtol=2e-6, atol=1e-7)   # the rest: a normal step
+    assert torch.allclose(p_our[1].detach(), p_ref[1].detach(), rtol=2e-6, atol=1e-7)
+    assert torch.isfinite(p_our[0]).all()
+    for b, g in zip(p_our, g0):
+        b.grad = g.clone()
+    our.step()
+    assert calls == [1] and our.overflow_steps == 1
+    our.step()
+    assert calls == [1]                                  # a clean step does not report again
