@@ -250,13 +250,13 @@ def tensor_rooflines(args, dev, R, peaks):
         def fwd(i):
             keep["h"], keep["c"] = ops.lstm_fwd(dt, xg, whh, H, 1)
         ms = event_time(fwd, 3, 1, dev)
-        n_f = lib._lib.dvae_lstm_launches(H, T, 0)
+        n_f = lib._lib.dvae_lstm_launches_for(dt, R2, T, H, 1, 0)
         out.append(entry(f"LSTM recurrence fwd H={H}: {n_f} launch(es) for {T} steps, fused cell epilogue",
                          2.0 * R2 * 4 * H * H * (T - 1), ms, launches=n_f,
                          note="ms_per_launch / flops_per_launch are per launch; achieved is over the whole recurrence"))
         dh = torch.randn(R2, T, H, device=dev).to(ad) * 0.01
         ms = event_time(lambda i: ops.lstm_bwd(dt, dh, xg, keep["c"], whh, H, 1), 3, 1, dev)
-        n_b = lib._lib.dvae_lstm_launches(H, T, 1)
+        n_b = lib._lib.dvae_lstm_launches_for(dt, R2, T, H, 1, 1)
         out.append(entry(f"LSTM recurrence bwd H={H}: {n_b} launch(es) for {T} steps (dh_rec GEMM + cell backward)",
                          2.0 * R2 * 4 * H * H * (T - 1), ms, launches=n_b,
                          note="ms_per_launch / flops_per_launch are per launch; achieved is over the whole recurrence"))

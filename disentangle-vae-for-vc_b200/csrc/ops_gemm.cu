@@ -1049,6 +1049,7 @@ int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_
   auto st = static_cast<cudaStream_t>(stream);
   if (dtype == kF32) return simt_lstm_fwd((float*)xg, (const float*)whh_p, (float*)h_all, c_all, rows, T, H, D, st);
   if (lstm_seq_supported(H, T)) return lstm_seq_fwd(dtype, xg, whh_p, h_all, c_all, rows, T, H, D, st);
+  if (lstm_res_supported(dtype, rows, T, H, D)) return lstm_res_fwd(dtype, xg, whh_p, h_all, c_all, rows, T, H, st);
   DISPATCH_AT(dtype, lstm_fwd_t<AT>((AT*)xg, (const AT*)whh_p, (AT*)h_all, c_all, rows, T, H, D, st));
 }
 
@@ -1059,6 +1060,9 @@ int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float*
   auto st = static_cast<cudaStream_t>(stream);
   if (dtype == kF32) return simt_lstm_bwd((const float*)dh_all, (const float*)gates, c_all, (const float*)whh_n, (float*)da_all, dc_ws, rows, T, H, D, st);
   if (lstm_seq_supported(H, T)) return lstm_seq_bwd(dtype, dh_all, gates, c_all, whh_n, da_all, rows, T, H, D, st);
+  static const int res_bwd = env_int("DVAE_LSTM_RES_BWD", 0);
+  if (res_bwd && lstm_res_supported(dtype, rows, T, H, D))
+    return lstm_res_bwd(dtype, dh_all, gates, c_all, whh_n, da_all, splitk_ws, rows, T, H, st);
   DISPATCH_AT(dtype, lstm_bwd_t<AT>((const AT*)dh_all, (const AT*)gates, c_all, (const AT*)whh_n, (AT*)da_all, dc_ws, splitk_ws,
                                     tickets, rows, T, H, D, st));
 }
@@ -1070,6 +1074,8 @@ int dvae_lstm_bwd_workspace(int dtype, int rows, int H, int D, long* ws_floats, 
   const int splits = lstm_bwd_splits(rows, H, D, eb);
   *num_tickets = tiles;
   *ws_floats = splits > 1 ? static_cast<long>(tiles) * splits * 128 * bn : 0;
+  // the resident kernel (ops_lstm_res.cu) parks the partial sums of its K slices here (T is not known to this query)
+  if (lstm_res_shape_ok(dtype, rows, 64, H, D)) *ws_floats = std::max(*ws_floats, lstm_res_bwd_scratch_floats(rows, H));
   return 0;
 }
 
@@ -1088,6 +1094,19 @@ int dvae_lstm_launches(int H, int T, int backward) {
   static const int fused = env_int("DVAE_LSTM_BWD_FUSED", 0);
   return backward ? (fused ? T : 2 * T - 1) : T;
 }
+
+// same, for the exact call: dvae_lstm_fwd / dvae_lstm_bwd pick the time-resident kernels (one launch per 1024 rows) when
+// the shape allows it
+int dvae_lstm_launches_for(int dtype, int rows, int T, int H, int D, int backward) {
+  static const int res_bwd = env_int("DVAE_LSTM_RES_BWD", 0);
+  if (dtype != kF32 && !lstm_seq_supported(H, T) && lstm_res_supported(dtype, rows, T, H, D) && (!backward || res_bwd))
+    return ceil_div(rows, 1024);
+  return dvae_lstm_launches(H, T, backward);
+}
+
+// 1 / 0: use / do not use the time-resident kernels of ops_lstm_res.cu for the H = 512 / 1024 recurrences (default 1, or
+// DVAE_LSTM_RES); a negative value only queries.  Returns the previous setting.
+int dvae_set_lstm_resident(int on) { return lstm_res_set_enabled(on); }
 
 // 1: subsequent GEMM launches from this host thread are background work (see want_persistent); 0: normal
 int dvae_set_background(int on) {
@@ -1111,6 +1130,12 @@ int dvae_debug_timing(unsigned long long* buf, int capacity) {
 // debug: per-step SM-clock stamps [T][8] of CTA (0,0) of the sequence-resident LSTM kernels (nullptr: off)
 int dvae_debug_seq_stamps(long long* buf) {
   lstm_seq_set_stamps(buf);
+  return 0;
+}
+
+// debug: globaltimer stamps [T][2 slots][8 points] of CTA 0 of the time-resident H = 512 / 1024 kernels (nullptr: off)
+int dvae_debug_res_stamps(unsigned long long* buf) {
+  lstm_res_set_stamps(buf);
   return 0;
 }
 

@@ -146,6 +146,75 @@ __global__ void add_f32_act_kernel(const float* __restrict__ a, const AT* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------ all weight copies in one launch
+// After every optimizer step every tensor-core copy of the parameters has to be re-derived (dvae_b200.engine.
+// PreparedWeights.refresh).  Tensor by tensor that is ~55 small launches; this kernel does it in one, driven by a table:
+// one descriptor per fp32 source tensor (what to derive from it and where to), one (descriptor, offset) pair per block.
+struct PrepDesc {
+  const float* src;
+  const float* src2;   // kPrepLstmBias: the second bias vector
+  void* dst0;
+  void* dst1;          // optional second destination (see the kinds)
+  long n;              // elements of src
+  int kind, d0, d1, pad;
+};
+enum PrepKind : int {
+  kPrepCast = 0,       // dst0[i] = act(src[i]);  dst1 (optional, src viewed [n / d1, d1]): rows [hi | lo] (d0 = 2) or [hi | hi | lo] (d0 = 3)
+  kPrepConv = 1,       // src [d0 = Co][d1 = Ci][5] -> dst0 [Co][5][Ci];  dst1 (optional) [Co][5][3Ci] = [hi | hi | lo]
+  kPrepLstmW = 2,      // src [4H][d1 = In] (d0 = H): dst0 natural cast, dst1 rows gate-interleaved (row 4u + g <- row g*H + u)
+  kPrepCopy = 3,       // dst0 (fp32)[i] = src[i]
+  kPrepLstmBias = 4,   // dst0 (fp32)[4u + g] = src[g*H + u] + src2[g*H + u]   (d0 = H)
+};
+template <typename AT>
+__global__ void __launch_bounds__(256) prep_all_kernel(const PrepDesc* __restrict__ descs, const int* __restrict__ blk_desc,
+                                                       const long* __restrict__ blk_off, int chunk) {
+  const PrepDesc d = descs[blk_desc[blockIdx.x]];
+  const long off = blk_off[blockIdx.x];
+  const long end = min(d.n, off + chunk);
+  for (long i = off + threadIdx.x; i < end; i += blockDim.x) {
+    const float v = d.src[i];
+    if (d.kind == kPrepCopy) {
+      static_cast<float*>(d.dst0)[i] = v;
+      continue;
+    }
+    if (d.kind == kPrepLstmBias) {
+      const int H = d.d0, g = static_cast<int>(i / H), u = static_cast<int>(i - static_cast<long>(g) * H);
+      static_cast<float*>(d.dst0)[4 * u + g] = v + d.src2[i];
+      continue;
+    }
+    const AT hi = from_f32<AT>(v);
+    if (d.kind == kPrepCast) {
+      static_cast<AT*>(d.dst0)[i] = hi;
+      if (d.dst1 != nullptr) {
+        const long K = d.d1, r = i / K, c = i - r * K;
+        AT* row = static_cast<AT*>(d.dst1) + r * d.d0 * K;
+        row[c] = hi;
+        if (d.d0 == 3) row[K + c] = hi;
+        row[(d.d0 - 1) * K + c] = from_f32<AT>(v - to_f32(hi));
+      }
+    } else if (d.kind == kPrepConv) {
+      const int Ci = d.d1;
+      const int k = static_cast<int>(i % 5);
+      const long rest = i / 5;
+      const int ci = static_cast<int>(rest % Ci);
+      const long co = rest / Ci;
+      static_cast<AT*>(d.dst0)[(co * 5 + k) * Ci + ci] = hi;
+      if (d.dst1 != nullptr) {
+        AT* row = static_cast<AT*>(d.dst1) + (co * 5 + k) * 3 * Ci;
+        row[ci] = hi;
+        row[Ci + ci] = hi;
+        row[2 * Ci + ci] = from_f32<AT>(v - to_f32(hi));
+      }
+    } else {   // kPrepLstmW
+      const int H = d.d0;
+      const long In = d.d1, r = i / In, c = i - r * In;
+      const int g = static_cast<int>(r / H), u = static_cast<int>(r - static_cast<long>(g) * H);
+      static_cast<AT*>(d.dst0)[i] = hi;
+      static_cast<AT*>(d.dst1)[(4L * u + g) * In + c] = hi;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ layout packing
 // x fp32 [R][C][T] (reference NCL) -> y act [R][T][C] (channels-last, the GEMM A-operand layout)
 // split != 0: besides y (the rounded values, "hi") also y_cat [R][T][3C] = [hi | lo | hi] with lo = round(x - hi): the
@@ -656,6 +725,17 @@ int dvae_copy_f32(const float* src, float* dst, long n, void* stream) {
 int dvae_add_inplace(int dtype, void* a, const void* b, long n, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
   DISPATCH_AT(dtype, add_inplace_kernel<AT><<<grid_for((n + 7) / 8, 256), 256, 0, st>>>((AT*)a, (const AT*)b, n));
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+// Every tensor-core copy of the parameters in ONE launch.  descs: device array of 64-byte descriptors {src, src2, dst0, dst1,
+// n (int64), kind, d0, d1, pad (int32)} -- see PrepKind in this file; blk_desc / blk_off: for each block, which descriptor and
+// which element offset its chunk of `chunk` source elements starts at.
+int dvae_prep_all(int dtype, const void* descs, const int* blk_desc, const long* blk_off, int num_blocks, int chunk, void* stream) {
+  auto st = static_cast<cudaStream_t>(stream);
+  static_assert(sizeof(PrepDesc) == 56 || sizeof(PrepDesc) == 64, "descriptor layout");
+  if (num_blocks <= 0) return 0;
+  DISPATCH_AT(dtype, prep_all_kernel<AT><<<num_blocks, 256, 0, st>>>(static_cast<const PrepDesc*>(descs), blk_desc, blk_off, chunk));
   DVAE_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "dvae_lstm_bwd_workspace": [_i, _i, _i, _i, _p, _p],
     "dvae_debug_timing": [_p, _i],
     "dvae_debug_seq_stamps": [_p],
+    "dvae_debug_res_stamps": [_p],
     "dvae_set_background": [_i],
     "dvae_lstm_wgrad_hh": [_i, _p, _p, _p, _i, _i, _i, _i, _f, _p],
     # weight preparation / layout
@@ -94,9 +95,11 @@ def register(name, argtypes):
 
 
 _FUNCS = {n: _bind(n, a) for n, a in _SIGNATURES.items()}
-for _n in ("dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile", "dvae_lstm_launches"):
+for _n in ("dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile", "dvae_lstm_launches", "dvae_lstm_launches_for", "dvae_set_lstm_resident"):
     getattr(_lib, _n).restype = C.c_int
 _lib.dvae_lstm_launches.argtypes = [C.c_int, C.c_int, C.c_int]
+_lib.dvae_lstm_launches_for.argtypes = [C.c_int] * 6
+_lib.dvae_set_lstm_resident.argtypes = [C.c_int]
 _lib.dvae_workspace_bytes.restype = C.c_long
 _lib.dvae_workspace_bytes.argtypes = [C.c_char_p, C.c_long, C.c_long, C.c_long]
 
@@ -124,14 +127,15 @@ def stream():
 LAUNCHES = 0
 _LAUNCHES_PER_CALL = {"dvae_bn_finalize_apply": 2, "dvae_bn_train_fwd": 3, "dvae_bn_train_bwd": 3, "dvae_bn_eval_fwd": 2, "dvae_segment_ids_sorted": 3,
                       "dvae_group_finalize": 2}
-_LSTM_SHAPE_ARGS = {"dvae_lstm_fwd": (7, 6), "dvae_lstm_bwd": (11, 10)}   # indices of (H, T): the library says how many launches
+_LSTM_SHAPE_ARGS = {"dvae_lstm_fwd": 5, "dvae_lstm_bwd": 9}   # index of `rows` (then T, H, D): the library says how many launches
 
 
 def call(name, *args):
     global LAUNCHES
     if name in _LSTM_SHAPE_ARGS:
-        iH, iT = _LSTM_SHAPE_ARGS[name]
-        LAUNCHES += _lib.dvae_lstm_launches(args[iH], args[iT], 1 if name == "dvae_lstm_bwd" else 0)
+        i = _LSTM_SHAPE_ARGS[name]
+        LAUNCHES += _lib.dvae_lstm_launches_for(args[0], args[i], args[i + 1], args[i + 2], args[i + 3],
+                                                1 if name == "dvae_lstm_bwd" else 0)
     else:
         LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
     rc = _FUNCS[name](*args)
@@ -152,10 +156,15 @@ def lstm_bwd_workspace(dt: int, rows: int, H: int, D: int):
     return ws.value, nt.value
 
 
+def set_lstm_resident(on: int) -> int:
+    """Switch the time-resident H = 512 / 1024 recurrence kernels on (1) / off (0); negative: query.  Returns the previous setting."""
+    return _lib.dvae_set_lstm_resident(int(on))
+
+
 def lstm_gate_tile(hidden: int) -> int:
     return _lib.dvae_lstm_gate_tile(hidden)
 
 
 def exported_symbols():
     return sorted(_SIGNATURES.keys()) + ["dvae_last_error", "dvae_version", "dvae_sm_arch", "dvae_lstm_gate_tile",
-                                             "dvae_lstm_launches", "dvae_workspace_bytes"]
+                                             "dvae_lstm_launches", "dvae_lstm_launches_for", "dvae_set_lstm_resident", "dvae_workspace_bytes"]

@@ -277,7 +277,9 @@ def _lstm_ref(xproj_nat, whh, D, H):
 
 
 @pytest.mark.parametrize("name", DTS)
-@pytest.mark.parametrize("rows,H,D,T", [(8, 64, 2, 64), (130, 64, 1, 64), (16, 512, 1, 64), (256, 1024, 1, 64)])
+@pytest.mark.parametrize("rows,H,D,T", [(8, 64, 2, 64), (130, 64, 1, 64), (16, 512, 1, 64), (256, 1024, 1, 64),
+                                        # rows % 512 == 0: the time-resident kernels of ops_lstm_res.cu (16-bit storage)
+                                        (512, 1024, 1, 64), (1024, 512, 1, 64)])
 def test_lstm(name, rows, H, D, T):
     _setup()
     from dvae_b200 import lib, ops
@@ -308,12 +310,38 @@ def test_lstm(name, rows, H, D, T):
     assert relw <= {"bf16": 3e-2, "fp32": 2e-5}.get(name, 3e-3), f"lstm dW_hh rel err {relw}"
 
 
+def test_lstm_resident_forward_is_bit_identical():
+    """The time-resident forward runs the same MMAs in the same order as the step-per-launch kernels: h, c and the saved gates
+    are bit-identical, at both hidden sizes, with one and with two launches per call (rows > 1024)."""
+    _setup()
+    from dvae_b200 import lib, ops
+    prev = lib.set_lstm_resident(-1)
+    try:
+        for name, H, rows, T in (("fp16", 1024, 1024, 64), ("bf16", 512, 2048, 16), ("fp16", 512, 512, 5)):
+            dt = _dt(name)
+            xg0 = _rand((rows, T, 4 * H), name, seed=21)
+            whh_p = _rand((1, 4 * H, H), name, 1.0 / H ** 0.5, seed=22)
+            out = {}
+            for mode in (0, 1):
+                lib.set_lstm_resident(mode)
+                xg = xg0.clone()
+                h, c = ops.lstm_fwd(dt, xg, whh_p, H, 1)
+                torch.cuda.synchronize()
+                out[mode] = (h, c, xg)
+            for a, b, nm in zip(out[0], out[1], ("h", "c", "gates")):
+                assert torch.equal(a, b), f"{name} H={H} rows={rows}: {nm} differs between the resident and the per-step kernels"
+    finally:
+        lib.set_lstm_resident(prev)
+
+
 @pytest.mark.parametrize("env", [
     {"DVAE_LSTM_SEQ": "0"},                                        # H = 64 through the step-per-launch path
     {"DVAE_LSTM_SEQ_IO": "direct"},                                # sequence-resident kernels without the TMA staging
     {"DVAE_LSTM_FWD_TMA": "0", "DVAE_LSTM_BWD_REDUCE": "0"},       # direct cell epilogue, store-epilogue backward
     {"DVAE_LSTM_PAIR": "1"},                                       # CTA-pair (cta_group::2) step kernels
     {"DVAE_LSTM_BWD_FUSED": "1"},                                  # cell backward fused into the step GEMM's epilogue
+    {"DVAE_LSTM_RES": "0"},                                        # H = 512 / 1024 through the step-per-launch path at every size
+    {"DVAE_LSTM_RES_BWD": "1"},                                    # time-resident backward (measured slower; kept as an option)
 ], ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
 def test_lstm_optional_paths(env):
     """The kernel variants that are not the default (selected by environment variables read once per process) stay correct:
