@@ -1049,7 +1049,10 @@ int dvae_lstm_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_
   auto st = static_cast<cudaStream_t>(stream);
   if (dtype == kF32) return simt_lstm_fwd((float*)xg, (const float*)whh_p, (float*)h_all, c_all, rows, T, H, D, st);
   if (lstm_seq_supported(H, T)) return lstm_seq_fwd(dtype, xg, whh_p, h_all, c_all, rows, T, H, D, st);
-  if (lstm_res_supported(dtype, rows, T, H, D)) return lstm_res_fwd(dtype, xg, whh_p, h_all, c_all, rows, T, H, st);
+  if (lstm_res_supported(dtype, rows, T, H, D)) {
+    const int e = lstm_res_fwd(dtype, xg, whh_p, h_all, c_all, rows, T, H, st);
+    if (e != 3) return e;   // 3: the grid cannot be co-resident on this device -> step-per-launch kernels
+  }
   DISPATCH_AT(dtype, lstm_fwd_t<AT>((AT*)xg, (const AT*)whh_p, (AT*)h_all, c_all, rows, T, H, D, st));
 }
 
@@ -1061,8 +1064,10 @@ int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float*
   if (dtype == kF32) return simt_lstm_bwd((const float*)dh_all, (const float*)gates, c_all, (const float*)whh_n, (float*)da_all, dc_ws, rows, T, H, D, st);
   if (lstm_seq_supported(H, T)) return lstm_seq_bwd(dtype, dh_all, gates, c_all, whh_n, da_all, rows, T, H, D, st);
   static const int res_bwd = env_int("DVAE_LSTM_RES_BWD", 0);
-  if (res_bwd && lstm_res_supported(dtype, rows, T, H, D))
-    return lstm_res_bwd(dtype, dh_all, gates, c_all, whh_n, da_all, splitk_ws, rows, T, H, st);
+  if (res_bwd && lstm_res_supported(dtype, rows, T, H, D)) {
+    const int e = lstm_res_bwd(dtype, dh_all, gates, c_all, whh_n, da_all, splitk_ws, rows, T, H, st);
+    if (e != 3) return e;
+  }
   DISPATCH_AT(dtype, lstm_bwd_t<AT>((const AT*)dh_all, (const AT*)gates, c_all, (const AT*)whh_n, (AT*)da_all, dc_ws, splitk_ws,
                                     tickets, rows, T, H, D, st));
 }

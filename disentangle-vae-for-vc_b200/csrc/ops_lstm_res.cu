@@ -30,6 +30,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <string>
 
 #include "act_types.cuh"
 #include "host_common.h"
@@ -39,7 +40,7 @@
 namespace dvae {
 
 constexpr int kResThreadsFwd = 384;     // warp 0 TMA producer, 1 MMA issuer, 2..9 cell epilogue, 10 store agent, 11 publishing agent
-constexpr int kResThreadsBwd = 448;     // warp 0 TMA producer, 1 MMA issuer, 2..5 partial sums, 6..13 cell backward
+constexpr int kResThreadsBwd = 352;     // warp 0 TMA producer, 1 MMA issuer, 2..9 partial-sum exchange + cell backward, 10 publishing agent
 constexpr int kResEpiThreads = 256;
 constexpr int kResBarThreads = kResEpiThreads + 32;   // forward: named barriers shared by the epilogue warps and one agent warp
 constexpr int kResKQ = 4;               // backward: K slices (one per gate)
@@ -54,13 +55,12 @@ __device__ unsigned int g_res_flags[kResFlagSlots][kResFlagWords];
 
 struct ResParams {
   CUtensorMap tmA;    // recurrent operand, load:  fwd h_all {H, T, rows} / bwd da_all {4H, T, rows}; box {64, 1, 128}
-  CUtensorMap tmW;    // weight slice, load once:  fwd whh_p {H, 4H, 1} box {64, BN/2, 1} / bwd whh_n {H, 4H, 1} box {64, 64, 1}
+  CUtensorMap tmW;    // weight slice, load once:  fwd whh_p {H, 4H, 1} box {64, BN/2, 1} / bwd W_hh^T {4H, H, 1} box {64, 64, 1}
   CUtensorMap tmO1;   // store: fwd activated gates {4H, T, rows} box {64, 1, 128}; unused by the backward
   void* xg;           // fwd: x-projection in, activated gates out;  bwd: saved activated gates
   float* c_all;
   void* h_all;        // fwd: layer output [rows, T, H];  bwd: da_all [rows, T, 4H] (output)
   const void* dh_all; // bwd: gradient wrt the layer output
-  float* part;        // bwd: partial sums of the K slices [KQ][rows][H] fp32
   unsigned int* flags;
   unsigned long long* stamps;   // debug (dvae_debug_res_stamps): globaltimer stamps [T][2 slots][8 points] of CTA 0, or null
   int row0;           // first row of this launch
@@ -76,7 +76,9 @@ struct ResCfg {
   static constexpr int STAGE = 128 * 128;           // one k-block of the recurrent operand: 128 rows x 128 B
   static constexpr int G_BOXES = BN * 2 / 128;      // fwd: 128-byte boxes of the staged gate tile
   static constexpr int H_ROW = BN / 4 * 2;          // fwd: bytes of h per row and tile
-  static constexpr int STG = BWD ? 0 : G_BOXES * 16384;   // fwd: the activated gates; everything else leaves as direct 32-byte stores
+  // fwd: staged gate tile (everything else leaves as direct 32-byte stores).  bwd: receive buffers of the three other K
+  // slices' partial sums for this CTA's quarter of the tile, [3][128 rows][32 fp32] (written by the peers through DSMEM)
+  static constexpr int STG = BWD ? 3 * 16384 : G_BOXES * 16384;
   static constexpr int BARS = 256;
   static constexpr int FIT = (232448 - 1024 - BARS - W_BYTES - STG) / STAGE;
   static constexpr int NST = FIT > 8 ? 8 : FIT;
@@ -106,6 +108,65 @@ __device__ __forceinline__ uint4 ld_relaxed_v4(const unsigned int* p) {
   uint4 v;
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
+}
+// ---- distributed shared memory (cluster of 8 in the backward kernel)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// asynchronous remote store: 16 bytes into another CTA's shared memory, completion counted (bytes) on THAT CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint4 v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w), "r"(remote_bar)
+               : "memory");
+}
+// Remote arrivals that only say "I have finished READING" (an accumulator in TMEM, a receive buffer): relaxed.  A release
+// arrive is a cluster-scope fence first -- it waits for the thread's outstanding global stores (~1 us each, measured).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// ... on the barrier at this offset in the leader (even-ranked) CTA of this CTA's pair
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint32_t bar) { mbar_arrive_remote(bar & ptx::kPeerBitMask); }
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred P1;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\nselp.b32 %0, 1, 0, P1;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// wait on a barrier whose arrivals come from other CTAs of the cluster (acquire at cluster scope); traps instead of hanging
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = ptx::globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 1023u) == 0 && ptx::globaltimer_ns() - t0 > 2000000000ull) {
+      printf("dvae_b200: resident LSTM cluster barrier timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+// tcgen05.commit of a CTA pair inside a larger cluster: arrive on the barrier at this offset in both CTAs of THIS pair
+__device__ __forceinline__ void umma_commit_pair_at(uint32_t bar, uint32_t pair_first_rank) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(static_cast<uint16_t>(3u << pair_first_rank))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
 }
 // (polls are relaxed loads: an acquire load per poll invalidates the SM's L1 every time; one acquire fence follows)
 __device__ __forceinline__ void wait_counter(const unsigned int* p, unsigned int target) {
@@ -138,8 +199,8 @@ template <typename AT, int H, int BN, bool BWD>
 __global__ void __launch_bounds__(BWD ? kResThreadsBwd : kResThreadsFwd, 1) lstm_res_kernel(const __grid_constant__ ResParams p) {
   using Cfg = ResCfg<AT, H, BN, BWD>;
   constexpr int KB = Cfg::KB, NST = Cfg::NST, STAGE = Cfg::STAGE, WKB = Cfg::WKB, NS = Cfg::NS;
-  constexpr uint32_t IDESC = instr_desc_fmt<MmaFmt<AT>::value, BN, false, BWD, 256>();
-  constexpr uint32_t ADV_B = (BWD ? 16 * 128 : 32) >> 4;   // descriptor advance per UMMA_K = 16 elements
+  constexpr uint32_t IDESC = instr_desc_fmt<MmaFmt<AT>::value, BN, false, false, 256>();   // both operands K-major
+  constexpr uint32_t ADV_B = 32 >> 4;   // descriptor advance per UMMA_K = 16 elements
   constexpr int KQ = kResKQ;
   // a k-block of the recurrent operand = 64 hidden units of one time step; it is complete when ARR CTAs have published
   constexpr unsigned int ARR = BWD ? 2u : 64u / (BN / 4);
@@ -157,22 +218,26 @@ __global__ void __launch_bounds__(BWD ? kResThreadsBwd : kResThreadsFwd, 1) lstm
   const uint32_t wfull_bar = bar_base + 8u * (2 * NST);
   auto acc_full_bar = [&](int a) { return bar_base + 8u * (2 * NST + 1 + a); };
   auto acc_empty_bar = [&](int a) { return bar_base + 8u * (2 * NST + 3 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::W_BYTES + NST * STAGE + Cfg::STG + 8 * (2 * NST + 5));
+  const uint32_t recv_full_bar = bar_base + 8u * (2 * NST + 5);   // backward: the peers' partial sums have arrived
+  const uint32_t send_ok_bar = bar_base + 8u * (2 * NST + 6);     // backward: the peers have consumed what this CTA sent
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + Cfg::W_BYTES + NST * STAGE + Cfg::STG + 8 * (2 * NST + 7));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cr = static_cast<int>(ptx::cluster_ctarank());   // rank in the pair; 0 = leader (issues the MMAs)
+  // forward: clusters of 2 (one pair).  backward: clusters of 8 = the KQ pairs that share an output tile, rank = 2 * kq + cr
+  const uint32_t crank = ptx::cluster_ctarank();
+  const int cr = static_cast<int>(crank & 1u);   // rank in the pair; 0 = leader (issues the MMAs)
+  const uint32_t pair_rank0 = crank & ~1u;       // cluster rank of this pair's leader
   const int pair = blockIdx.x >> 1;
   const int slice = pair % NS, grp = pair / NS;
   // forward: slice = gate-column tile.  backward: slice = (hidden-column tile nt, K slice kq); the KQ pairs of one nt are
-  // neighbours and reduce into each other
+  // neighbours (one cluster) and reduce into each other
   const int kq = BWD ? slice % KQ : 0;
   const int nt = BWD ? slice / KQ : slice;
   const int T = p.T;
   // 128-row tile (within this launch) of slot s: row block 2*grp + s, this CTA's half
   auto row_tile = [&](int s) { return (2 * grp + s) * 2 + cr; };
   unsigned int* ready = p.flags;                                                  // [row tile][k-block], one line per row tile
-  unsigned int* part_ready = p.flags + kResMaxRowTiles * kResFlagStride;          // [row tile][nt], one line each (backward)
   // the k-block this CTA's output belongs to
   const int my_kb = BWD ? nt * 2 + kq / 2 : nt * (BN / 4) / 64;
 
@@ -193,8 +258,10 @@ __global__ void __launch_bounds__(BWD ? kResThreadsBwd : kResThreadsFwd, 1) lstm
     ptx::mbar_init(wfull_bar, 1);
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(acc_full_bar(a), 1);
-      ptx::mbar_init(acc_empty_bar(a), 2 * (BWD ? 4 : 8));   // one arrival per accumulator-reading warp of both CTAs
+      ptx::mbar_init(acc_empty_bar(a), 2 * 8);   // one arrival per epilogue warp of both CTAs
     }
+    ptx::mbar_init(recv_full_bar, 1);       // armed by this CTA with the bytes the three peers will send (st.async complete_tx)
+    ptx::mbar_init(send_ok_bar, 3 * 8);     // ... and of the three CTAs this one sends to
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -213,8 +280,7 @@ __global__ void __launch_bounds__(BWD ? kResThreadsBwd : kResThreadsFwd, 1) lstm
     if (lane == 0) {
       if (cr == 0) ptx::mbar_expect_tx(wfull_bar, 2 * Cfg::W_BYTES);
       for (int kb = 0; kb < KB; ++kb) {
-        if constexpr (BWD) ptx::tma_load_3d_pair(w_base + kb * WKB, &p.tmW, wfull_bar, nt * BN + cr * 64, kq * H + kb * 64, 0);
-        else ptx::tma_load_3d_pair(w_base + kb * WKB, &p.tmW, wfull_bar, kb * 64, nt * BN + cr * (BN / 2), 0);
+        ptx::tma_load_3d_pair(w_base + kb * WKB, &p.tmW, wfull_bar, (BWD ? kq * H : 0) + kb * 64, nt * BN + cr * (BN / 2), 0);
       }
       int it = 0;
       for (int st = 1; st < T; ++st) {
@@ -224,7 +290,7 @@ __global__ void __launch_bounds__(BWD ? kResThreadsBwd : kResThreadsFwd, 1) lstm
           const int rt = row_tile(s);
           const unsigned int* cnt = ready + rt * kResFlagStride;
           uint32_t have = 0;   // bit kb: that k-block of h_{t-1} / da_{t+1} has been published by all its producers
-          stamp(st, s, 0);
+          if (!BWD) stamp(st, s, 0);
           for (int kb = 0; kb < KB; ++kb, ++it) {
             // data-flow start: a k-block is loaded as soon as ITS producers have published; the MMAs of the early k-blocks
             // overlap the epilogues of the CTAs that are late
@@ -246,7 +312,7 @@ __global__ void __launch_bounds__(BWD ? kResThreadsBwd : kResThreadsFwd, 1) lstm
               }
               // the loads below are TMA (async proxy) reads of L2, issued after the counter value has returned
               fence_proxy_async_all();
-              if (kb == 0) stamp(st, s, 1);
+              if (kb == 0 && !BWD) stamp(st, s, 1);
             }
             const int sg = it % NST;
             const uint32_t ph = (it / NST) & 1;
@@ -255,7 +321,7 @@ __global__ void __launch_bounds__(BWD ? kResThreadsBwd : kResThreadsFwd, 1) lstm
             ptx::tma_load_3d_pair(ring_base + sg * STAGE, &p.tmA, full_bar(sg), (BWD ? kq * H : 0) + kb * 64, t_a,
                                   p.row0 + rt * 128);
           }
-          stamp(st, s, 2);
+          if (!BWD) stamp(st, s, 2);
         }
       }
     }
@@ -276,16 +342,16 @@ __global__ void __launch_bounds__(BWD ? kResThreadsBwd : kResThreadsFwd, 1) lstm
             ptx::tc_fence_after();
             if (lane == 0) {
               const uint64_t adesc = smem_desc(ring_base + sg * STAGE, 16, 1024, 2);
-              const uint64_t bdesc = BWD ? smem_desc(w_base + kb * WKB, 64 * 128, 1024, 2) : smem_desc(w_base + kb * WKB, 16, 1024, 2);
+              const uint64_t bdesc = smem_desc(w_base + kb * WKB, 16, 1024, 2);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 ptx::umma_pair<2>(tmem_base + s * BN, adesc + k * 2, bdesc + k * ADV_B, IDESC, (kb > 0 || k > 0) ? 1u : 0u);
-              ptx::umma_commit_pair(empty_bar(sg));
+              umma_commit_pair_at(empty_bar(sg), pair_rank0);
             }
             __syncwarp();
           }
           if (lane == 0) {
-            ptx::umma_commit_pair(acc_full_bar(s));
+            umma_commit_pair_at(acc_full_bar(s), pair_rank0);
             stamp(st, s, 3);
           }
           __syncwarp();
@@ -416,7 +482,7 @@ __global__ void __launch_bounds__(BWD ? kResThreadsBwd : kResThreadsFwd, 1) lstm
           if (st > 0) {
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_leader(acc_empty_bar(s));
+            if (lane == 0) mbar_arrive_leader_relaxed(acc_empty_bar(s));
           }
           ptx::fence_proxy_async_smem();
           ptx::bar_arrive(1, kResBarThreads);   // gate tile staged
@@ -436,131 +502,192 @@ __global__ void __launch_bounds__(BWD ? kResThreadsBwd : kResThreadsFwd, 1) lstm
     }
   } else {
     // =============================================================================================== backward
+    if (warp == 10) {
+      // publishing agent: da_t is written by the epilogue threads with plain stores; bar 2 orders them before this thread's
+      // gpu-scope release.  (A separate warp: the release fence would otherwise also wait for the epilogue thread's own
+      // outstanding loads of the next item.)
+      for (int st = 0; st < T; ++st) {
+        for (int s = 0; s < 2; ++s) {
+          ptx::bar_sync(2, kResBarThreads);
+          if (lane == 0) {
+            red_release_u32(ready + row_tile(s) * kResFlagStride + my_kb, 1u);
+            stamp(st, s, 7);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+    // Epilogue warps 2..9 of every CTA.  The pair's accumulator holds ITS K slice (gate kq) of dh_rec for a 256 x 128 tile; the
+    // four pairs of the cluster each own a quarter of the tile's hidden units for the cell backward.  Per item:
+    //   1. the three quarters that belong to the other pairs go straight from TMEM into their receive buffers (DSMEM stores,
+    //      then one remote mbarrier arrive per warp) -- no global memory, no fence, no flag;
+    //   2. the own quarter is summed with the three received ones in a fixed order (deterministic), the senders are told that
+    //      their data has been consumed, and the cell backward runs (inputs were requested before the accumulator wait);
+    //   3. da_t leaves as direct 32-byte stores and is published to the consumers of the next step (all clusters).
     const AT* gates = static_cast<const AT*>(p.xg);
     const AT* dh_all = static_cast<const AT*>(p.dh_all);
     AT* da_all = static_cast<AT*>(p.h_all);
     const long ldx = static_cast<long>(T) * 4 * H, ldc = static_cast<long>(T) * H;
-    if (warp < 6) {
-      // ---------------------------------------------------------- partial sums (warps 2..5, one per TMEM lane quarter): this
-      // pair's K slice of the 256 x 128 tile -> scratch [kq][row][H], whole 32-byte sectors straight from the registers
-      const int q = warp & 3;
-      const int row = q * 32 + lane;
-      const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-      for (int st = 1; st < T; ++st) {
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-          const int rt = row_tile(s);
-          const long m = static_cast<long>(p.row0) + rt * 128 + row;
-          float* pp = p.part + (static_cast<long>(kq) * p.rows + m) * H + nt * BN;
+    constexpr int UPT = BN / KQ / 2;   // hidden units per thread in the cell phase
+    static_assert(UPT == 16, "cell phase: 16 hidden units per thread");
+    const int q = warp & 3;             // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;   // which half of a quarter's 32 units
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int u0 = nt * BN + kq * (BN / KQ) + half * UPT;   // first hidden unit of this thread in the cell phase
+    const uint32_t recv = stg;          // [3][128 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+    // where this thread's 16 columns of a quarter live inside a receive buffer row: chunks 4*half .. 4*half+3
+    auto chunk_off = [&](int j) { return static_cast<uint32_t>(row * 128 + (((4 * half + j) ^ (row & 7)) << 4)); };
+    float dcst[2][UPT];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int i = 0; i < UPT; ++i) dcst[s][i] = 0.f;
+    // saved tensors of an item, requested while the previous item is being finished
+    typename Act8<AT>::raw_t g_raw[8];
+    typename Act8<float>::raw_t c_raw[2], cp_raw[2];
+    typename Act8<AT>::raw_t dh_raw[2];
+    auto request = [&](int st, int s) {
+      const int t = T - 1 - st;
+      const long m = static_cast<long>(p.row0) + row_tile(s) * 128 + row;
+      const AT* gp = gates + m * ldx + static_cast<long>(t) * 4 * H + 4 * u0;
+      const float* cp = p.c_all + m * ldc + static_cast<long>(t) * H + u0;
+      const AT* dp = dh_all + m * ldc + static_cast<long>(t) * H + u0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g_raw[j] = Act8<AT>::load_raw(gp + 8 * j);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) c_raw[j] = Act8<float>::load_raw(cp + 8 * j);
+      if (t > 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) cp_raw[j] = Act8<float>::load_raw(cp - H + 8 * j);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) dh_raw[j] = Act8<AT>::load_raw(dp + 8 * j);
+      if (t > 0) {   // what this slot reads at the next step: HBM -> L2 now
+        prefetch_l2_line(gp - 4 * H);
+        prefetch_l2_line(dp - H);
+        if (t > 1) prefetch_l2_line(cp - 2 * H);
+      }
+    };
+    request(0, 0);
+    for (int st = 0; st < T; ++st) {
+      const int t = T - 1 - st;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int rt = row_tile(s);
+        const long m = static_cast<long>(p.row0) + rt * 128 + row;
+        float dh[UPT];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) Act8<AT>::unpack(dh_raw[j], dh + 8 * j);
+        if (st > 0) {
+          const int item = (st - 1) * 2 + s;   // index among the items that have an accumulator
           ptx::mbar_wait(acc_full_bar(s), (st - 1) & 1);
           ptx::tc_fence_after();
           if (threadIdx.x == 64) stamp(st, s, 4);
-#pragma unroll 1
-          for (int c = 0; c < BN; c += 32) {
+          if (threadIdx.x == 64) ptx::mbar_expect_tx(recv_full_bar, 3 * 16384);   // what the three peers send for this item
+          if (item > 0) mbar_wait_cluster(send_ok_bar, (item - 1) & 1);   // the peers have consumed the previous item's quarters
+          // 1. the other pairs' quarters: TMEM -> their receive buffers
+#pragma unroll
+          for (int r = 1; r < KQ; ++r) {
+            const int dq = (kq + r) & (KQ - 1);                      // destination pair
+            const int slot = kq < dq ? kq : kq - 1;                  // sources are kept in ascending kq order
+            const uint32_t dst = mapa_u32(recv + slot * 16384, static_cast<uint32_t>(dq * 2 + cr));
+            const uint32_t dbar = mapa_u32(recv_full_bar, static_cast<uint32_t>(dq * 2 + cr));
             __syncwarp();
-            float v[32];
-            ptx::tmem_ld_x32(tmem_base + s * BN + lane_addr + c, v);
+            float v[16];
+            tmem_ld_x16(tmem_base + s * BN + lane_addr + dq * (BN / KQ) + half * UPT, v);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              st_global_v8(pp + c + 8 * j,
-                           make_uint4(__float_as_uint(v[8 * j]), __float_as_uint(v[8 * j + 1]), __float_as_uint(v[8 * j + 2]),
-                                      __float_as_uint(v[8 * j + 3])),
-                           make_uint4(__float_as_uint(v[8 * j + 4]), __float_as_uint(v[8 * j + 5]), __float_as_uint(v[8 * j + 6]),
-                                      __float_as_uint(v[8 * j + 7])));
+              st_async_v4(dst + chunk_off(j), make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                         __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])), dbar);
           }
+          // own quarter
+          float own[16];
+          __syncwarp();
+          tmem_ld_x16(tmem_base + s * BN + lane_addr + kq * (BN / KQ) + half * UPT, own);
+          ptx::tmem_ld_wait();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_leader(acc_empty_bar(s));
-          ptx::bar_sync(1, 128);
-          if (threadIdx.x == 64) {
-            red_release_u32(part_ready + (rt * kResMaxNT + nt) * kResFlagStride, 1u);
-            stamp(st, s, 5);
-          }
-        }
-      }
-      ptx::tc_fence_before();
-    } else {
-      // ---------------------------------------------------------- cell backward (warps 6..13) for this CTA's quarter of the
-      // tile's hidden units: thread = (row, 16 units); dc stays in registers for the whole sequence
-      constexpr int UPT = BN / KQ / 2;
-      static_assert(UPT == 16, "cell phase: 16 hidden units per thread");
-      const int pt = static_cast<int>(threadIdx.x) - 192;
-      const int row = pt & 127, half = pt >> 7;
-      const int u0 = nt * BN + kq * (BN / KQ) + half * UPT;
-      float dcst[2][UPT];
+          if (lane == 0) mbar_arrive_leader_relaxed(acc_empty_bar(s));
+          if (threadIdx.x == 64) stamp(st, s, 5);
+          // 2. sum the four K slices in ascending kq order
+          mbar_wait_cluster(recv_full_bar, item & 1);
+          if (threadIdx.x == 64) stamp(st, s, 6);
 #pragma unroll
-      for (int s = 0; s < 2; ++s)
+          for (int k = 0; k < KQ; ++k) {
+            if (k == kq) {
 #pragma unroll
-        for (int i = 0; i < UPT; ++i) dcst[s][i] = 0.f;
-      for (int st = 0; st < T; ++st) {
-        const int t = T - 1 - st;
+              for (int i = 0; i < 16; ++i) dh[i] += own[i];
+            } else {
+              const int slot = k < kq ? k : k - 1;
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int rt = row_tile(s);
-          const long m = static_cast<long>(p.row0) + rt * 128 + row;
-          const AT* gp = gates + m * ldx + static_cast<long>(t) * 4 * H + 4 * u0;
-          const float* cp = p.c_all + m * ldc + static_cast<long>(t) * H + u0;
-          const AT* dp = dh_all + m * ldc + static_cast<long>(t) * H + u0;
-          AT* dap = da_all + m * ldx + static_cast<long>(t) * 4 * H + u0;
-          if (t > 0) {   // what this slot reads at the next step: HBM -> L2 now
-            prefetch_l2_line(gp - 4 * H);
-            prefetch_l2_line(dp - H);
-            if (t > 1) prefetch_l2_line(cp - 2 * H);
-          }
-          if (st > 0) {
-            if (lane == 0) wait_counter(part_ready + (rt * kResMaxNT + nt) * kResFlagStride, static_cast<unsigned int>(KQ) * st);
-            __syncwarp();
-          }
-          if (pt == 0) stamp(st, s, 6);
-          uint4 dalo[4];
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            float g4[32], cc[8], cpv[8], dh[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) Act8<AT>::load(gp + 32 * ch + 8 * j, g4 + 8 * j);
-            Act8<float>::load(cp + 8 * ch, cc);
-            if (t > 0) Act8<float>::load(cp - H + 8 * ch, cpv);
-            else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) cpv[i] = 0.f;
-            }
-            Act8<AT>::load(dp + 8 * ch, dh);
-            if (st > 0) {
-#pragma unroll
-              for (int k = 0; k < KQ; ++k) {   // fixed order: deterministic sums
-                const float4* pp = reinterpret_cast<const float4*>(p.part + (static_cast<long>(k) * p.rows + m) * H + u0 + 8 * ch);
-                const float4 v0 = __ldcg(pp), v1 = __ldcg(pp + 1);
-                dh[0] += v0.x; dh[1] += v0.y; dh[2] += v0.z; dh[3] += v0.w;
-                dh[4] += v1.x; dh[5] += v1.y; dh[6] += v1.z; dh[7] += v1.w;
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = ptx::ld_shared_v4(recv + slot * 16384 + chunk_off(j));
+                dh[4 * j] += __uint_as_float(u.x); dh[4 * j + 1] += __uint_as_float(u.y);
+                dh[4 * j + 2] += __uint_as_float(u.z); dh[4 * j + 3] += __uint_as_float(u.w);
               }
             }
-            float da[4][8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float ig = g4[4 * i], fg = g4[4 * i + 1], gg = g4[4 * i + 2], og = g4[4 * i + 3];
-              const float tc = GateMath<AT>::tnh(cc[i]);
-              const float dht = dh[i];
-              const float dct = dcst[s][8 * ch + i] + dht * og * (1.f - tc * tc);
-              da[3][i] = dht * tc * og * (1.f - og);
-              da[0][i] = dct * gg * ig * (1.f - ig);
-              da[2][i] = dct * ig * (1.f - gg * gg);
-              da[1][i] = dct * cpv[i] * fg * (1.f - fg);
-              dcst[s][8 * ch + i] = dct * fg;
-            }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (ch == 0) dalo[g] = pack8_16<AT>(da[g]);
-              else st_global_v8(dap + g * H, dalo[g], pack8_16<AT>(da[g]));
-            }
           }
-          ptx::bar_sync(2, 256);
-          if (pt == 0) {
-            red_release_u32(ready + rt * kResFlagStride + my_kb, 1u);
-            stamp(st, s, 7);
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int r = 1; r < KQ; ++r)
+              mbar_arrive_remote(mapa_u32(send_ok_bar, static_cast<uint32_t>(((kq + r) & (KQ - 1)) * 2 + cr)));
           }
         }
+        // 3. cell backward
+        if (threadIdx.x == 64) stamp(st, s, 0);
+        float g4[4 * UPT], cc[UPT], cpv[UPT];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Act8<AT>::unpack(g_raw[j], g4 + 8 * j);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) Act8<float>::unpack(c_raw[j], cc + 8 * j);
+        if (t > 0) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) Act8<float>::unpack(cp_raw[j], cpv + 8 * j);
+        } else {
+#pragma unroll
+          for (int i = 0; i < UPT; ++i) cpv[i] = 0.f;
+        }
+        AT* dap = da_all + m * ldx + static_cast<long>(t) * 4 * H + u0;
+        if (threadIdx.x == 64 && p.stamps != nullptr) {
+          float acc = 0.f;
+          for (int i = 0; i < 4 * UPT; ++i) acc += g4[i];
+          for (int i = 0; i < UPT; ++i) acc += cc[i] + cpv[i] + dh[i];
+          if (acc == 123.456f) printf("x");
+          stamp(st, s, 1);
+        }
+        uint4 dalo[4];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          float da[4][8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int u = 8 * ch + i;
+            const float ig = g4[4 * u], fg = g4[4 * u + 1], gg = g4[4 * u + 2], og = g4[4 * u + 3];
+            const float tc = GateMath<AT>::tnh(cc[u]);
+            const float dht = dh[u];
+            const float dct = dcst[s][u] + dht * og * (1.f - tc * tc);
+            da[3][i] = dht * tc * og * (1.f - og);
+            da[0][i] = dct * gg * ig * (1.f - ig);
+            da[2][i] = dct * ig * (1.f - gg * gg);
+            da[1][i] = dct * cpv[u] * fg * (1.f - fg);
+            dcst[s][u] = dct * fg;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (ch == 0) dalo[g] = pack8_16<AT>(da[g]);
+            else st_global_v8(dap + g * H, dalo[g], pack8_16<AT>(da[g]));
+          }
+        }
+        if (threadIdx.x == 64) stamp(st, s, 2);
+        ptx::bar_arrive(2, kResBarThreads);   // da_t of this tile is stored: the agent publishes it
+        if (s == 0) request(st, 1);
+        else if (st + 1 < T) request(st + 1, 0);
       }
+    }
+    ptx::tc_fence_before();
     }
   }
   ptx::cluster_sync();   // the leader's MMAs / commits touch the peer: nobody leaves before both are done
@@ -617,8 +744,6 @@ static int res_launch(ResParams& p, int rows_l, cudaStream_t st) {
     DVAE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     configured = true;
   }
-  if (int e = res_flag_slot(&p.flags, st)) return e;
-  p.stamps = g_res_stamps;
   const int groups = rows_l / 512;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * Cfg::NS * groups);
@@ -627,13 +752,40 @@ static int res_launch(ResParams& p, int rows_l, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = BWD ? 2 * kResKQ : 2;   // backward: the KQ pairs of a tile exchange partial sums through DSMEM
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // every CTA waits for others of the same launch: the whole grid has to be co-resident (clusters of 8 need 8 free SMs of
+  // one GPC each).  Ask the driver once per kernel; a launch that does not fit is refused, never attempted.
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    cudaLaunchConfig_t probe = cfg;
+    probe.gridDim = dim3(2 * Cfg::NS * (kResMaxRowTiles * 128 / 512));
+    int n = 0;
+    DVAE_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &probe));
+    max_clusters = n;
+    if (res_env_int("DVAE_RES_VERBOSE", 0)) fprintf(stderr, "dvae_b200: resident LSTM kernel (bwd=%d, H=%d): max active clusters %d, smem %d\n", (int)BWD, H, n, Cfg::SMEM);
+  }
+  if (static_cast<int>(cfg.gridDim.x / attr[0].val.clusterDim.x) > max_clusters) {
+    set_last_error("resident LSTM: the device cannot hold " + std::to_string(cfg.gridDim.x / attr[0].val.clusterDim.x) +
+                   " clusters of this kernel at once (max " + std::to_string(max_clusters) + ")");
+    return 3;
+  }
+  if (int e = res_flag_slot(&p.flags, st)) return e;
+  p.stamps = g_res_stamps;
   DVAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   return 0;
+}
+
+// W_hh [4H][H] -> W_hh^T [H][4H] (16-bit elements): the backward's B operand, K-major like the forward's
+__global__ void __launch_bounds__(256) res_transpose16_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int R, int C) {
+  __shared__ uint16_t tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) tile[i][threadIdx.x] = src[static_cast<long>(r0 + i) * C + c0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) dst[static_cast<long>(c0 + i) * R + r0 + threadIdx.x] = tile[threadIdx.x][i];
 }
 
 // rows per launch: all CTAs of a launch must be co-resident (they wait for each other)
@@ -666,18 +818,21 @@ static int lstm_res_fwd_t(AT* xg, const AT* whh_p, AT* h_all, float* c_all, int 
 }
 
 template <typename AT, int H>
-static int lstm_res_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, const AT* whh_n, AT* da_all, float* part, int rows,
+static int lstm_res_bwd_t(const AT* dh_all, const AT* gates, const float* c_all, const AT* whh_n, AT* da_all, float* scratch, int rows,
                           int T, cudaStream_t st) {
   constexpr int BN = 128;
   using Cfg = ResCfg<AT, H, BN, true>;
   ResParams p{};
   if (int e = encode_map3(&p.tmA, da_all, 2, 4 * H, T, rows, (uint64_t)4 * H * 2, (uint64_t)T * 4 * H * 2, 64, 1, 128)) return e;
-  if (int e = encode_map3(&p.tmW, whh_n, 2, H, 4 * H, 1, (uint64_t)H * 2, (uint64_t)4 * H * H * 2, 64, 64, 1, true)) return e;
+  AT* whh_t = reinterpret_cast<AT*>(scratch);   // [H][4H]
+  res_transpose16_kernel<<<dim3(H / 32, 4 * H / 32), dim3(32, 8), 0, st>>>(reinterpret_cast<const uint16_t*>(whh_n),
+                                                                         reinterpret_cast<uint16_t*>(whh_t), 4 * H, H);
+  DVAE_CHECK_CUDA(cudaGetLastError());
+  if (int e = encode_map3(&p.tmW, whh_t, 2, 4 * H, H, 1, (uint64_t)4 * H * 2, (uint64_t)4 * H * H * 2, 64, 64, 1)) return e;
   p.xg = const_cast<AT*>(gates);
   p.h_all = da_all;
   p.c_all = const_cast<float*>(c_all);
   p.dh_all = dh_all;
-  p.part = part;
   p.rows = rows;
   p.T = T;
   const int per = res_rows_per_launch<Cfg::NS>();
@@ -700,13 +855,13 @@ int lstm_res_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_a
                    : lstm_res_fwd_t<AT, 512, 64>((AT*)xg, (const AT*)whh_p, (AT*)h_all, c_all, rows, T, st);
 }
 
-// floats of scratch (partial sums of the K slices) the resident backward wants
-long lstm_res_bwd_scratch_floats(int rows, int H) { return static_cast<long>(kResKQ) * rows * H; }
+// floats of scratch the resident backward wants: the transposed weight copy [H][4H] of 16-bit elements
+long lstm_res_bwd_scratch_floats(int /*rows*/, int H) { return 2L * H * H; }
 
 int lstm_res_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all, float* part,
                  int rows, int T, int H, cudaStream_t st) {
   if (part == nullptr) {
-    set_last_error("resident LSTM backward needs its partial-sum scratch (dvae_lstm_bwd_workspace)");
+    set_last_error("resident LSTM backward needs its scratch buffer (dvae_lstm_bwd_workspace)");
     return 1;
   }
   if (dtype == kF16) {

@@ -88,9 +88,55 @@ class PreparedWeights:
             self.lstm[prefix] = dict(layers=per_layer, D=D, H=H)
         self.refresh(P)
 
+    def _table(self, P: Dict[str, Tensor]):
+        """The refresh as a table for ops.PrepTable: one descriptor per fp32 source tensor."""
+        E = []
+        for conv in self._convs:
+            w = P[conv + ".weight"]
+            cat = self.conv0_cat if (self.split and conv == ENC_CONVS[0][0]) else None
+            E.append((ops.PREP_CONV, w, None, self.conv[conv], cat, w.shape[0], w.shape[1]))
+        for name in self._linears:
+            w = P[name + ".weight"]
+            sp = self.enc_linear_split if (self.split and name == "enc_linear.linear_layer") else None
+            E.append((ops.PREP_CAST, w, None, self.lin[name], sp, 2, w.shape[1]))
+        if self.split and "enc_linear.linear_layer" not in self._linears:
+            return None
+        if self._fused_heads:
+            n_s = self.n_style
+            for w, b, rows in ((P["style.linear_layer.weight"], P["style.linear_layer.bias"], slice(0, n_s)),
+                               (P["content.linear_layer.weight"], P["content.linear_layer.bias"], slice(n_s, None))):
+                E.append((ops.PREP_CAST, w, None, self.heads_w[rows], self.heads_w3[rows] if self.split else None, 3, w.shape[1]))
+                E.append((ops.PREP_COPY, b, None, self.heads_b[rows], None, 0, 0))
+        for prefix, info in self.lstm.items():
+            D, H = info["D"], info["H"]
+            for l, lw in enumerate(info["layers"]):
+                for d in range(D):
+                    suf = "_reverse" if d == 1 else ""
+                    sl = slice(d * 4 * H, (d + 1) * 4 * H)
+                    w_ih, w_hh = P[f"{prefix}.weight_ih_l{l}{suf}"], P[f"{prefix}.weight_hh_l{l}{suf}"]
+                    E.append((ops.PREP_LSTM_W, w_ih, None, lw["wih_n"][sl], lw["wih_p"][sl], H, w_ih.shape[1]))
+                    E.append((ops.PREP_LSTM_W, w_hh, None, lw["whh_n"][d], lw["whh_p"][d], H, H))
+                    E.append((ops.PREP_LSTM_BIAS, P[f"{prefix}.bias_ih_l{l}{suf}"], P[f"{prefix}.bias_hh_l{l}{suf}"], lw["bias_p"][sl],
+                              None, H, 0))
+        if not all(e[1].is_contiguous() and e[3].is_contiguous() for e in E):
+            return None
+        return E
+
     def refresh(self, P: Dict[str, Tensor]) -> None:
-        """Re-derive every tensor-core copy from the fp32 masters, in place (after an optimizer step / load_state_dict)."""
+        """Re-derive every tensor-core copy from the fp32 masters, in place (after an optimizer step / load_state_dict).
+        One launch (dvae_prep_all, driven by a table that is rebuilt only when a tensor has moved); DVAE_B200_PREP_ALL=0 or the
+        strict-fp32 mode keep the tensor-by-tensor path (~55 launches), which the table path is tested against bit for bit."""
         dt = self.dt
+        if dt in (lib.BF16, lib.F16, lib.TF32) and os.environ.get("DVAE_B200_PREP_ALL", "1") == "1":
+            tab = getattr(self, "_prep_table", None)
+            if tab is None or not tab.valid() or self._prep_params != tuple(P[k].data_ptr() for k in sorted(P)):
+                E = self._table(P)
+                tab = ops.PrepTable(dt, E, next(iter(P.values())).device) if E is not None else False
+                self._prep_table = tab
+                self._prep_params = tuple(P[k].data_ptr() for k in sorted(P))
+            if tab:
+                tab.run()
+                return
         for conv in self._convs:
             cat = self.conv0_cat if (self.split and conv == ENC_CONVS[0][0]) else None
             ops.prep_conv_weight(dt, P[conv + ".weight"], out=self.conv[conv], out_cat=cat)

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "dvae_add_f32_act": [_i, _p, _p, _p, _l, _p],
     "dvae_prep_conv_weight": [_i, _p, _p, _p, _i, _i, _p],
     "dvae_prep_cast_split": [_i, _p, _p, _l, _l, _i, _p],
+    "dvae_prep_all": [_i, _p, _p, _p, _i, _i, _p],
     "dvae_conv_wgrad_unpack": [_p, _p, _i, _i, _p],
     "dvae_prep_lstm_weight": [_i, _p, _p, _i, _i, _i, _p],
     "dvae_prep_lstm_bias": [_p, _p, _p, _i, _i, _p],

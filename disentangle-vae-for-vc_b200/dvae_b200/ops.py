@@ -218,6 +218,42 @@ def prep_cast(dt: int, src: Tensor, dst: Tensor, scale: float = 1.0) -> None:
     call("dvae_prep_cast", dt, ptr(src), ptr(dst), src.numel(), float(scale), stream())
 
 
+PREP_CAST, PREP_CONV, PREP_LSTM_W, PREP_COPY, PREP_LSTM_BIAS = 0, 1, 2, 3, 4   # PrepKind of csrc/ops_pointwise.cu
+
+
+class PrepTable:
+    """Device-side table for dvae_prep_all: every tensor-core copy of the parameters re-derived in ONE launch.
+    entries: (kind, src, src2, dst0, dst1, d0, d1) with fp32 sources; built once, valid while the tensors stay where they are."""
+
+    CHUNK = 8192
+
+    def __init__(self, dt: int, entries, device):
+        import struct
+        self.dt = dt
+        self.keep = entries                      # keeps the tensors alive
+        self.ptrs = tuple(t.data_ptr() for e in entries for t in e[1:5] if t is not None)
+        raw = bytearray()
+        blk_desc, blk_off = [], []
+        for i, (kind, src, src2, dst0, dst1, d0, d1) in enumerate(entries):
+            _chk(src, torch.float32)
+            n = src.numel()
+            raw += struct.pack("<QQQQqiiii", ptr(src), ptr(src2) or 0, ptr(dst0), ptr(dst1) or 0, n, kind, d0, d1, 0)
+            for off in range(0, n, self.CHUNK):
+                blk_desc.append(i)
+                blk_off.append(off)
+        assert len(raw) == 56 * len(entries)
+        self.descs = torch.frombuffer(raw, dtype=torch.uint8).to(device)
+        self.blk_desc = torch.tensor(blk_desc, dtype=torch.int32, device=device)
+        self.blk_off = torch.tensor(blk_off, dtype=torch.int64, device=device)
+        self.nblocks = len(blk_desc)
+
+    def valid(self) -> bool:
+        return self.ptrs == tuple(t.data_ptr() for e in self.keep for t in e[1:5] if t is not None)
+
+    def run(self) -> None:
+        call("dvae_prep_all", self.dt, ptr(self.descs), ptr(self.blk_desc), ptr(self.blk_off), self.nblocks, self.CHUNK, stream())
+
+
 def add_f32_act(dt: int, a: Tensor, b: Tensor) -> Tensor:
     """fp32 out = a (fp32) + b (activation dtype), same shape."""
     _chk(a, torch.float32), _chk(b, act_dtype(dt))

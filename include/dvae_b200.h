@@ -82,6 +82,10 @@ int dvae_add_inplace(int dtype, void* a, const void* b, long n, void* stream);
 int dvae_add_f32_act(int dtype, const float* a, const void* b, float* out, long n, void* stream);  /* residual, channels-last */
 int dvae_prep_conv_weight(int dtype, const float* w, void* wk, void* wk_cat, int Co, int Ci, void* stream);   /* wk_cat (may be null): [Co,5,3Ci] = [hi | hi | lo] */
 int dvae_prep_cast_split(int dtype, const float* src, void* dst, long rows, long K, int parts, void* stream);   /* [hi | lo] or [hi | hi | lo] per row */
+/* every tensor-core copy of the parameters in ONE launch (engine.PreparedWeights.refresh): descs = device array of 56-byte
+ * descriptors {const float* src, src2; void* dst0, dst1; int64 n; int32 kind, d0, d1, pad} (kinds: csrc/ops_pointwise.cu PrepKind),
+ * blk_desc / blk_off = per block the descriptor index and the first source element of its chunk of `chunk` elements */
+int dvae_prep_all(int dtype, const void* descs, const int* blk_desc, const long* blk_off, int num_blocks, int chunk, void* stream);
 int dvae_conv_wgrad_unpack(const float* dwk, float* dw, int Co, int Ci, void* stream);
 int dvae_prep_lstm_weight(int dtype, const float* w, void* dst, int H, int In, int tile, void* stream);
 int dvae_prep_lstm_bias(const float* b_ih, const float* b_hh, float* dst, int H, int tile, void* stream);

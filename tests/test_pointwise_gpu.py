@@ -312,3 +312,39 @@ def test_fused_adam_skips_and_reports_non_finite_gradients():
     assert calls == [1] and our.overflow_steps == 1
     our.step()
     assert calls == [1]                                  # a clean step does not report again
+
+
+@pytest.mark.parametrize("name", ["fp16", "bf16", "tf32"])
+def test_one_launch_weight_refresh_matches_tensor_by_tensor(name, monkeypatch):
+    """engine.PreparedWeights.refresh: the table-driven single launch (dvae_prep_all) against the ~55 per-tensor launches,
+    bit for bit, on every tensor-core copy of the DisentangledVAE parameters (split-precision copies of the fp16 mode included)."""
+    from dvae_b200 import lib
+    from dvae_b200.engine import PreparedWeights
+    from model.disentangled_vae import DisentangledVAE
+    torch.manual_seed(3)
+    net = DisentangledVAE(speaker_size=4, latent_dim=32, batch_size=8).cuda()
+    P0 = {k: v.detach().clone() for k, v in net.named_parameters()}
+    dt = {"fp16": lib.F16, "bf16": lib.BF16, "tf32": lib.TF32}[name]
+    got = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DVAE_B200_PREP_ALL", mode)
+        P = {k: v.clone() for k, v in P0.items()}
+        pw = PreparedWeights(dt, P)
+        assert bool(getattr(pw, "_prep_table", None)) == (mode == "1"), "wrong refresh path engaged"
+        for k in P:                           # a second refresh after the parameters moved (as after an optimizer step)
+            P[k].mul_(1.01)
+        pw.refresh(P)
+        t = dict(("conv." + k, v) for k, v in pw.conv.items())
+        t.update(("lin." + k, v) for k, v in pw.lin.items())
+        t["heads_w"], t["heads_b"] = pw.heads_w, pw.heads_b
+        if pw.split:
+            t["conv0_cat"], t["enc_linear_split"], t["heads_w3"] = pw.conv0_cat, pw.enc_linear_split, pw.heads_w3
+        for prefix, info in pw.lstm.items():
+            for l, lw in enumerate(info["layers"]):
+                for kk in ("wih_p", "wih_n", "whh_p", "whh_n", "bias_p"):
+                    t[f"{prefix}.{l}.{kk}"] = lw[kk]
+        got[mode] = {k: v.clone() for k, v in t.items()}
+    torch.cuda.synchronize()
+    assert got["0"].keys() == got["1"].keys()
+    for k in got["0"]:
+        assert torch.equal(got["0"][k], got["1"][k]), f"{name}: {k} differs between the two refresh paths"
