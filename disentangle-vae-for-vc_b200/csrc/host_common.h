@@ -60,16 +60,13 @@ int lstm_seq_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_a
 int lstm_seq_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all,
                  int rows, int T, int H, int D, cudaStream_t st);
 
-// Weight-stationary, time-resident recurrence for H = 512 / 1024 (ops_lstm_res.cu): one launch per layer and pass, CTA
-// pairs keep their slice of W_hh in shared memory and hand h_t / da_t to each other through L2.
+// Weight-stationary, time-resident forward recurrence for H = 512 / 1024 (ops_lstm_res.cu): one launch per layer, CTA pairs
+// keep their slice of W_hh in shared memory and hand h_t to each other through L2.  lstm_res_fwd returns 3 when the grid
+// cannot be co-resident on this device (the caller then takes the step-per-launch kernels).
 bool lstm_res_supported(int dtype, int rows, int T, int H, int D);
-bool lstm_res_shape_ok(int dtype, int rows, int T, int H, int D);   // same, ignoring the on / off switch
 void lstm_res_set_stamps(unsigned long long* buf);
 int lstm_res_set_enabled(int on);   // on < 0: query only; returns the previous setting
 int lstm_res_fwd(int dtype, void* xg, const void* whh_p, void* h_all, float* c_all, int rows, int T, int H, cudaStream_t st);
-long lstm_res_bwd_scratch_floats(int rows, int H);
-int lstm_res_bwd(int dtype, const void* dh_all, const void* gates, const float* c_all, const void* whh_n, void* da_all, float* part,
-                 int rows, int T, int H, cudaStream_t st);
 
 // Strict-fp32 mode (ops_simt.cu): CUDA-core fp32 implementations of every contraction, same index conventions as the
 // tensor-core launchers

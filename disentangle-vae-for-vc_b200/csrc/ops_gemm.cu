@@ -1063,11 +1063,6 @@ int dvae_lstm_bwd(int dtype, const void* dh_all, const void* gates, const float*
   auto st = static_cast<cudaStream_t>(stream);
   if (dtype == kF32) return simt_lstm_bwd((const float*)dh_all, (const float*)gates, c_all, (const float*)whh_n, (float*)da_all, dc_ws, rows, T, H, D, st);
   if (lstm_seq_supported(H, T)) return lstm_seq_bwd(dtype, dh_all, gates, c_all, whh_n, da_all, rows, T, H, D, st);
-  static const int res_bwd = env_int("DVAE_LSTM_RES_BWD", 0);
-  if (res_bwd && lstm_res_supported(dtype, rows, T, H, D)) {
-    const int e = lstm_res_bwd(dtype, dh_all, gates, c_all, whh_n, da_all, splitk_ws, rows, T, H, st);
-    if (e != 3) return e;
-  }
   DISPATCH_AT(dtype, lstm_bwd_t<AT>((const AT*)dh_all, (const AT*)gates, c_all, (const AT*)whh_n, (AT*)da_all, dc_ws, splitk_ws,
                                     tickets, rows, T, H, D, st));
 }
@@ -1079,8 +1074,6 @@ int dvae_lstm_bwd_workspace(int dtype, int rows, int H, int D, long* ws_floats, 
   const int splits = lstm_bwd_splits(rows, H, D, eb);
   *num_tickets = tiles;
   *ws_floats = splits > 1 ? static_cast<long>(tiles) * splits * 128 * bn : 0;
-  // the resident kernel (ops_lstm_res.cu) parks the partial sums of its K slices here (T is not known to this query)
-  if (lstm_res_shape_ok(dtype, rows, 64, H, D)) *ws_floats = std::max(*ws_floats, lstm_res_bwd_scratch_floats(rows, H));
   return 0;
 }
 
@@ -1100,16 +1093,13 @@ int dvae_lstm_launches(int H, int T, int backward) {
   return backward ? (fused ? T : 2 * T - 1) : T;
 }
 
-// same, for the exact call: dvae_lstm_fwd / dvae_lstm_bwd pick the time-resident kernels (one launch per 1024 rows) when
-// the shape allows it
+// same, for the exact call: dvae_lstm_fwd picks the time-resident kernel (one launch per 1024 rows) when the shape allows it
 int dvae_lstm_launches_for(int dtype, int rows, int T, int H, int D, int backward) {
-  static const int res_bwd = env_int("DVAE_LSTM_RES_BWD", 0);
-  if (dtype != kF32 && !lstm_seq_supported(H, T) && lstm_res_supported(dtype, rows, T, H, D) && (!backward || res_bwd))
-    return ceil_div(rows, 1024);
+  if (!backward && dtype != kF32 && !lstm_seq_supported(H, T) && lstm_res_supported(dtype, rows, T, H, D)) return ceil_div(rows, 1024);
   return dvae_lstm_launches(H, T, backward);
 }
 
-// 1 / 0: use / do not use the time-resident kernels of ops_lstm_res.cu for the H = 512 / 1024 recurrences (default 1, or
+// 1 / 0: use / do not use the time-resident kernel of ops_lstm_res.cu for the H = 512 / 1024 forward recurrences (default 1, or
 // DVAE_LSTM_RES); a negative value only queries.  Returns the previous setting.
 int dvae_set_lstm_resident(int on) { return lstm_res_set_enabled(on); }
 

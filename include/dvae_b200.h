@@ -31,9 +31,9 @@ int dvae_sm_arch(void);              /* 100: built for sm_100a only */
 int dvae_lstm_gate_tile(int H);
 int dvae_debug_seq_stamps(long long* buf);   /* optional per-step SM-clock stamps [T][8] of the sequence-resident LSTM kernels (debug) */
 int dvae_lstm_launches(int H, int T, int backward);   /* kernels dvae_lstm_fwd / dvae_lstm_bwd enqueue for this shape */
-int dvae_lstm_launches_for(int dtype, int rows, int T, int H, int D, int backward);   /* same, for the exact call (time-resident kernels: one launch per 1024 rows) */
+int dvae_lstm_launches_for(int dtype, int rows, int T, int H, int D, int backward);   /* same, for the exact call (time-resident forward kernel: one launch per 1024 rows) */
 int dvae_debug_res_stamps(unsigned long long* buf);   /* optional globaltimer stamps [T][2][8] of CTA 0 of the time-resident LSTM kernels (debug) */
-int dvae_set_lstm_resident(int on);   /* 1 / 0: time-resident kernels for the H = 512 / 1024 recurrences (ops_lstm_res.cu) on / off; < 0 queries; returns the previous setting */
+int dvae_set_lstm_resident(int on);   /* 1 / 0: time-resident forward kernel for the H = 512 / 1024 recurrences (ops_lstm_res.cu) on / off; < 0 queries; returns the previous setting */
 int dvae_set_background(int on);   /* GEMMs launched while on: small-footprint kernels that co-run with a latency-critical stream */
 int dvae_debug_timing(unsigned long long* buf, int capacity);   /* optional per-CTA phase stamps of the GEMM kernel (debug) */      /* gate-interleave tile (columns) used by the LSTM forward for hidden size H */
 

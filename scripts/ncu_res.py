@@ -1,4 +1,4 @@
-"""One forward and one backward launch of the time-resident LSTM kernels at H = 1024, rows = 1024 (for ncu)."""
+"""One forward (time-resident kernel) and one backward (step-per-launch kernels) of an LSTM layer at rows = 1024 (for ncu)."""
 import os
 import sys
 

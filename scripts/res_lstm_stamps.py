@@ -1,5 +1,5 @@
-"""Per-step phase stamps of CTA 0 of the time-resident LSTM kernels (csrc/ops_lstm_res.cu): where a step's chain goes.
-`python scripts/res_lstm_stamps.py [H] [fwd|bwd]`"""
+"""Per-step phase stamps of CTA 0 of the time-resident LSTM forward kernel (csrc/ops_lstm_res.cu): where a step's chain goes.
+`python scripts/res_lstm_stamps.py [H]`"""
 import os
 import sys
 
@@ -9,14 +9,14 @@ import torch
 from dvae_b200 import lib, ops
 
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-bwd = len(sys.argv) > 2 and sys.argv[2] == "bwd"
+bwd = False
 rows, T = 1024, 64
 dt, td = lib.F16, torch.float16
 xg0 = torch.randn(rows, T, 4 * H, device="cuda").to(td)
 whh = (torch.randn(1, 4 * H, H, device="cuda") / H ** 0.5).to(td)
 dh = (torch.randn(rows, T, H, device="cuda") * 0.1).to(td)
 buf = torch.zeros(T * 2 * 8, dtype=torch.int64, device="cuda")
-names = ["wait", "flag", "loads", "mma", "acc", "staged", "handback", "published"]
+names = ["wait", "first_kblock", "loads_issued", "mma_done", "acc_seen", "tile_done", "agent", "published"]
 for rep in range(2):
     xg = xg0.clone()
     if not bwd:

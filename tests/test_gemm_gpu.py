@@ -341,7 +341,6 @@ def test_lstm_resident_forward_is_bit_identical():
     {"DVAE_LSTM_PAIR": "1"},                                       # CTA-pair (cta_group::2) step kernels
     {"DVAE_LSTM_BWD_FUSED": "1"},                                  # cell backward fused into the step GEMM's epilogue
     {"DVAE_LSTM_RES": "0"},                                        # H = 512 / 1024 through the step-per-launch path at every size
-    {"DVAE_LSTM_RES_BWD": "1"},                                    # time-resident backward (measured slower; kept as an option)
 ], ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
 def test_lstm_optional_paths(env):
     """The kernel variants that are not the default (selected by environment variables read once per process) stay correct:
