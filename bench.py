@@ -497,6 +497,30 @@ def run_ours(args):
     fwd_bwd(x1, x2)
     opt_ms = timed(lambda: trainer.optimizer.step(), 5, 2) / 5
 
+    # ---- the same step replayed as ONE CUDA graph (dvae_b200.graph.GraphedTrainStep: weight refresh + forward + loss + backward;
+    # single GPU: the bucketed all-reduce is not captured).  Device time and the host time of a replay.
+    graph_info = None
+    if world == 1 and not args.lean:
+        try:
+            from dvae_b200.graph import GraphedTrainStep
+            model.noise_hook = dev_noise
+            gstep = GraphedTrainStep(trainer, x1, x2)
+            g_ms = timed(lambda: gstep(x1, x2), args.steps, 3) / args.steps
+            g_enq = []
+            for _ in range(3):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                gstep(x1, x2)
+                g_enq.append((time.perf_counter() - t0) * 1e3)
+            torch.cuda.synchronize(dev)
+            graph_info = {"ms_per_step": g_ms, "value": frames_per_step / (g_ms * 1e-3), "unit": UNIT,
+                          "host_ms_per_step": min(g_enq),
+                          "includes": "refresh of the tensor-core weight copies + fwd + loss + bwd as one graph launch; inputs and noise "
+                                      "copied into the graph's static tensors every step (device to device here)"}
+            del gstep
+        except Exception as e:   # reported, never fatal: the eager numbers above are the bench
+            graph_info = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -518,6 +542,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "gpu_launches_per_step": launches / args.steps,
         "host_enqueue_ms_per_step": host_enqueue_ms,
+        "cuda_graph_step": graph_info,
         "full_train_step": {"ms_per_step": full_ms, "value": world * frames_per_step / (full_ms * 1e-3), "unit": UNIT,
                             "includes": "fwd + loss + bwd + fused Adam (one launch) + refresh of the tensor-core weight copies"},
         "optimizer_ms": opt_ms,

@@ -63,6 +63,11 @@ class VariationalBaseModelVAE():
         """zero_grad -> forward -> loss -> backward -> optimizer; returns the 8 loss terms as Python floats.
         `speaker_ids` is accepted and unused, like the reference (the style group is the (x1, x2) pair: SURVEY F2).
         The 8 scalars come back in ONE device->host copy instead of eight `.item()` syncs."""
+        g = self._graphed_step(data1, data2) if train else None
+        if g is not None:
+            vals = g(data1, data2)
+            self.optimizer.step()
+            return tuple(vals.tolist())
         if train:
             self.optimizer.zero_grad()
         out = self.model(data1, data2)
@@ -71,6 +76,29 @@ class VariationalBaseModelVAE():
             losses[0].backward()
             self.optimizer.step()
         return tuple(torch.stack([l.detach() for l in losses]).tolist())
+
+    def _graphed_step(self, data1, data2):
+        """CUDA-graph replay of forward + loss + backward (dvae_b200.graph.GraphedTrainStep) when it has been asked for
+        (`self.cuda_graph = True` or DVAE_B200_GRAPH=1), the model trains on one GPU and the batch has the captured shape; the
+        first two steps of a shape run eagerly (they create the optimizer state and learn the gradient-buffer layout)."""
+        import os
+        if not (getattr(self, "cuda_graph", False) or os.environ.get("DVAE_B200_GRAPH", "0") == "1"):
+            return None
+        if not (self.model.training and data1.is_cuda) or getattr(self.model._engine, "buckets", None) is not None:
+            return None
+        key = (tuple(data1.shape), tuple(data2.shape))
+        st = self.__dict__.setdefault("_graph_state", {})
+        ent = st.get(key)
+        if ent is None:
+            st[key] = 1            # eager steps seen with this shape
+            return None
+        if isinstance(ent, int):
+            if ent < 2:
+                st[key] = ent + 1
+                return None
+            from dvae_b200.graph import GraphedTrainStep
+            ent = st[key] = GraphedTrainStep(self, data1, data2)
+        return ent
 
     def train(self, train_loader, epoch, logging_func=print):
         """One epoch (:74-101).  Returns the reference's 7-tuple of summed loss terms.
@@ -91,6 +119,12 @@ class VariationalBaseModelVAE():
                 tot = [a + b for a, b in zip(tot, vals)]
                 last_style_kl = vals[7]
         for batch_idx, (data1, data2, speaker_ids) in enumerate(tqdm(DevicePrefetcher(train_loader, dev))):
+            g = self._graphed_step(data1, data2)
+            if g is not None:
+                vals = g(data1, data2)
+                self.optimizer.step()
+                account(scalars.push(vals))
+                continue
             self.optimizer.zero_grad()
             out = self.model(data1, data2)
             losses = self.loss_functionGVAE2(data1, data2, *out, train=True)

@@ -15,6 +15,8 @@ then have cosine > 0.999 (tf32) / > 0.96 per tensor and > 0.997 over all paramet
 gradients; PyTorch's bf16 autocast of the oracle is at 0.94 / 0.99 with free decisions)."""
 import os
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -398,3 +400,57 @@ def test_config2_step_against_oracle(name):
         assert v <= (l_tol if i < 5 else kl_tol), f"loss term {i}: rel {v:.3e}"
     assert mm > c_min and mg > c_glob, f"matched decisions: min {mm} ({mk}), global {mg}"
     assert fm > f_min and fg > f_glob, f"free decisions: min {fm} ({fk}), global {fg}"
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """dvae_b200.graph.GraphedTrainStep (weight refresh + forward + loss + backward as one CUDA-graph launch; optimizer outside)
+    against the eager step AT THE SAME PARAMETERS, on the same inputs and noise, across optimizer steps (a graph that kept using
+    the weights it was captured with would show up at the second comparison): same loss terms, same gradients up to the order of
+    the fp32 atomics inside the weight-gradient kernels.  Then the opt-in path of `step()` / `train()`: it engages after two
+    eager steps of a shape and BatchNorm's step counters count real steps only (not the capture's warm-up pass)."""
+    from dvae_b200.graph import GraphedTrainStep
+    from model.disentangled_vae import ConvolutionalMulVAE
+    R = 8
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xs = [(torch.rand(R, 80, 64, device="cuda", generator=g), torch.rand(R, 80, 64, device="cuda", generator=g)) for _ in range(5)]
+    noise = [torch.randn(R, 28, device="cuda", generator=g), torch.randn(R, 28, device="cuda", generator=g), torch.randn(R, 4, device="cuda", generator=g)]
+    torch.manual_seed(11)
+    w = ConvolutionalMulVAE("VCTK", 64, 80, 32, 1e-3, 0.01, 500, False, batch_size=R, speaker_size=4, latent_dim=32)
+    w.model.train()
+    k = [0]
+
+    def hook(shape):
+        k[0] += 1
+        return noise[(k[0] - 1) % 3]
+    w.model.noise_hook = hook
+    for x1, x2 in xs[:2]:
+        w.step(x1, x2, None, train=True)
+    gs = GraphedTrainStep(w, *xs[0])
+    params = dict(w.model.named_parameters())
+    for x1, x2 in xs[2:]:
+        for p in params.values():
+            p.grad = None
+        k[0] = 0
+        out = w.model(x1, x2)
+        le = w.loss_functionGVAE2(x1, x2, *out, train=True)
+        le[0].backward()
+        le = torch.stack([l.detach() for l in le]).clone()
+        ge = {n: p.grad.detach().clone() for n, p in params.items()}
+        k[0] = 0
+        lg = gs(x1, x2).clone()
+        assert torch.allclose(le, lg, rtol=2e-5, atol=1e-7), (le, lg)
+        for n, p in params.items():
+            a, b = ge[n], p.grad
+            if a.norm().item() > 0:
+                assert (a - b).norm().item() <= 2e-3 * a.norm().item(), n
+        w.optimizer.step()
+    # the opt-in path of the wrapper
+    torch.manual_seed(11)
+    w2 = ConvolutionalMulVAE("VCTK", 64, 80, 32, 1e-3, 0.01, 500, False, batch_size=R, speaker_size=4, latent_dim=32)
+    w2.model.train()
+    w2.cuda_graph = True
+    w2.model.noise_hook = hook
+    vals = [w2.step(x1, x2, None, train=True) for x1, x2 in xs]
+    assert any(not isinstance(v, int) for v in w2._graph_state.values()), "the graph path did not engage"
+    assert all(np.isfinite(v).all() for v in np.array(vals))
+    assert int(w2.model.state_dict()["postnet.convolutions.0.1.num_batches_tracked"].item()) == 2 * len(xs)
