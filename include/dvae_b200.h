@@ -28,14 +28,14 @@ const char* dvae_last_error(void);
 long dvae_workspace_bytes(const char* op, long n0, long n1, long n2);
 int dvae_version(void);
 int dvae_sm_arch(void);              /* 100: built for sm_100a only */
-int dvae_lstm_gate_tile(int H);
+int dvae_lstm_gate_tile(int H);   /* gate-interleave tile (columns) used by the LSTM forward for hidden size H */
 int dvae_debug_seq_stamps(long long* buf);   /* optional per-step SM-clock stamps [T][8] of the sequence-resident LSTM kernels (debug) */
 int dvae_lstm_launches(int H, int T, int backward);   /* kernels dvae_lstm_fwd / dvae_lstm_bwd enqueue for this shape */
 int dvae_lstm_launches_for(int dtype, int rows, int T, int H, int D, int backward);   /* same, for the exact call (time-resident forward kernel: one launch per 1024 rows) */
-int dvae_debug_res_stamps(unsigned long long* buf);   /* optional globaltimer stamps [T][2][8] of CTA 0 of the time-resident LSTM kernels (debug) */
+int dvae_debug_res_stamps(unsigned long long* buf);   /* optional globaltimer stamps [T][2][8] of CTA 0 of the time-resident LSTM forward kernel (debug) */
 int dvae_set_lstm_resident(int on);   /* 1 / 0: time-resident forward kernel for the H = 512 / 1024 recurrences (ops_lstm_res.cu) on / off; < 0 queries; returns the previous setting */
 int dvae_set_background(int on);   /* GEMMs launched while on: small-footprint kernels that co-run with a latency-critical stream */
-int dvae_debug_timing(unsigned long long* buf, int capacity);   /* optional per-CTA phase stamps of the GEMM kernel (debug) */      /* gate-interleave tile (columns) used by the LSTM forward for hidden size H */
+int dvae_debug_timing(unsigned long long* buf, int capacity);   /* optional per-CTA phase stamps of the GEMM kernel (debug) */
 
 /* ---- nn.Linear (model/disentangled_vae.py:98-100 LinearNorm.forward; :165-171, :194, :211-213, :232-233, :247) */
 int dvae_linear_fwd(int dtype, const void* x, long ldx, const void* w, const float* bias, void* out, float* out_f32,
