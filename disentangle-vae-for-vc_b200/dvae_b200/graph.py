@@ -18,7 +18,7 @@ Reference call sequence this replaces: `VariationalBaseModelVAE.step` (model/var
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import List
 
 import torch
 
@@ -94,12 +94,11 @@ class GraphedTrainStep:
         losses[0].backward()
         return out, losses
 
-    def matches(self, x1: torch.Tensor, x2: torch.Tensor) -> bool:
-        return (tuple(x1.shape), tuple(x2.shape)) == self.shape and x1.device == self.x1.device
-
     def __call__(self, x1: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
         """Runs the captured step on (x1, x2).  Returns the 8 loss terms as ONE device tensor (valid until the next call); the
         parameter gradients are in `p.grad` (overwritten, not accumulated); the model outputs of the step are `self.outputs`."""
+        if (tuple(x1.shape), tuple(x2.shape)) != self.shape:
+            raise ValueError(f"GraphedTrainStep was captured for shapes {self.shape}, got {tuple(x1.shape)}, {tuple(x2.shape)}")
         self.x1.copy_(x1, non_blocking=True)
         self.x2.copy_(x2, non_blocking=True)
         hook = self.model.noise_hook
