@@ -733,7 +733,7 @@ int dvae_add_inplace(int dtype, void* a, const void* b, long n, void* stream) {
 // which element offset its chunk of `chunk` source elements starts at.
 int dvae_prep_all(int dtype, const void* descs, const int* blk_desc, const long* blk_off, int num_blocks, int chunk, void* stream) {
   auto st = static_cast<cudaStream_t>(stream);
-  static_assert(sizeof(PrepDesc) == 56 || sizeof(PrepDesc) == 64, "descriptor layout");
+  static_assert(sizeof(PrepDesc) == 56, "descriptor layout: dvae_b200/ops.py PrepTable packs 56-byte records");
   if (num_blocks <= 0) return 0;
   DISPATCH_AT(dtype, prep_all_kernel<AT><<<num_blocks, 256, 0, st>>>(static_cast<const PrepDesc*>(descs), blk_desc, blk_off, chunk));
   DVAE_CHECK_CUDA(cudaGetLastError());

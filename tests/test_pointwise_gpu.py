@@ -334,6 +334,10 @@ def test_one_launch_weight_refresh_matches_tensor_by_tensor(name, monkeypatch):
         for k in P:                           # a second refresh after the parameters moved (as after an optimizer step)
             P[k].mul_(1.01)
         pw.refresh(P)
+        # a parameter that moved to other memory (e.g. .to() / a re-assigned .data): the table must notice and follow
+        moved = "dec_lstm2.weight_hh_l1"
+        P[moved] = P[moved].clone().mul_(0.5)
+        pw.refresh(P)
         t = dict(("conv." + k, v) for k, v in pw.conv.items())
         t.update(("lin." + k, v) for k, v in pw.lin.items())
         t["heads_w"], t["heads_b"] = pw.heads_w, pw.heads_b
