@@ -175,6 +175,40 @@ def test_training_trajectory_follows_oracle_adam(name):
 
 
 @pytest.mark.parametrize("name", DTS)
+@pytest.mark.parametrize("training", [False, True])
+def test_standalone_encode_decode_postnet(name, training):
+    """The three sub-calls the reference exposes next to forward() -- `encode(x)`, `decode(z)` and the `postnet` module
+    (model/disentangled_vae.py:198-248, :54-78; used under no_grad by the conversion code) -- each on its own against the oracle,
+    with batch statistics (train mode) and with running statistics (eval mode)."""
+    from oracle import dvae_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = False   # the checker runs in true fp32
+    torch.backends.cudnn.allow_tf32 = False
+    sd = O.synth_state_dict(0)
+    R = 6
+    x1, _, _ = O.synth_inputs(R)
+    w = _build(name, R, sd)
+    w.model.train(training)
+    osd = O.clone_sd(sd, device="cuda")
+    x = x1.cuda()
+    with torch.no_grad():
+        got = w.model.encode(x)
+        ref = O.encode(O.clone_sd(sd, device="cuda"), x, training)
+        for a, b in zip(got, ref):
+            assert (a.float() - b).norm().item() <= TENSOR_TOL[name] * b.norm().item() + 1e-6, (a.float() - b).norm().item() / b.norm().item()
+        z = torch.randn(R, 32, device="cuda", generator=torch.Generator(device="cuda").manual_seed(9)) * 0.5
+        rec = w.model.decode(z)
+        rec_ref = O.decode(O.clone_sd(sd, device="cuda"), z, training)
+        assert tuple(rec.shape) == (R, 80, 64)
+        rel = (rec.float() - rec_ref).norm().item() / rec_ref.norm().item()
+        assert rel <= 2 * TENSOR_TOL[name], f"decode rel {rel}"
+        post = w.model.postnet(rec_ref)
+        post_ref = O.postnet(osd, rec_ref, training)
+        assert tuple(post.shape) == tuple(post_ref.shape)
+        rel = (post.float() - post_ref).norm().item() / post_ref.norm().item()
+        assert rel <= HAT_TOL[name], f"postnet rel {rel}"
+
+
+@pytest.mark.parametrize("name", DTS)
 def test_eval_forward_and_conversion(name, golden_dir):
     from oracle import dvae_oracle as O
     from model.variational_base_vae import chunking_mel
