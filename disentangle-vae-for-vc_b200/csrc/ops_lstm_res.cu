@@ -26,10 +26,10 @@
 // 16-bit storage (fp16 / bf16) only, rows a multiple of 512, unidirectional; anything else (and DVAE_LSTM_RES=0) takes the
 // step-per-launch kernels.
 //
-// Measured (profiles/r02_lstm_resident.txt): 17.0 -> 12.7 us per step at H = 1024, 9.3 -> 7.6 at H = 512.  What bounds it now is
-// the issue rate of tcgen05.mma.cta_group::2 at N <= 128 (~65 ns per instruction whatever N; 128 instructions per pair and
-// step), not the hand-off chain.  Two resident BACKWARD designs were built, verified and dropped (same file, git history:
-// c50914d partial sums through L2, 92a8b57 clusters of 8 exchanging partial sums through DSMEM): both slower than the
+// Measured (profiles/r02_lstm_resident.txt): 17.0 -> 12.8 us per step at H = 1024, 9.3 -> 7.6 at H = 512.  What bounds it now is the
+// rate at which one SM pulls the recurrent operand through TMA (~60 GB/s: 0.27 us per 16 KB k-block whatever N is), then the
+// hand-off chain (release ~1.9 us + propagation ~2.8 us).  Two resident BACKWARD designs were built, verified and dropped (git
+// history: c50914d partial sums through L2, 92a8b57 clusters of 8 exchanging partial sums through DSMEM): both slower than the
 // step-per-launch backward; numbers in profiles/r02_negative_experiments.txt.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
